@@ -1,0 +1,84 @@
+// Shared device helpers for the xdb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XD_OK 0
+#define XD_ERR_ARG 1      // unsupported shape / alignment / null pointer
+#define XD_ERR_CUDA 2     // launch or driver error
+#define XD_ERR_TMAP 3     // cuTensorMapEncodeTiled failed
+
+#define XD_CHECK_ARG(cond) do { if (!(cond)) { xd_set_error(__FILE__, __LINE__, #cond); return XD_ERR_ARG; } } while (0)
+#define XD_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { xd_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); return XD_ERR_CUDA; } } while (0)
+
+void xd_set_error(const char* file, int line, const char* msg);
+
+enum { XD_F32 = 0, XD_BF16 = 1 };
+enum { XD_ACT_NONE = 0, XD_ACT_SILU = 1, XD_ACT_GELU_TANH = 2 };
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  == x * sigmoid(2u)
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return x / (1.0f + __expf(-2.0f * u));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == XD_ACT_SILU) return silu_f(v);
+    if (act == XD_ACT_GELU_TANH) return gelu_tanh_f(v);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 8 x bf16 <-> 8 x float through one 16-byte access
+struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+
+// Generic epilogue description shared by the tcgen05 and the SIMT GEMM/conv kernels:
+//   v = acc + bias[n];  v = act(v);  v *= gate[(m / gate_rows) * gate_ld + n];
+//   v += residual[m * res_ld + n];  out[m * out_ld + n] = v   (fp32 or bf16)
+struct Epilogue {
+    const float* bias;
+    const float* gate;
+    const void* residual;
+    void* out;
+    long long gate_ld, res_ld, out_ld;
+    int act, gate_rows, res_dtype, out_dtype;
+};
+
+__device__ __forceinline__ float epi_value(const Epilogue& e, float acc, long long m, int n) {
+    float v = acc;
+    if (e.bias) v += __ldg(e.bias + n);
+    v = apply_act(v, e.act);
+    if (e.gate) v *= __ldg(e.gate + (m / e.gate_rows) * e.gate_ld + n);
+    if (e.residual) {
+        if (e.res_dtype == XD_F32) v += ((const float*)e.residual)[m * e.res_ld + n];
+        else v += __bfloat162float(((const bf16*)e.residual)[m * e.res_ld + n]);
+    }
+    return v;
+}
+__device__ __forceinline__ void epi_store(const Epilogue& e, float v, long long m, int n) {
+    if (e.out_dtype == XD_F32) ((float*)e.out)[m * e.out_ld + n] = v;
+    else ((bf16*)e.out)[m * e.out_ld + n] = __float2bfloat16_rn(v);
+}
