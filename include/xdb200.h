@@ -1,0 +1,145 @@
+/* xdb200 -- C ABI of the B200-native (sm_100a) kernels behind the xdiffusion sampling hot path.
+ *
+ * The reference (Dwaynekj/xdiffusion) has no FFI: its hot path is PyTorch eager.  Each entry point
+ * below replaces the chain of ATen ops the reference dispatches at the cited file:line (paths
+ * relative to the reference root) and is what a binding for this path would bind
+ * (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions: raw DEVICE pointers + explicit sizes / leading dimensions (in ELEMENTS); the caller
+ * allocates every output and workspace (no cudaMalloc/free inside -> CUDA-graph capturable); no
+ * host synchronisation; `stream` is a cudaStream_t; returns 0 on success, otherwise an XD_ERR_*
+ * code with a message in xd_last_error().  bf16 = __nv_bfloat16.  dtype codes: 0 = fp32, 1 = bf16.
+ * Activations: 0 none, 1 SiLU, 2 GELU(tanh).
+ */
+#ifndef XDB200_H
+#define XDB200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XD_OK 0
+#define XD_ERR_ARG 1
+#define XD_ERR_CUDA 2
+#define XD_ERR_TMAP 3
+
+int xd_abi_version(void);
+const char* xd_last_error(void);
+
+/* ---- dense contractions on tcgen05 / TMEM, operands staged by TMA --------------------------- */
+
+/* out[m,n] = epilogue( sum_k A[m,k] Wt[n,k] + sum_k2 A2[m,k2] Wt[n,K+k2] )
+ *   epilogue: v += bias[n]; v = act(v); v *= gate[(m / gate_rows)*gate_ld + n];
+ *             v += residual[m*res_ld + n]; store as out_dtype.
+ * A, A2, Wt bf16 row-major; K, K2 multiples of 64; bias/gate fp32.  force_bn: 0 = auto, else 64/128/256.
+ * Replaces torch.nn.Linear / addmm (score_networks/dit.py:26-40,63-68; layers/attention.py:343-347;
+ * layers/mlp.py:30-38; layers/embedding.py:89-94,328-332; layers/resnet.py:143-149), Conv1d k=1
+ * (layers/attention.py:75,97) and Conv2d 1x1 (layers/resnet.py:168-170), with the adaLN gate +
+ * residual (dit.py:46-51) and GELU-tanh (mlp.py:41-42) fused into the epilogue. */
+int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                    long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                    int gate_rows, long long gate_ld, const void* residual, int res_dtype, long long res_ld,
+                    void* out, int out_dtype, long long out_ld, int force_bn, void* stream);
+
+/* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC bf16 (pixel stride ldx), packed weights
+ * Wp[Cout][9*C + Cs] (tap-major, then channel; then the optional 1x1 skip weights over Xs).
+ * Replaces Conv2d 3x3 (layers/resnet.py:129,155-157; score_networks/unet.py:107-114) and Conv3d
+ * (1,3,3) with frames folded into nimg (layers/resnet_3d.py:150-157,199-207); the resblock's
+ * `skip_connection(x) + h` (layers/resnet.py:161-170,201) is the second K segment / the residual. */
+int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                       long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                       const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                       long long out_ld, int force_bn, void* stream);
+
+/* CUDA-core twins with the identical contract (on-device cross-check; K not a multiple of 64). */
+int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                      long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                      int gate_rows, long long gate_ld, const void* residual, int res_dtype, long long res_ld,
+                      void* out, int out_dtype, long long out_ld, void* stream);
+int xd_conv3x3_bf16_simt(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                         long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                         const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                         long long out_ld, void* stream);
+
+/* First / last UNet convolutions (C_in or C_out tiny: bandwidth-bound, not GEMM-shaped).
+ * x fp32 NCHW -> bf16 NHWC (score_networks/unet.py:107-114);  bf16 NHWC -> fp32 NCHW (unet.py:248-255).
+ * w is the reference's fp32 [Cout][Cin][3][3] tensor unchanged. */
+int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, int W, const float* w, const float* bias,
+                           int Cout, void* out, long long ldo, void* stream);
+int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, int H, int W, int C, const float* w,
+                            const float* bias, int Cout, float* out, void* stream);
+
+/* Fused softmax attention, head_dim 64.  Element (b,h,row,d) at ptr + b*bs + h*hs + row*rs + d.
+ * logits = scale * q.k (+ q.relk[h, j-i+Tk-1]); relk fp32 [H][2Tk-1][64] or NULL; scramble=1 stores
+ * through the reference's raw (B,H,L,D)->(B,H*D,L) reinterpretation with channel stride o_cs.
+ * Replaces bmm+softmax+bmm at layers/attention.py:182-188 (UNet), :371-375 (DiT), :219-224 (PixArt
+ * cross), :551-676 (temporal, relative positions). */
+int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
+                      long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
+                      long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs, long long o_rs,
+                      int B, int H, int Tq, int Tk, int head_dim, float scale, const float* relk, int scramble,
+                      long long o_cs, void* stream);
+
+/* ---- bandwidth-bound kernels ------------------------------------------------------------------ */
+
+/* GroupNorm over NHWC bf16: a "sample" is P consecutive pixels of C channels.  stats fp32
+ * [nsamples][groups][2] (sum, sum of squares), zeroed inside.  apply: y = GN(x)*gamma+beta, then
+ * y = y*(1+scale)+shift with [scale | shift] = scale_shift[(sample / ss_div)*ss_ld + ...] if non-NULL,
+ * then SiLU if silu.  (torch.nn.GroupNorm(32,C) + SiLU: layers/resnet.py:126-128,151-153,193-197;
+ * layers/attention.py:64; score_networks/unet.py:246-247.) */
+int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, float* stats,
+                       void* stream);
+int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* stats,
+                       const float* gamma, const float* beta, const float* scale_shift, long long ss_ld,
+                       int ss_div, float eps, int silu, void* out, long long ldo, void* stream);
+
+/* out(bf16)[m,:] = LayerNorm(x[m,:]; no affine) * (1 + scale[r,:]) + shift[r,:], r = (m / rows_per_mod)*mod_ld.
+ * (score_networks/dit.py:16-17,46-51,70-72; pixart.py:20-21,82-92) */
+int xd_layernorm_modulate(const float* x, long long ld, int M, int D, const float* shift, const float* scale,
+                          long long mod_ld, int rows_per_mod, float eps, void* out, long long ldo, void* stream);
+
+/* Sinusoidal timestep embedding.  mode 0: a = t*freq (layers/utils.py:102-117); mode 1: a =
+ * (t*1000/max_time)*freq (layers/embedding.py:66-76); mode 2: t <- atan(exp(-clip(t)/2))/(pi/2) first
+ * (embedding.py:131-133).  order 0 = [sin|cos], 1 = [cos|sin].  t: int64 or fp32 [B]. */
+int xd_timestep_embed(const void* t, int t_is_i64, int B, const float* freq, int half, int mode, float max_time,
+                      float clip_lo, float clip_hi, int order, float* out_f32, void* out_bf16, void* stream);
+int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n, void* stream);
+/* c = table[labels] + temb (DiTCombineEmbeddngs, layers/embedding.py:371-406); silu_out = bf16 SiLU(c). */
+int xd_class_combine(const float* table, const long long* labels, const float* temb, int B, int D, float* c_out,
+                     void* silu_out, void* stream);
+/* PatchEmbed im2col (layers/embedding.py:455-457,502-504) and unpatchify (score_networks/dit.py:187-204). */
+int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out_bf16, void* stream);
+int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out, void* stream);
+int xd_add_rows_periodic(const float* a, const float* b, long long rows, int cols, int period, float* out,
+                         void* stream);
+int xd_add_table(const float* a, const float* tab, int G, int R, int C, float* out, void* stream);
+/* Downsample = AvgPool2d(2) (layers/resnet.py:463), Upsample = nearest x2 (resnet.py:495-499), NHWC bf16. */
+int xd_avgpool2x2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out, long long ldo,
+                       void* stream);
+int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out, long long ldo,
+                       void* stream);
+int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, int C, void* out, long long ldo, void* stream);
+/* eps = u + w (c - u)  (samplers/ancestral.py:229-231, samplers/ddim.py:69-71) */
+int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, long long n, void* stream);
+
+/* ---- fused sampler step --------------------------------------------------------------------- */
+
+/* mode 0 ancestral (samplers/ancestral.py:21-72,189-267), 1 DDIM (samplers/ddim.py:43-123), 2 Euler
+ * (samplers/rectified_flow.py:46-84).  coefs fp32 [N][8], row = loop index, read from *idx_dev when
+ * non-NULL else idx_host.  z NULL -> in-kernel Philox normals.  threshold=1 -> dynamic thresholding
+ * (utils.py:379-396) with floor(rank)=thr_k, frac=thr_w, cap=thr_c.  In place (out == x) allowed. */
+int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float* o, const float* z,
+                    long long z_step_stride, float* out, const float* coefs, const int* idx_dev, int idx_host,
+                    long long n_total, int n_per_sample, int threshold, int thr_k, float thr_w, float thr_c,
+                    unsigned long long seed, void* stream);
+/* *idx_dev <- set_to (>= 0) or *idx_dev - 1; then out_*[b] = tab_*[*idx_dev] for b < B
+ * (the per-step `t = torch.tensor([idx]*B)` / logsnr lookups of diffusion/ddpm.py:928-955). */
+int xd_schedule_advance(int* idx_dev, int set_to, const long long* tab_i64, const float* tab_f32a,
+                        const float* tab_f32b, long long* out_i64, float* out_f32a, float* out_f32b, int B,
+                        void* stream);
+/* (clamp(x,-1,1)+1)/2  (utils.py:62-64) */
+int xd_unnormalize(const float* x, float* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDB200_H */

@@ -1,0 +1,346 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the oracle / plain fp32 torch math
+on the same seeded inputs.  Integer / table / sampler-step work is bit-exact; bf16 tensor-core
+contractions are compared on bf16-rounded inputs (exact products, fp32 accumulate) so the only
+differences are summation order (1e-5) and the final bf16 store (2^-9 relative per element)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets as onets  # noqa: E402
+from oracle import samplers as osamplers  # noqa: E402
+from oracle import schedules as oschedules  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from xdiffusion_b200 import ops as _ops
+    return _ops
+
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _gemm_ref(a, w, bias, act, gate, gate_rows, residual):
+    v = a.float() @ w.float().T
+    if bias is not None:
+        v = v + bias
+    if act == 1:
+        v = F.silu(v)
+    elif act == 2:
+        v = F.gelu(v, approximate="tanh")
+    if gate is not None:
+        v = v * gate.repeat_interleave(gate_rows, dim=0)[: v.shape[0]]
+    if residual is not None:
+        v = v + residual.float()
+    return v
+
+
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 384), (2048, 1152, 384), (1000, 64, 384),
+                                    (154, 384, 768), (64, 2304, 384), (300, 200, 128), (4096, 384, 1536)])
+def test_gemm_plain(ops, backend, M, N, K, monkeypatch):
+    monkeypatch.setattr(ops, "MATMUL_BACKEND", backend)
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.linear(a, w, bias, out_dtype=torch.float32)
+    ref = _gemm_ref(a, w, bias, 0, None, 1, None)
+    assert rel_l2(out, ref) < 1e-5
+    out = ops.linear(a, w, bias, act=ops.ACT_GELU, out_dtype=torch.bfloat16)
+    assert rel_l2(out, _gemm_ref(a, w, bias, 2, None, 1, None)) < 3e-3
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_tile_widths_and_epilogues(ops, bn):
+    g = torch.Generator().manual_seed(bn)
+    M, N, K, rows = 512, 512, 256, 16
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    a2 = bf(torch.randn(M, 128, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K + 128, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    gate_buf = torch.randn(M // rows, 3 * N, generator=g).to(DEV)
+    gate = gate_buf[:, N:2 * N]                      # strided view, like an adaLN chunk
+    res = torch.randn(M, N, generator=g).to(DEV)
+    out = ops.linear(a, w, bias, act=ops.ACT_SILU, out_dtype=torch.float32, gate=gate, gate_rows=rows,
+                     residual=res, a2=a2, force_bn=bn)
+    ref = _gemm_ref(torch.cat([a, a2], 1), w, bias, 1, gate, rows, res)
+    assert rel_l2(out, ref) < 1e-5
+    # in-place residual (x += gate * f(x)) with a bf16 residual and bf16 output
+    resb = bf(res)
+    out = ops.linear(a, w[:, :K].contiguous(), None, out_dtype=torch.bfloat16, residual=resb, force_bn=bn)
+    assert rel_l2(out, _gemm_ref(a, w[:, :K], None, 0, None, 1, resb)) < 3e-3
+
+
+def _pack_conv(w, wskip=None):
+    """[Cout,C,3,3] -> [Cout, 9*C (+Cs)] tap-major (same packing as the product's weight repack)."""
+    co, c = w.shape[:2]
+    p = w.permute(0, 2, 3, 1).reshape(co, 9 * c)
+    if wskip is not None:
+        p = torch.cat([p, wskip.reshape(co, -1)], 1)
+    return bf(p).contiguous()
+
+
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("nimg,H,C,Co,Cs", [(2, 32, 128, 128, 0), (2, 16, 256, 256, 0), (3, 8, 256, 256, 0),
+                                             (5, 4, 512, 256, 512), (2, 16, 384, 256, 384), (1, 32, 256, 128, 256),
+                                             (9, 4, 256, 256, 0)])
+def test_conv3x3(ops, backend, nimg, H, C, Co, Cs, monkeypatch):
+    monkeypatch.setattr(ops, "MATMUL_BACKEND", backend)
+    g = torch.Generator().manual_seed(nimg * 100 + H + C + Co)
+    x = bf(torch.randn(nimg, C, H, H, generator=g))
+    w = bf(torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(Co, generator=g)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1)
+    xs = ws = None
+    if Cs:
+        xs = bf(torch.randn(nimg, Cs, H, H, generator=g))
+        ws = bf(torch.randn(Co, Cs, 1, 1, generator=g) / math.sqrt(Cs))
+        ref = ref + F.conv2d(xs.float(), ws.float())
+    res = None
+    if not Cs and C == Co:
+        res = bf(torch.randn(nimg, Co, H, H, generator=g))
+        ref = ref + res.float()
+    nhwc = lambda t: None if t is None else t.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = ops.conv3x3(nhwc(x), _pack_conv(w, ws).to(DEV), bias.to(DEV), residual=nhwc(res), xs=nhwc(xs))
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 3e-3
+
+
+def test_conv3x3_strided_concat_slot(ops):
+    """input and output living inside wider (concat) buffers"""
+    g = torch.Generator().manual_seed(5)
+    nimg, H, C, Co = 2, 16, 256, 256
+    wide = bf(torch.randn(nimg, H, H, C + 128, generator=g)).to(DEV)
+    x = wide[..., 128:]
+    w = bf(torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    outw = torch.zeros(nimg, H, H, Co + 64, dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3(x, _pack_conv(w).to(DEV), out=outw[..., :Co])
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float().cpu(), w.float(), padding=1)
+    assert rel_l2(outw[..., :Co].permute(0, 3, 1, 2), ref) < 3e-3
+    assert float(outw[..., Co:].abs().max()) == 0.0
+
+
+def test_conv_in_out(ops):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 1, 32, 32, generator=g)
+    w = torch.randn(128, 1, 3, 3, generator=g)
+    out = torch.empty(3, 32, 32, 128, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.conv3x3_in(x.to(DEV), w.to(DEV), None, out)
+    assert rel_l2(out.permute(0, 3, 1, 2), F.conv2d(x, w, padding=1)) < 3e-3
+    h = bf(torch.randn(3, 32, 32, 128, generator=g))
+    w2 = torch.randn(1, 128, 3, 3, generator=g) / 30
+    o2 = torch.empty(3, 1, 32, 32, device=DEV)
+    torch.ops.xdb200.conv3x3_out(h.to(DEV), w2.to(DEV), None, o2)
+    assert rel_l2(o2, F.conv2d(h.float().permute(0, 3, 1, 2), w2, padding=1)) < 1e-5
+
+
+@pytest.mark.parametrize("ns,P,C", [(2, 1024, 128), (3, 256, 384), (2, 64, 512), (4, 16, 256), (1, 16384, 128)])
+def test_groupnorm(ops, ns, P, C):
+    g = torch.Generator().manual_seed(P + C)
+    x = bf(torch.randn(ns, P, C, generator=g) * 2 + 0.5)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ss = torch.randn(ns, 2 * C, generator=g) * 0.3
+    xr = x.float().permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+    out = ops.groupnorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), silu=True)
+    assert rel_l2(out.permute(0, 2, 1), F.silu(ref)) < 3e-3
+    ref2 = F.silu(ref * (1 + ss[:, :C, None]) + ss[:, C:, None])
+    out = ops.groupnorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), scale_shift=ss.to(DEV), silu=True)
+    assert rel_l2(out.permute(0, 2, 1), ref2) < 3e-3
+
+
+def test_layernorm_modulate(ops):
+    g = torch.Generator().manual_seed(3)
+    B, T, D = 5, 16, 384
+    x = torch.randn(B * T, D, generator=g) * 3 + 1
+    mod = torch.randn(B, 6 * D, generator=g)
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    ref = F.layer_norm(x, (D,), eps=1e-6).view(B, T, D) * (1 + scale[:, None]) + shift[:, None]
+    md = mod.to(DEV)
+    out = ops.layernorm_modulate(x.to(DEV), md[:, :D], md[:, D:2 * D], T)
+    assert rel_l2(out, ref.view(B * T, D)) < 3e-3
+
+
+def test_attention_layouts(ops):
+    g = torch.Generator().manual_seed(9)
+    # DiT: [Q|K|V]-major, T=16, 6 heads  (oracle.nets.mhsa core)
+    B, T, H = 5, 16, 6
+    qkv = bf(torch.randn(B * T, 3 * H * 64, generator=g))
+    v5 = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = ((v5[0] * 64 ** -0.5) @ v5[1].transpose(-2, -1)).softmax(-1) @ v5[2]          # B,H,T,64
+    d = qkv.to(DEV).view(B, T, 3, H, 64)
+    q, k, v = (d[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = ops.attention(q, k, v, 64 ** -0.5)
+    assert rel_l2(out, ref) < 4e-3
+    # UNet: per-head interleaved, T=256, 4 heads  (oracle.nets.qkv_attention_interleaved)
+    B, T, H = 3, 256, 4
+    qkv = bf(torch.randn(B, T, 3 * H * 64, generator=g))
+    ref = onets.qkv_attention_interleaved(qkv.float().permute(0, 2, 1), H)             # B, H*64, T
+    d = qkv.to(DEV).view(B, T, H, 3, 64)
+    q, k, v = (d[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = ops.attention(q, k, v, 1 / 8.0)                                               # B,H,T,64 view of [B,T,H*64]
+    assert rel_l2(out.permute(0, 1, 3, 2).reshape(B, H * 64, T), ref) < 4e-3
+    # PixArt cross attention: 16 queries x 77 keys
+    B, H = 4, 6
+    qq = bf(torch.randn(B, 16, H, 64, generator=g))
+    kv = bf(torch.randn(B, 77, 2, H, 64, generator=g))
+    ref = ((qq.float().permute(0, 2, 1, 3) @ kv[:, :, 0].float().permute(0, 2, 3, 1)) * 64 ** -0.5).softmax(-1) \
+        @ kv[:, :, 1].float().permute(0, 2, 1, 3)
+    kd = kv.to(DEV)
+    out = ops.attention(qq.to(DEV).permute(0, 2, 1, 3), kd[:, :, 0].permute(0, 2, 1, 3),
+                        kd[:, :, 1].permute(0, 2, 1, 3), 64 ** -0.5)
+    assert rel_l2(out, ref) < 4e-3
+
+
+def test_attention_relative_position_scrambled(ops):
+    """TemporalSelfAttention core incl. the reference's raw reshape (oracle.nets.relpos_attention)."""
+    g = torch.Generator().manual_seed(21)
+    Bp, H, L = 32, 4, 16
+    qkv = bf(torch.randn(Bp, L, 3 * H * 64, generator=g) * 0.3)
+    ek = torch.randn(H, 2 * L - 1, 64, generator=g) / 8
+    ref = onets.relpos_attention(qkv.float().permute(0, 2, 1), H, ek)                   # (Bp, H*64, L)
+    d = qkv.to(DEV).view(Bp, L, H, 3, 64)
+    q, k, v = (d[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = torch.empty(Bp, L, H * 64, dtype=torch.bfloat16, device=DEV)                 # rows = positions
+    ops.attention(q, k, v, 1.0, out=out.view(Bp, L, H, 64).permute(0, 2, 1, 3), relk=ek.to(DEV), scramble=True,
+                  o_cs=1)
+    assert rel_l2(out.permute(0, 2, 1), ref) < 4e-3
+
+
+def test_timestep_embeddings(ops, golden):
+    kat = golden("kat")
+    half = 64
+    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    t = torch.tensor([0, 1, 500, 999])
+    out = torch.empty(4, 128, device=DEV)
+    torch.ops.xdb200.timestep_embed(t.to(DEV), freq.to(DEV), 1, 1000.0, 0.0, 0.0, 0, out)
+    assert (out.cpu() - kat["sin_unet_1000"]).abs().max() < 2e-6
+    tf = torch.tensor([0.001, 0.5, 0.999])
+    out = torch.empty(3, 128, device=DEV)
+    torch.ops.xdb200.timestep_embed(tf.to(DEV), freq.to(DEV), 1, 1.0, 0.0, 0.0, 0, out)
+    assert (out.cpu() - kat["sin_unet_1"]).abs().max() < 2e-6
+    fd = torch.exp(-math.log(10000) * torch.arange(0, 128, dtype=torch.float32) / 128)
+    out = torch.empty(4, 256, device=DEV)
+    torch.ops.xdb200.timestep_embed(t.to(DEV), fd.to(DEV), 0, 1.0, 0.0, 0.0, 1, out)
+    assert (out.cpu() - kat["sin_dit"]).abs().max() < 2e-6
+
+
+def test_patchify_unpatchify_pool(ops):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 1, 32, 32, generator=g)
+    w = torch.randn(384, 1, 8, 8, generator=g)
+    out = torch.empty(3 * 16, 64, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.patchify(x.to(DEV), 8, out)
+    ref = F.conv2d(bf(x).float(), w, stride=8).flatten(2).transpose(1, 2).reshape(48, 384)
+    assert rel_l2(out.float().cpu() @ w.view(384, 64).T, ref) < 1e-5
+    y = torch.randn(48, 64, generator=g)
+    img = torch.empty(3, 1, 32, 32, device=DEV)
+    torch.ops.xdb200.unpatchify(y.to(DEV), 8, img)
+    assert torch.equal(img.cpu(), onets.unpatchify(y.view(3, 16, 64), 8, 1))
+    h = bf(torch.randn(2, 16, 16, 128, generator=g)).to(DEV)
+    o = torch.empty(2, 8, 8, 128, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.avgpool2x2(h, o)
+    assert rel_l2(o.permute(0, 3, 1, 2), F.avg_pool2d(h.float().permute(0, 3, 1, 2), 2)) < 3e-3
+    u = torch.empty(2, 32, 32, 128, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.upsample2x(h, u)
+    assert torch.equal(u.permute(0, 3, 1, 2).float(), F.interpolate(h.float().permute(0, 3, 1, 2), scale_factor=2))
+
+
+def _coefs_discrete(tables, logvar, pred):
+    T = tables["betas"].shape[0]
+    c = torch.zeros(T, 8)
+    if pred == "epsilon":
+        c[:, 0], c[:, 1] = tables["sqrt_recip_alphas_cumprod"], tables["sqrt_recipm1_alphas_cumprod"]
+    else:
+        c[:, 0], c[:, 1] = tables["sqrt_alphas_cumprod"], tables["sqrt_one_minus_alphas_cumprod"]
+    c[:, 2], c[:, 3] = tables["posterior_mean_coef1"], tables["posterior_mean_coef2"]
+    c[:, 4] = torch.exp(0.5 * logvar)
+    return c
+
+
+@pytest.mark.parametrize("pred", ["epsilon", "v"])
+@pytest.mark.parametrize("threshold", [False, True])
+def test_sampler_step_discrete_bit_exact(ops, pred, threshold):
+    tables = oschedules.discrete_tables(1000, "linear")
+    logvar = oschedules.fixed_large_logvar(tables)
+    coefs = _coefs_discrete(tables, logvar, pred).to(DEV)
+    g = torch.Generator().manual_seed(17)
+    B = 6
+    for i in (999, 500, 37, 1, 0):
+        x, o, z = (torch.randn(B, 1, 32, 32, generator=g) for _ in range(3))
+        x = x * torch.linspace(0.2, 3.0, B)[:, None, None, None]
+        ref = osamplers.ancestral_discrete(x, o, z, i, tables, logvar, pred, (0.99, 1.7) if threshold else None)
+        ranks = torch.tensor(0.99, dtype=torch.float32) * (1024 - 1)
+        out = torch.empty_like(x, device=DEV)
+        torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out, coefs, None, i,
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0)
+        assert torch.equal(out.cpu(), ref), (i, float((out.cpu() - ref).abs().max()))
+        # device-resident loop index (the CUDA-graph path)
+        idx = torch.tensor([i], dtype=torch.int32, device=DEV)
+        out2 = torch.empty_like(out)
+        torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out2, coefs, idx, -1,
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0)
+        assert torch.equal(out2, out)
+
+
+def test_sampler_step_euler_and_philox(ops):
+    g = torch.Generator().manual_seed(4)
+    x, o = torch.randn(4, 1, 32, 32, generator=g), torch.randn(4, 1, 32, 32, generator=g)
+    coefs = torch.zeros(1000, 8)
+    coefs[:, 0] = 1.0 / 1000
+    out = torch.empty_like(x, device=DEV)
+    torch.ops.xdb200.sampler_step(2, 0, 0, x.to(DEV), o.to(DEV), None, 0, out, coefs.to(DEV), None, 5, 0, 0, 0.0,
+                                  0.0, 0)
+    assert torch.equal(out.cpu(), osamplers.euler_flow(x, o, 1000))
+    # in-kernel noise: x0 == 0 => out = sigma * z ~ N(0, sigma^2), different per step and per seed
+    n = 1 << 20
+    zeros = torch.zeros(1, n, device=DEV)
+    c = torch.zeros(4, 8, device=DEV)
+    c[:, 4] = 1.0
+    outs = []
+    for step, seed in ((1, 1), (2, 1), (1, 2)):
+        o_ = torch.empty_like(zeros)
+        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, o_, c, None, step, 0, 0, 0.0, 0.0, seed)
+        outs.append(o_.cpu())
+    for o_ in outs:
+        assert abs(float(o_.mean())) < 5e-3 and abs(float(o_.std()) - 1) < 5e-3
+        assert abs(float((o_ ** 4).mean()) - 3) < 0.05
+    assert abs(float((outs[0] * outs[1]).mean())) < 5e-3 and abs(float((outs[0] * outs[2]).mean())) < 5e-3
+
+
+def test_schedule_advance_and_misc(ops):
+    idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    tab = torch.arange(1000, dtype=torch.int64, device=DEV) * 3
+    tf = torch.linspace(0, 1, 1000, device=DEV)
+    oi = torch.empty(7, dtype=torch.int64, device=DEV)
+    of = torch.empty(7, device=DEV)
+    torch.ops.xdb200.schedule_advance(idx, 999, tab, tf, None, oi, of, None, 7)
+    assert int(idx) == 999 and bool((oi == 2997).all()) and bool((of == tf[999]).all())
+    torch.ops.xdb200.schedule_advance(idx, -1, tab, tf, None, oi, of, None, 7)
+    assert int(idx) == 998 and bool((oi == 2994).all())
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(4096, generator=g), torch.randn(4096, generator=g)
+    out = torch.empty(4096, device=DEV)
+    torch.ops.xdb200.cfg_combine(a.to(DEV), b.to(DEV), 2.0, out)
+    assert torch.equal(out.cpu(), osamplers.cfg_combine(a, b, 2.0))
+    torch.ops.xdb200.unnormalize((a * 2).to(DEV), out)
+    assert torch.equal(out.cpu(), osamplers.unnormalize(a * 2))
+
+
+def test_cpu_tensors_are_rejected(ops):
+    a = torch.randn(128, 64).bfloat16()
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.xdb200.gemm(a, None, a, None, 0, None, 1, None, torch.empty(128, 128), 0)

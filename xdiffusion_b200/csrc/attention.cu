@@ -1,0 +1,197 @@
+// Fused softmax attention, head dim 64, bf16 in / bf16 out, fp32 math, online softmax.
+// One thread owns one query row (q and the output accumulator live in registers); K/V chunks of
+// 16 keys are staged in shared memory as fp32 and broadcast to the rows that share them.  A CTA
+// holds 128 query rows: one (batch, head) slab when Tq >= 128, else 128/Tq (batch, head) pairs.
+//
+// Element (b, h, row, d) of q/k/v/o lives at  ptr + b*bs + h*hs + row*rs + d  (elements), which
+// covers every layout on the hot path:
+//   UNet  QKVAttention            qkv[B*T, 3C], per-head interleaved  (layers/attention.py:161-188)
+//   DiT   MultiHeadSelfAttention  qkv[B*T, 3D], [Q|K|V]-major         (layers/attention.py:350-380)
+//   PixArt LastChannelCrossAttention  q[B*16, D], kv[B*77, 2D]        (layers/attention.py:209-228)
+//   video TemporalSelfAttention: + relative-position logits q.E_k[h, j-i+L-1], no scale, and the
+//       reference's raw (B,H,L,D)->(B,H*D,L) reinterpretation on store (layers/attention.py:551-676)
+#include "common.cuh"
+
+namespace {
+
+constexpr int D = 64;
+constexpr int KC = 16;          // keys per shared-memory chunk
+constexpr int ROWS = 128;       // query rows (threads) per CTA
+
+struct AttnParams {
+    const bf16 *q, *k, *v;
+    bf16* o;
+    long long q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
+    int B, H, Tq, Tk;
+    float scale;
+    const float* relk;          // optional [H][2*Tk-1][64] relative-position key table
+    int scramble;               // temporal quirk: out viewed as (H*64, L) from a (H, L, 64) buffer
+    long long o_cs;             // scramble: element stride between "channels" of the (C, L) view
+};
+
+__global__ void __launch_bounds__(ROWS)
+attention_kernel(const AttnParams p) {
+    extern __shared__ float smem[];             // [pairs][2][KC][D]
+    const int pairs = p.Tq >= ROWS ? 1 : ROWS / p.Tq;
+    const int slabs = p.Tq >= ROWS ? p.Tq / ROWS : 1;
+    const int tid = threadIdx.x;
+    int pair_local, row;
+    long long bh;
+    if (p.Tq >= ROWS) {
+        bh = blockIdx.x / slabs;
+        row = (blockIdx.x % slabs) * ROWS + tid;
+        pair_local = 0;
+    } else {
+        pair_local = tid / p.Tq;
+        row = tid % p.Tq;
+        bh = (long long)blockIdx.x * pairs + pair_local;
+    }
+    const long long nbh = (long long)p.B * p.H;
+    const bool active = bh < nbh;
+    const int b = active ? (int)(bh / p.H) : 0, h = active ? (int)(bh % p.H) : 0;
+
+    float q[D], o[D];
+    if (active) {
+        const bf16* qp = p.q + b * p.q_bs + h * p.q_hs + (long long)row * p.q_rs;
+#pragma unroll
+        for (int d = 0; d < D; d += 8) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(qp + d), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[d + i] = f[i] * p.scale;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[d] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = 0.f;
+    float mx = -INFINITY, l = 0.f;
+
+    const long long bh0 = p.Tq >= ROWS ? bh : (long long)blockIdx.x * pairs;
+    float* sK = smem + pair_local * 2 * KC * D;
+    float* sV = sK + KC * D;
+    for (int k0 = 0; k0 < p.Tk; k0 += KC) {
+        const int kn = min(KC, p.Tk - k0);
+        __syncthreads();
+        // cooperative load: pairs * kn keys * 8 vectors, for K and V
+        for (int i = tid; i < pairs * KC * 8; i += ROWS) {
+            const int pr = i / (KC * 8), rem = i % (KC * 8), kk = rem / 8, vv = rem % 8;
+            const long long bhl = bh0 + pr;
+            if (kk < kn && bhl < nbh) {
+                const int bb = (int)(bhl / p.H), hh = (int)(bhl % p.H);
+                float f[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.k + bb * p.k_bs + hh * p.k_hs + (long long)(k0 + kk) * p.k_rs + vv * 8), f);
+                float* dst = smem + (pr * 2 * KC + kk) * D + vv * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = f[j];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.v + bb * p.v_bs + hh * p.v_hs + (long long)(k0 + kk) * p.v_rs + vv * 8), f);
+                dst += KC * D;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = f[j];
+            }
+        }
+        __syncthreads();
+        float s[KC];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            float acc = 0.f;
+            if (kk < kn) {
+                const float4* kr = reinterpret_cast<const float4*>(sK + kk * D);
+#pragma unroll
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 t = kr[d4];
+                    acc = fmaf(q[4 * d4], t.x, acc); acc = fmaf(q[4 * d4 + 1], t.y, acc);
+                    acc = fmaf(q[4 * d4 + 2], t.z, acc); acc = fmaf(q[4 * d4 + 3], t.w, acc);
+                }
+                if (p.relk) {
+                    const float4* er = reinterpret_cast<const float4*>(
+                        p.relk + ((long long)h * (2 * p.Tk - 1) + (k0 + kk - row + p.Tk - 1)) * D);
+#pragma unroll
+                    for (int d4 = 0; d4 < D / 4; ++d4) {
+                        const float4 t = __ldg(er + d4);
+                        acc = fmaf(q[4 * d4], t.x, acc); acc = fmaf(q[4 * d4 + 1], t.y, acc);
+                        acc = fmaf(q[4 * d4 + 2], t.z, acc); acc = fmaf(q[4 * d4 + 3], t.w, acc);
+                    }
+                }
+            } else {
+                acc = -INFINITY;
+            }
+            s[kk] = acc;
+            cmax = fmaxf(cmax, acc);
+        }
+        const float nmx = fmaxf(mx, cmax);
+        const float corr = __expf(mx - nmx);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] *= corr;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            if (kk < kn) {
+                const float pw = __expf(s[kk] - nmx);
+                l += pw;
+                const float4* vr = reinterpret_cast<const float4*>(sV + kk * D);
+#pragma unroll
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 t = vr[d4];
+                    o[4 * d4] = fmaf(pw, t.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pw, t.y, o[4 * d4 + 1]);
+                    o[4 * d4 + 2] = fmaf(pw, t.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pw, t.w, o[4 * d4 + 3]);
+                }
+            }
+        }
+        mx = nmx;
+    }
+    if (!active) return;
+    const float inv = 1.0f / l;
+    if (!p.scramble) {
+        bf16* op = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_rs;
+#pragma unroll
+        for (int d = 0; d < D; d += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = o[d + i] * inv;
+            *reinterpret_cast<bf16x8*>(op + d) = pack8(f);
+        }
+    } else {
+        // a[b, h, row, d] is element (h*L + row)*64 + d of a flat buffer that the reference then
+        // views as (C = H*64, L): flat = c*L + l.
+        const int L = p.Tq;
+        bf16* ob = p.o + b * p.o_bs;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int flat = (h * L + row) * D + d;
+            const int c = flat / L, lpos = flat % L;
+            ob[(long long)lpos * p.o_rs + (long long)c * p.o_cs] = __float2bfloat16_rn(o[d] * inv);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
+                                 long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
+                                 long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs,
+                                 long long o_rs, int B, int H, int Tq, int Tk, int head_dim, float scale,
+                                 const float* relk, int scramble, long long o_cs, void* stream) {
+    XD_CHECK_ARG(q && k && v && o && head_dim == D && B > 0 && H > 0 && Tq > 0 && Tk > 0);
+    XD_CHECK_ARG((Tq >= ROWS && Tq % ROWS == 0) || (Tq < ROWS && ROWS % Tq == 0));
+    XD_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && q_hs % 8 == 0 && k_hs % 8 == 0 && v_hs % 8 == 0 &&
+                 q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0);
+    XD_CHECK_ARG(scramble || (o_rs % 8 == 0 && o_hs % 8 == 0 && o_bs % 8 == 0));
+    XD_CHECK_ARG(!relk || Tq == Tk);
+    AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, q_bs, q_hs, q_rs, k_bs, k_hs, k_rs,
+                 v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs};
+    const int pairs = Tq >= ROWS ? 1 : ROWS / Tq;
+    const long long nbh = (long long)B * H;
+    const long long blocks = Tq >= ROWS ? nbh * (Tq / ROWS) : (nbh + pairs - 1) / pairs;
+    const size_t smem = (size_t)pairs * 2 * KC * D * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * KC * D * 4);
+        configured = true;
+    }
+    attention_kernel<<<(unsigned)blocks, ROWS, smem, (cudaStream_t)stream>>>(p);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}

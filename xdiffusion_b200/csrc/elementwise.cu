@@ -1,0 +1,270 @@
+// Small bandwidth-bound kernels around the score networks: sinusoidal timestep embeddings (both
+// reference formulas), patchify / unpatchify, class-embedding combine, 2x2 average pool, nearest
+// 2x upsample, activation casts, broadcast adds and the classifier-free-guidance combine.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float load_time(const void* t, int is_i64, long long i) {
+    return is_i64 ? (float)((const long long*)t)[i] : ((const float*)t)[i];
+}
+
+// out[b, :] = [sin(a) | cos(a)] (order 0) or [cos(a) | sin(a)] (order 1), a = tx * freq[i], with
+//   mode 0: tx = t                                  (layers/utils.py:102-117, DiT)
+//   mode 1: tx = t * 1000 / max_time                (layers/embedding.py:66-76, UNet)
+//   mode 2: tx = atan(exp(-0.5 clip(t,lo,hi))) / (pi/2) * 1000 / max_time   (embedding.py:131-133)
+// freq is the host-built fp32 table (same torch ops as the reference), so only sinf/cosf differ.
+__global__ void sinusoid_kernel(const void* t, int is_i64, int B, const float* __restrict__ freq, int half, int mode,
+                                float max_time, float clip_lo, float clip_hi, int order, float* out_f32,
+                                bf16* out_bf16) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    float tx = load_time(t, is_i64, b);
+    if (mode == 2) {
+        tx = fminf(fmaxf(tx, clip_lo), clip_hi);
+        tx = atanf(expf(-0.5f * tx)) / (0.5f * 3.14159265358979323846f);
+    }
+    if (mode >= 1) tx = __fdiv_rn(__fmul_rn(tx, 1000.0f), max_time);
+    const float a = __fmul_rn(tx, freq[j]);
+    float s, c;
+    sincosf(a, &s, &c);
+    const float first = order == 0 ? s : c, second = order == 0 ? c : s;
+    const long long o = (long long)b * 2 * half;
+    if (out_f32) { out_f32[o + j] = first; out_f32[o + half + j] = second; }
+    if (out_bf16) { out_bf16[o + j] = __float2bfloat16_rn(first); out_bf16[o + half + j] = __float2bfloat16_rn(second); }
+}
+
+// act + cast, n elements
+__global__ void act_cast_kernel(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = in_dtype == XD_F32 ? ((const float*)in)[i] : __bfloat162float(((const bf16*)in)[i]);
+    v = apply_act(v, act);
+    if (out_dtype == XD_F32) ((float*)out)[i] = v;
+    else ((bf16*)out)[i] = __float2bfloat16_rn(v);
+}
+
+// c = table[label] + temb ; optionally also silu(c) as bf16 (input of every adaLN GEMM)
+__global__ void class_combine_kernel(const float* __restrict__ table, const long long* __restrict__ labels,
+                                     const float* __restrict__ temb, int B, int Dm, float* c_out, bf16* silu_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Dm) return;
+    const int b = i / Dm, d = i % Dm;
+    float v = temb[i];
+    if (table) v = table[labels[b] * Dm + d] + v;
+    if (c_out) c_out[i] = v;
+    if (silu_out) silu_out[i] = __float2bfloat16_rn(silu_f(v));
+}
+
+// x fp32 NCHW -> bf16 [B*gh*gw, C*p*p], column order (c, py, px) = flattened Conv2d weight
+__global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p, bf16* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int gh = H / p, gw = W / p, K = C * p * p;
+    const long long total = (long long)B * gh * gw * K;
+    if (i >= total) return;
+    const int k = (int)(i % K);
+    const long long tok = i / K;
+    const int px = k % p, py = (k / p) % p, c = k / (p * p);
+    const int tw = (int)(tok % gw), th = (int)((tok / gw) % gh);
+    const long long b = tok / ((long long)gw * gh);
+    out[i] = __float2bfloat16_rn(x[((b * C + c) * H + th * p + py) * W + tw * p + px]);
+}
+
+// y fp32 [B*gh*gw, p*p*c] -> fp32 NCHW : img[n, c, h*p+py, w*p+px] = y[n, h, w, py, px, c]  (dit.py:187-204)
+__global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy, int B, int C, int H, int W, int p,
+                                  float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * C * H * W;
+    if (i >= total) return;
+    const int xx = (int)(i % W), yy = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C);
+    const long long b = i / ((long long)W * H * C);
+    const int gw = W / p, gh = H / p;
+    const long long tok = (b * gh + yy / p) * gw + xx / p;
+    out[i] = y[tok * ldy + ((yy % p) * p + xx % p) * C + c];
+}
+
+// out[r, c] = a[r, c] + b[(r % period), c]   (fp32; token position embeddings: period = tokens per sample)
+__global__ void add_rows_periodic_kernel(const float* a, const float* b, long long rows, int cols, int period,
+                                         float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    out[i] = a[i] + b[(r % period) * cols + c];
+}
+
+// out[g, r, c] = a[r, c] + tab[g, c]    (PixArt adaLN-single: table(6*D) + t0, for all blocks at once)
+__global__ void add_table_kernel(const float* a, const float* tab, int G, int R, int Ccols, float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)G * R * Ccols;
+    if (i >= total) return;
+    const int c = (int)(i % Ccols);
+    const int r = (int)((i / Ccols) % R);
+    const int g = (int)(i / ((long long)Ccols * R));
+    out[i] = a[(long long)r * Ccols + c] + tab[(long long)g * Ccols + c];
+}
+
+// 2x2 average pool / nearest 2x upsample over NHWC bf16 (8 channels per thread)
+__global__ void avgpool2_kernel(const bf16* __restrict__ x, long long ldx, int nimg, int H, int W, int C, bf16* out,
+                                long long ldo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = C / 8, Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)nimg * Ho * Wo * V;
+    if (i >= total) return;
+    const int j = (int)(i % V);
+    const long long m = i / V;
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho);
+    const long long img = m / ((long long)Wo * Ho);
+    float acc[8] = {};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + ((img * H + 2 * ho + dy) * W + 2 * wo + dx) * ldx + j * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= 0.25f;
+    *reinterpret_cast<bf16x8*>(out + m * ldo + j * 8) = pack8(acc);
+}
+
+__global__ void upsample2_kernel(const bf16* __restrict__ x, long long ldx, int nimg, int H, int W, int C, bf16* out,
+                                 long long ldo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = C / 8, Ho = H * 2, Wo = W * 2;
+    const long long total = (long long)nimg * Ho * Wo * V;
+    if (i >= total) return;
+    const int j = (int)(i % V);
+    const long long m = i / V;
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho);
+    const long long img = m / ((long long)Wo * Ho);
+    *reinterpret_cast<bf16x8*>(out + m * ldo + j * 8) =
+        *reinterpret_cast<const bf16x8*>(x + ((img * H + ho / 2) * W + wo / 2) * ldx + j * 8);
+}
+
+// rows x C bf16 copy between strided buffers (skip-connection concat slots)
+__global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int C, bf16* out,
+                                 long long ldo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = C / 8;
+    if (i >= rows * V) return;
+    const long long r = i / V;
+    const int j = (int)(i % V);
+    *reinterpret_cast<bf16x8*>(out + r * ldo + j * 8) = *reinterpret_cast<const bf16x8*>(x + r * ldx + j * 8);
+}
+
+// eps = u + w (c - u)   (samplers/ancestral.py:229-231), float4 vectorised
+__global__ void cfg_kernel(const float4* __restrict__ c, const float4* __restrict__ u, float w, float4* out,
+                           long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 a = c[i], b = u[i];
+    float4 r;
+    r.x = __fadd_rn(b.x, __fmul_rn(w, __fsub_rn(a.x, b.x)));
+    r.y = __fadd_rn(b.y, __fmul_rn(w, __fsub_rn(a.y, b.y)));
+    r.z = __fadd_rn(b.z, __fmul_rn(w, __fsub_rn(a.z, b.z)));
+    r.w = __fadd_rn(b.w, __fmul_rn(w, __fsub_rn(a.w, b.w)));
+    out[i] = r;
+}
+
+inline unsigned blocks_for(long long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+extern "C" int xd_timestep_embed(const void* t, int t_is_i64, int B, const float* freq, int half, int mode,
+                                 float max_time, float clip_lo, float clip_hi, int order, float* out_f32,
+                                 void* out_bf16, void* stream) {
+    XD_CHECK_ARG(t && freq && B > 0 && half > 0 && (out_f32 || out_bf16) && mode >= 0 && mode <= 2);
+    sinusoid_kernel<<<blocks_for((long long)B * half), 256, 0, (cudaStream_t)stream>>>(
+        t, t_is_i64, B, freq, half, mode, max_time, clip_lo, clip_hi, order, out_f32, (bf16*)out_bf16);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n,
+                           void* stream) {
+    XD_CHECK_ARG(in && out && n > 0);
+    act_cast_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(in, in_dtype, out, out_dtype, act, n);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_class_combine(const float* table, const long long* labels, const float* temb, int B, int Dm,
+                                float* c_out, void* silu_out, void* stream) {
+    XD_CHECK_ARG(temb && (c_out || silu_out) && (table == nullptr) == (labels == nullptr));
+    class_combine_kernel<<<blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream>>>(table, labels, temb, B, Dm,
+                                                                                        c_out, (bf16*)silu_out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out, void* stream) {
+    XD_CHECK_ARG(x && out && p > 0 && H % p == 0 && W % p == 0);
+    patchify_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, p,
+                                                                                           (bf16*)out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out,
+                             void* stream) {
+    XD_CHECK_ARG(y && out && p > 0 && H % p == 0 && W % p == 0);
+    unpatchify_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(y, ldy, B, C, H, W, p,
+                                                                                             out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_add_rows_periodic(const float* a, const float* b, long long rows, int cols, int period, float* out,
+                                    void* stream) {
+    XD_CHECK_ARG(a && b && out && period > 0);
+    add_rows_periodic_kernel<<<blocks_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, b, rows, cols, period, out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_add_table(const float* a, const float* tab, int G, int R, int C, float* out, void* stream) {
+    XD_CHECK_ARG(a && tab && out);
+    add_table_kernel<<<blocks_for((long long)G * R * C), 256, 0, (cudaStream_t)stream>>>(a, tab, G, R, C, out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_avgpool2x2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out,
+                                  long long ldo, void* stream) {
+    XD_CHECK_ARG(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
+    avgpool2_kernel<<<blocks_for((long long)nimg * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, nimg, H, W, C, (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out,
+                                  long long ldo, void* stream) {
+    XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
+    upsample2_kernel<<<blocks_for((long long)nimg * H * 2 * W * 2 * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, nimg, H, W, C, (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, int C, void* out, long long ldo,
+                                 void* stream) {
+    XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
+    copy_rows_kernel<<<blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, rows, C,
+                                                                                   (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, long long n,
+                              void* stream) {
+    XD_CHECK_ARG(cond && uncond && out && n % 4 == 0);
+    cfg_kernel<<<blocks_for(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)cond, (const float4*)uncond, w,
+                                                                    (float4*)out, n / 4);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}

@@ -1,0 +1,382 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM conv3x3 for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * Wt[n, k]            (A bf16 row-major, Wt bf16 [N, K] row-major)
+//
+// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0      TMA producer: per 64-wide k-block one A box (128 rows x 128 B) and one B box
+//               (BN rows x 128 B) into a STAGES-deep ring, 128-byte swizzle, mbarrier complete_tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 UMMA K=16 steps per k-block),
+//               tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias / activation / gate /
+//               residual -> fp32 or bf16 global stores
+// Two CTAs are co-resident per SM (BN <= 128) so one CTA's epilogue overlaps the other's MMAs.
+//
+// Implicit conv3x3 (NHWC, pad 1): the A operand of k-block (tap, 64-channel chunk) is a 4-D TMA
+// box (64 ch, W, TH rows, TN images) of the activation tensor shifted by the tap offset; TMA's
+// out-of-bounds zero fill *is* the padding.  An optional second A segment (1x1, no shift) lets a
+// resblock's skip projection accumulate into the same TMEM tile (K = 9*C + Cskip).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+    int M, N;
+    int nk0, nk1;       // k-blocks taken from A0 / A1
+    int conv;           // 0: plain rows, 1: conv3x3 geometry
+    int cpb;            // conv: 64-channel chunks per tap
+    int H, W;           // conv: image height / width
+    int vec_ok;         // epilogue pointers/strides allow 16-byte accesses
+    Epilogue epi;
+};
+
+template <int BN> struct Cfg {
+    static constexpr int STAGES = (BN <= 128) ? 3 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int MIN_CTAS = (BN <= 128) ? 2 : 1;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, Cfg<BN>::MIN_CTAS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM;
+    const int nk = p.nk0 + p.nk1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmB);
+        if (p.nk1) ptx::prefetch_tmap(&tmA1);
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr, BN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int img = 0, h0 = 0;
+            if (p.conv) {
+                const int hw = p.H * p.W;
+                img = m0 / hw;
+                h0 = (m0 - img * hw) / p.W;
+            }
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % C::STAGES;
+                const uint32_t ph = (kb / C::STAGES) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sA = smem + s * C::STAGE_BYTES;
+                uint8_t* sB = sA + C::A_BYTES;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                if (kb < p.nk0) {
+                    if (!p.conv) {
+                        ptx::tma_load_4d(sA, &tmA0, &full_bar[s], kb * BK, m0, 0, 0);
+                    } else {
+                        const int tap = kb / p.cpb;
+                        const int cc = kb - tap * p.cpb;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        ptx::tma_load_4d(sA, &tmA0, &full_bar[s], cc * BK, dx, h0 + dy, img);
+                    }
+                } else {
+                    const int k1 = kb - p.nk0;
+                    if (!p.conv) ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, m0, 0, 0);
+                    else ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, 0, h0, img);
+                }
+                ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n_tile0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % C::STAGES;
+            const uint32_t ph = (kb / C::STAGES) & 1;
+            ptx::mbar_wait(&full_bar[s], ph);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = ptx::smem_u32(smem + s * C::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + C::A_BYTES;
+                const uint64_t da = ptx::smem_desc_sw128(a_addr);
+                const uint64_t db = ptx::smem_desc_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
+                    ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty_bar[s]);
+                if (kb == nk - 1) ptx::umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+        const long long m = (long long)m0 + q * 32 + lane;
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after();
+        const Epilogue& e = p.epi;
+        const long long gate_row = e.gate ? (m / e.gate_rows) * e.gate_ld : 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            __syncwarp();                                // tcgen05.ld is warp-collective (.sync.aligned)
+            ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + c * 32, r);
+            ptx::tmem_ld_wait();
+            const int n = n_tile0 + c * 32;
+            if (n >= p.N) break;                         // warp-uniform
+            if (m >= p.M) continue;                      // row tail: nothing to store
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.vec_ok && n + 32 <= p.N) {
+                if (e.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (e.act != XD_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
+                }
+                if (e.gate) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + gate_row + n + j));
+                        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+                    }
+                }
+                if (e.residual) {
+                    if (e.res_dtype == XD_F32) {
+                        const float* rp = (const float*)e.residual + m * e.res_ld + n;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(rp + j);
+                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        }
+                    } else {
+                        const bf16* rp = (const bf16*)e.residual + m * e.res_ld + n;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float f[8];
+                            unpack8(*reinterpret_cast<const bf16x8*>(rp + j), f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[j + i] += f[i];
+                        }
+                    }
+                }
+                if (e.out_dtype == XD_F32) {
+                    float* op = (float*)e.out + m * e.out_ld + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    bf16* op = (bf16*)e.out + m * e.out_ld + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(op + j) = pack8(v + j);
+                }
+            } else {
+                for (int j = 0; j < 32 && n + j < p.N; ++j) epi_store(e, epi_value(e, v[j], m, n + j), m, n + j);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_d, BN);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+// bf16 tensor map, inner box = 64 elements (128 B), 128-byte swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { xd_set_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled entry point not found"); return XD_ERR_TMAP; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
+                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        static char msg[160];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        xd_set_error(__FILE__, __LINE__, msg);
+        return XD_ERR_TMAP;
+    }
+    return XD_OK;
+}
+
+int tmap_rows(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    // rank-4 view (cols, rows, 1, 1) so that the plain GEMM shares the conv kernel's 4-D load.
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, 1, 1};
+    cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
+    cuuint32_t box[4] = {BK, (cuuint32_t)box_rows, 1, 1};
+    return make_tmap(tm, ptr, 4, dims, str, box);
+}
+
+int tmap_weights(CUtensorMap* tm, const void* ptr, long long n, long long k, long long ld, int bn) {
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)n};
+    cuuint64_t str[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    return make_tmap(tm, ptr, 2, dims, str, box);
+}
+
+int tmap_nhwc(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, long long ld) {
+    // ld = elements between consecutive pixels (>= C: the tensor may be a channel slice of a wider buffer)
+    const int hw = H * W;
+    const int th = hw >= BM ? BM / W : H;
+    const int tn = hw >= BM ? 1 : BM / hw;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
+    cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)th, (cuuint32_t)tn};
+    return make_tmap(tm, ptr, 4, dims, str, box);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int epilogue_vec_ok(const Epilogue& e) {
+    bool ok = aligned16(e.out) && aligned16(e.bias) && aligned16(e.gate) && aligned16(e.residual);
+    ok = ok && (e.out_ld % 8 == 0) && (e.res_ld % 8 == 0) && (e.gate_ld % 4 == 0);
+    return ok ? 1 : 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM) !=
+            cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
+            return XD_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(a0, a1, b, p);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+int pick_bn(int N, int M) {
+    if (N <= 64) return 64;
+    // fill the machine: prefer 128-wide tiles, go to 256 only when there are plenty of tiles
+    const long long tiles128 = (long long)((N + 127) / 128) * ((M + BM - 1) / BM);
+    if (N % 256 == 0 && tiles128 >= 4 * 148 * 2) return 256;
+    return 128;
+}
+
+int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p,
+             cudaStream_t st) {
+    switch (bn) {
+        case 64: return launch<64>(a0, a1, b, p, st);
+        case 128: return launch<128>(a0, a1, b, p, st);
+        case 256: return launch<256>(a0, a1, b, p, st);
+    }
+    return XD_ERR_ARG;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI (declared in include/xdb200.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                               long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                               int gate_rows, long long gate_ld, const void* residual, int res_dtype,
+                               long long res_ld, void* out, int out_dtype, long long out_ld, int force_bn,
+                               void* stream) {
+    XD_CHECK_ARG(A && Wt && out && M > 0 && N > 0 && K > 0);
+    XD_CHECK_ARG(K % BK == 0 && K2 % BK == 0 && (A2 != nullptr) == (K2 > 0));
+    XD_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda2 % 8 == 0 && aligned16(A) && aligned16(Wt) && aligned16(A2));
+    XD_CHECK_ARG(!gate || gate_rows > 0);
+    TcParams p{};
+    p.M = M; p.N = N; p.nk0 = K / BK; p.nk1 = K2 / BK; p.conv = 0;
+    p.epi = Epilogue{bias, gate, residual, out, gate_ld, res_ld, out_ld, act, gate_rows, res_dtype, out_dtype};
+    p.vec_ok = epilogue_vec_ok(p.epi);
+    const int bn = force_bn ? force_bn : pick_bn(N, M);
+    CUtensorMap ta0, ta1, tb;
+    int rc;
+    if ((rc = tmap_rows(&ta0, A, M, K, lda, BM))) return rc;
+    ta1 = ta0;
+    if (A2 && (rc = tmap_rows(&ta1, A2, M, K2, lda2, BM))) return rc;
+    if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, bn))) return rc;
+    return dispatch(bn, ta0, ta1, tb, p, (cudaStream_t)stream);
+}
+
+extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                                  long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                                  const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                                  long long out_ld, int force_bn, void* stream) {
+    XD_CHECK_ARG(X && Wp && out && nimg > 0 && H > 0 && W > 0 && Cout > 0);
+    XD_CHECK_ARG(C % BK == 0 && Cs % BK == 0 && (Xs != nullptr) == (Cs > 0));
+    XD_CHECK_ARG(ldx % 8 == 0 && lds % 8 == 0 && aligned16(X) && aligned16(Xs) && aligned16(Wp));
+    const int hw = H * W;
+    // an M tile is 128 consecutive NHWC pixels: whole rows of one image, or whole images
+    XD_CHECK_ARG(W <= BM && BM % W == 0 && (hw % BM == 0 || BM % hw == 0));
+    TcParams p{};
+    p.M = nimg * hw; p.N = Cout; p.conv = 1; p.cpb = C / BK; p.nk0 = 9 * p.cpb; p.nk1 = Cs / BK; p.H = H; p.W = W;
+    p.epi = Epilogue{bias, nullptr, residual, out, 0, res_ld, out_ld, act, 1, res_dtype, out_dtype};
+    p.vec_ok = epilogue_vec_ok(p.epi);
+    const int bn = force_bn ? force_bn : pick_bn(Cout, p.M);
+    CUtensorMap ta0, ta1, tb;
+    int rc;
+    if ((rc = tmap_nhwc(&ta0, X, nimg, H, W, C, ldx))) return rc;
+    ta1 = ta0;
+    if (Xs && (rc = tmap_nhwc(&ta1, Xs, nimg, H, W, Cs, lds))) return rc;
+    const long long ktot = 9LL * C + Cs;
+    if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, bn))) return rc;
+    return dispatch(bn, ta0, ta1, tb, p, (cudaStream_t)stream);
+}

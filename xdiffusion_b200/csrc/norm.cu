@@ -1,0 +1,188 @@
+// Bandwidth-bound normalisation kernels.
+//   GroupNorm(32 groups, eps) [+ (1+scale)*y+shift] [+ SiLU] over NHWC bf16   (layers/resnet.py:126-128,
+//       151-153,193-197; layers/attention.py:64 in the reference)
+//   LayerNorm(no affine, eps) * (1+scale) + shift over fp32 token rows -> bf16 (score_networks/dit.py:16-17,46-51)
+// Statistics in fp32; 16-byte vector accesses; warp-shuffle / shared-memory reductions.
+#include "common.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------- GroupNorm
+// stats[sample][group] = (sum, sum of squares) accumulated with atomics from pixel slabs.
+// "sample" = P consecutive pixels (rows of C channels, stride ld).
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, float* __restrict__ stats) {
+    __shared__ float acc[64][2];
+    const int V = C >> 3;                       // 16-byte vectors per pixel
+    const int ppb = 256 / V;                    // pixels per block iteration
+    const int sample = blockIdx.y;
+    const int slabs = gridDim.x;
+    const int per = (P + slabs - 1) / slabs;
+    const int p0 = blockIdx.x * per, p1 = min(P, p0 + per);
+    if (threadIdx.x < 64) { acc[threadIdx.x][0] = 0.f; acc[threadIdx.x][1] = 0.f; }
+    __syncthreads();
+    const int j = threadIdx.x % V, po = threadIdx.x / V;
+    if (po < ppb) {
+        float s[8] = {}, q[8] = {};
+        const bf16* base = x + ((long long)sample * P) * ld + j * 8;
+        for (int p = p0 + po; p < p1; p += ppb) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * ld), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+        }
+        const int cpg = C / G;
+        int g = (j * 8) / cpg;
+        float gs = 0.f, gq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int gk = (j * 8 + k) / cpg;
+            if (gk != g) { atomicAdd(&acc[g][0], gs); atomicAdd(&acc[g][1], gq); g = gk; gs = 0.f; gq = 0.f; }
+            gs += s[k]; gq += q[k];
+        }
+        atomicAdd(&acc[g][0], gs);
+        atomicAdd(&acc[g][1], gq);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&stats[((long long)sample * G + threadIdx.x) * 2 + 0], acc[threadIdx.x][0]);
+        atomicAdd(&stats[((long long)sample * G + threadIdx.x) * 2 + 1], acc[threadIdx.x][1]);
+    }
+}
+
+// y = x * A[c] + B[c] with A = rstd*gamma*(1+scale), B = (beta - mean*rstd*gamma)*(1+scale) + shift
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
+                long long ss_ld, int ss_div, float eps, int silu, bf16* __restrict__ out, long long ldo) {
+    extern __shared__ float coef[];             // [2][C]
+    const int sample = blockIdx.y;
+    const int cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)P * (float)cpg);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sum = stats[((long long)sample * G + g) * 2], sq = stats[((long long)sample * G + g) * 2 + 1];
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        float a = rstd * gamma[c], b = beta[c] - mean * rstd * gamma[c];
+        if (ss) {
+            const float* row = ss + (long long)(sample / ss_div) * ss_ld;
+            const float sc = 1.0f + row[c], sh = row[C + c];
+            a *= sc; b = b * sc + sh;
+        }
+        coef[c] = a; coef[C + c] = b;
+    }
+    __syncthreads();
+    const int V = C >> 3;
+    const int slabs = gridDim.x;
+    const int per = (P + slabs - 1) / slabs;
+    const int p0 = blockIdx.x * per, p1 = min(P, p0 + per);
+    const long long n = (long long)(p1 - p0) * V;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = (int)(i % V);
+        const long long p = (long long)sample * P + p0 + i / V;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + p * ld + j * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float y = fmaf(f[k], coef[j * 8 + k], coef[C + j * 8 + k]);
+            f[k] = silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<bf16x8*>(out + p * ldo + j * 8) = pack8(f);
+    }
+}
+
+// ----------------------------------------------------------------------------- LayerNorm + modulate
+template <int NV>   // D = NV * 128
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ x, long long ld, int M, const float* __restrict__ shift,
+                   const float* __restrict__ scale, long long mod_ld, int rows_per_mod, float eps,
+                   bf16* __restrict__ out, long long ldo) {
+    const int lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const float* xr = x + m * ld;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float D = (float)(NV * 128);
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    const long long mr = (m / rows_per_mod) * mod_ld;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int d = (i * 32 + lane) * 4;
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+        if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + mr + d));
+        if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + mr + d));
+        const float y0 = fmaf(v[i].x * rstd, 1.0f + sc.x, sh.x), y1 = fmaf(v[i].y * rstd, 1.0f + sc.y, sh.y);
+        const float y2 = fmaf(v[i].z * rstd, 1.0f + sc.z, sh.z), y3 = fmaf(v[i].w * rstd, 1.0f + sc.w, sh.w);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + m * ldo + d) = pk;
+    }
+}
+
+}  // namespace
+
+extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, float* stats,
+                                  void* stream) {
+    XD_CHECK_ARG(x && stats && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0 && ld % 8 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(stats, 0, sizeof(float) * 2 * nsamples * groups, st) != cudaSuccess) return XD_ERR_CUDA;
+    int slabs = (2 * 148 + nsamples - 1) / nsamples;
+    const int ppb = 256 / (C / 8);
+    slabs = max(1, min(slabs, (P + ppb * 4 - 1) / (ppb * 4)));
+    gn_stats_kernel<<<dim3(slabs, nsamples), 256, 0, st>>>((const bf16*)x, ld, P, C, groups, stats);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups,
+                                  const float* stats, const float* gamma, const float* beta, const float* scale_shift,
+                                  long long ss_ld, int ss_div, float eps, int silu, void* out, long long ldo,
+                                  void* stream) {
+    XD_CHECK_ARG(x && stats && gamma && beta && out && C % 8 == 0 && C % groups == 0 && ld % 8 == 0 && ldo % 8 == 0);
+    int slabs = (4 * 148 + nsamples - 1) / nsamples;
+    slabs = max(1, min(slabs, (P + 15) / 16));
+    gn_apply_kernel<<<dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
+        (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_layernorm_modulate(const float* x, long long ld, int M, int D, const float* shift,
+                                     const float* scale, long long mod_ld, int rows_per_mod, float eps, void* out,
+                                     long long ldo, void* stream) {
+    XD_CHECK_ARG(x && out && M > 0 && D % 128 == 0 && D <= 1024 && ld % 4 == 0 && ldo % 4 == 0 && mod_ld % 4 == 0);
+    XD_CHECK_ARG(rows_per_mod > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((M + 7) / 8);
+#define XD_LN(NV) ln_modulate_kernel<NV><<<grid, 256, 0, st>>>(x, ld, M, shift, scale, mod_ld, rows_per_mod, eps, (bf16*)out, ldo)
+    switch (D / 128) {
+        case 1: XD_LN(1); break;
+        case 2: XD_LN(2); break;
+        case 3: XD_LN(3); break;
+        case 4: XD_LN(4); break;
+        case 6: XD_LN(6); break;
+        case 8: XD_LN(8); break;
+        default: XD_CHECK_ARG(false && "unsupported D");
+    }
+#undef XD_LN
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}

@@ -1,0 +1,188 @@
+// CUDA-core kernels: (a) bf16 GEMM / conv3x3 with the same epilogue contract as the tcgen05
+// kernels (used to cross-check them on the device and for shapes the tensor-core path does not
+// take: K % 64 != 0), (b) the UNet's first conv (C_in tiny, fp32 NCHW in) and last conv
+// (C_out tiny, fp32 NCHW out), which are bandwidth-bound and not GEMM-shaped.
+#include "common.cuh"
+
+namespace {
+
+// 64x64 output tile, 16-wide k step, 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const bf16* __restrict__ A, long long lda, const bf16* __restrict__ A2, long long lda2, int K2,
+                 const bf16* __restrict__ Wt, long long ldw, int M, int N, int K, Epilogue e) {
+    __shared__ float sA[16][65];
+    __shared__ float sB[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long m0 = (long long)blockIdx.y * 64;
+    const int n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    const int Kt = K + K2;
+    for (int k0 = 0; k0 < Kt; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c = i & 15;
+            const int k = k0 + c;
+            float a = 0.f, b = 0.f;
+            if (m0 + r < M && k < Kt)
+                a = __bfloat162float(k < K ? A[(m0 + r) * lda + k] : A2[(m0 + r) * lda2 + (k - K)]);
+            if (n0 + r < N && k < Kt) b = __bfloat162float(Wt[(long long)(n0 + r) * ldw + k]);
+            sA[c][r] = a;
+            sB[c][r] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; b[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long m = m0 + ty * 4 + i;
+            const int n = n0 + tx * 4 + j;
+            if (m < M && n < N) epi_store(e, epi_value(e, acc[i][j], m, n), m, n);
+        }
+}
+
+// Direct conv3x3 (pad 1) over NHWC bf16 with packed weights [Cout][9*C + Cs]; one thread per output.
+__global__ void conv3x3_simt_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
+                                    const bf16* __restrict__ Xs, long long lds, int Cs,
+                                    const bf16* __restrict__ Wp, int Cout, Epilogue e) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nimg * H * W * Cout;
+    if (idx >= total) return;
+    const int n = (int)(idx % Cout);
+    const long long m = idx / Cout;
+    const int w = (int)(m % W), h = (int)((m / W) % H);
+    const long long img = m / ((long long)W * H);
+    const long long ktot = 9LL * C + Cs;
+    const bf16* wrow = Wp + (long long)n * ktot;
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const bf16* xp = X + ((img * H + hh) * W + ww) * ldx;
+        const bf16* wp = wrow + (long long)tap * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+    }
+    if (Cs) {
+        const bf16* xp = Xs + m * lds;
+        const bf16* wp = wrow + 9LL * C;
+        for (int c = 0; c < Cs; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+    }
+    epi_store(e, epi_value(e, acc, m, n), m, n);
+}
+
+// First conv: x fp32 NCHW (Cin <= 4), w fp32 [Cout][Cin][3][3] -> bf16 NHWC (ld = ldo).
+// One thread per (pixel, 8 output channels).
+__global__ void conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin, int H, int W,
+                                  const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                  bf16* __restrict__ out, long long ldo) {
+    const int cg = Cout / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nimg * H * W * cg;
+    if (idx >= total) return;
+    const int g = (int)(idx % cg);
+    const long long m = idx / cg;
+    const int ww = (int)(m % W), hh = (int)((m / W) % H);
+    const long long img = m / ((long long)W * H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+    for (int c = 0; c < Cin; ++c) {
+        const float* xp = x + (img * Cin + c) * H * W;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+            if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
+            const float v = __ldg(xp + y * W + xx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, __ldg(w + ((long long)(g * 8 + j) * Cin + c) * 9 + tap), acc[j]);
+        }
+    }
+    *reinterpret_cast<bf16x8*>(out + m * ldo + g * 8) = pack8(acc);
+}
+
+// Last conv: bf16 NHWC (C % 8 == 0) -> fp32 NCHW, Cout tiny.  One warp per output pixel.
+__global__ void conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
+                                   const float* __restrict__ w /*[Cout][C][3][3]*/, const float* __restrict__ bias,
+                                   int Cout, float* __restrict__ out) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)nimg * H * W;
+    if (warp >= total) return;
+    const int ww = (int)(warp % W), hh = (int)((warp / W) % H);
+    const long long img = warp / ((long long)W * H);
+    for (int co = 0; co < Cout; ++co) {
+        float acc = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+            if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
+            const bf16* xp = X + ((img * H + y) * W + xx) * ldx;
+            for (int c8 = lane * 8; c8 < C; c8 += 256) {
+                float f[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(xp + c8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(f[j], __ldg(w + ((long long)co * C + c8 + j) * 9 + tap), acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[((img * Cout + co) * H + hh) * W + ww] = acc + (bias ? bias[co] : 0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                                 long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                                 int gate_rows, long long gate_ld, const void* residual, int res_dtype,
+                                 long long res_ld, void* out, int out_dtype, long long out_ld, void* stream) {
+    XD_CHECK_ARG(A && Wt && out && M > 0 && N > 0 && K > 0 && (A2 != nullptr) == (K2 > 0));
+    XD_CHECK_ARG(!gate || gate_rows > 0);
+    Epilogue e{bias, gate, residual, out, gate_ld, res_ld, out_ld, act, gate_rows > 0 ? gate_rows : 1, res_dtype, out_dtype};
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)A, lda, (const bf16*)A2, lda2, K2,
+                                                             (const bf16*)Wt, ldw, M, N, K, e);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_conv3x3_bf16_simt(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                                    long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                                    const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                                    long long out_ld, void* stream) {
+    XD_CHECK_ARG(X && Wp && out && nimg > 0 && (Xs != nullptr) == (Cs > 0));
+    Epilogue e{bias, nullptr, residual, out, 0, res_ld, out_ld, act, 1, res_dtype, out_dtype};
+    const long long total = (long long)nimg * H * W * Cout;
+    conv3x3_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)X, ldx, nimg, H, W, C, (const bf16*)Xs, lds, Cs, (const bf16*)Wp, Cout, e);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, int W, const float* w,
+                                      const float* bias, int Cout, void* out, long long ldo, void* stream) {
+    XD_CHECK_ARG(x && w && out && Cout % 8 == 0 && ldo % 8 == 0);
+    const long long total = (long long)nimg * H * W * (Cout / 8);
+    conv3x3_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, nimg, Cin, H, W, w, bias,
+                                                                                        Cout, (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, int H, int W, int C, const float* w,
+                                       const float* bias, int Cout, float* out, void* stream) {
+    XD_CHECK_ARG(X && w && out && C % 8 == 0 && ldx % 8 == 0);
+    const long long warps = (long long)nimg * H * W;
+    conv3x3_out_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)X, ldx, nimg, H, W, C, w, bias, Cout, out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}

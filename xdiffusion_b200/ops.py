@@ -1,0 +1,357 @@
+"""torch custom ops (namespace ``xdb200``) over the C ABI in include/xdb200.h.
+
+Every op is an out-variant over CUDA tensors that forwards raw pointers, sizes, strides and the
+current CUDA stream to libxdb200.so.  They are registered for the CUDA dispatch key only: calling
+one with CPU tensors raises (there is no CPU or eager-PyTorch fallback).  The functional helpers
+at the bottom allocate outputs with torch's caching allocator, which keeps the whole forward
+capturable in a CUDA graph.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+MODE_ANCESTRAL, MODE_DDIM, MODE_EULER = 0, 1, 2
+
+# "tc": tcgen05/TMEM/TMA kernels (product path).  "simt": CUDA-core twins (device cross-check only).
+MATMUL_BACKEND = os.environ.get("XDB200_MATMUL", "tc")
+LAUNCHES = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"xdb200: unsupported dtype {t.dtype}")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.XdError("xdb200 ops take CUDA tensors only (no CPU fallback)")
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+_defs = []
+
+
+def _op(schema):
+    def deco(fn):
+        _defs.append((schema, fn))
+        return fn
+    return deco
+
+
+# ------------------------------------------------------------------------------------ contractions
+@_op("gemm(Tensor a, Tensor? a2, Tensor w, Tensor? bias, int act, Tensor? gate, int gate_rows, "
+     "Tensor? residual, Tensor(a!) out, int force_bn) -> ()")
+def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):
+    _cuda(a, a2, w, bias, gate, residual, out)
+    M, K = a.shape
+    K2 = 0 if a2 is None else a2.shape[1]
+    N = w.shape[0]
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K + K2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1 and out.shape == (M, N)
+    args = [_p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K2, _p(w), w.stride(0), M, N, K,
+            _p(bias), act, _p(gate), gate_rows, 0 if gate is None else gate.stride(0), _p(residual),
+            0 if residual is None else _dt(residual), 0 if residual is None else residual.stride(0),
+            _p(out), _dt(out), out.stride(0)]
+    if MATMUL_BACKEND == "tc" and K % 64 == 0 and K2 % 64 == 0:
+        _lib.check(_lib.lib().xd_gemm_bf16_tc(*args, force_bn, _stream()), "xd_gemm_bf16_tc")
+    else:
+        _lib.check(_lib.lib().xd_gemm_bf16_simt(*args, _stream()), "xd_gemm_bf16_simt")
+    _count()
+
+
+@_op("conv3x3(Tensor x, Tensor? xs, Tensor wp, Tensor? bias, int act, Tensor? residual, Tensor(a!) out, "
+     "int force_bn) -> ()")
+def _conv3x3(x, xs, wp, bias, act, residual, out, force_bn):
+    """x [nimg,H,W,C] bf16 NHWC view (channel stride 1, dense pixels, pixel stride >= C)."""
+    _cuda(x, xs, wp, bias, residual, out)
+    nimg, H, W, C = x.shape
+    Cs = 0 if xs is None else xs.shape[3]
+    Cout = wp.shape[0]
+    assert wp.shape[1] == 9 * C + Cs and wp.is_contiguous()
+    for t in (x, xs, out, residual):
+        if t is not None:
+            assert t.stride(3) == 1 and t.stride(1) == W * t.stride(2) and t.stride(0) == H * t.stride(1)
+    args = [_p(x), x.stride(2), nimg, H, W, C, _p(xs), 0 if xs is None else xs.stride(2), Cs, _p(wp), Cout,
+            _p(bias), act, _p(residual), 0 if residual is None else _dt(residual),
+            0 if residual is None else residual.stride(2), _p(out), _dt(out), out.stride(2)]
+    if MATMUL_BACKEND == "tc":
+        _lib.check(_lib.lib().xd_conv3x3_bf16_tc(*args, force_bn, _stream()), "xd_conv3x3_bf16_tc")
+    else:
+        _lib.check(_lib.lib().xd_conv3x3_bf16_simt(*args, _stream()), "xd_conv3x3_bf16_simt")
+    _count()
+
+
+@_op("conv3x3_in(Tensor x, Tensor w, Tensor? bias, Tensor(a!) out) -> ()")
+def _conv3x3_in(x, w, bias, out):
+    _cuda(x, w, bias, out)
+    nimg, Cin, H, W = x.shape
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    _lib.check(_lib.lib().xd_conv3x3_in_f32_nchw(_p(x), nimg, Cin, H, W, _p(w), _p(bias), w.shape[0], _p(out),
+                                                 out.stride(2), _stream()), "xd_conv3x3_in_f32_nchw")
+    _count()
+
+
+@_op("conv3x3_out(Tensor x, Tensor w, Tensor? bias, Tensor(a!) out) -> ()")
+def _conv3x3_out(x, w, bias, out):
+    _cuda(x, w, bias, out)
+    nimg, H, W, C = x.shape
+    assert out.is_contiguous() and w.is_contiguous() and out.dtype == torch.float32
+    _lib.check(_lib.lib().xd_conv3x3_out_f32_nchw(_p(x), x.stride(2), nimg, H, W, C, _p(w), _p(bias), w.shape[0],
+                                                  _p(out), _stream()), "xd_conv3x3_out_f32_nchw")
+    _count()
+
+
+@_op("attention(Tensor q, Tensor k, Tensor v, Tensor(a!) o, float scale, Tensor? relk, int scramble, int o_cs) -> ()")
+def _attention(q, k, v, o, scale, relk, scramble, o_cs):
+    """q [B,H,Tq,64], k/v [B,H,Tk,64], o [B,H,Tq,64]: arbitrary-stride bf16 views (last stride 1)."""
+    _cuda(q, k, v, o, relk)
+    B, H, Tq, D = q.shape
+    Tk = k.shape[2]
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(3) == 1
+    _lib.check(_lib.lib().xd_attention_bf16(
+        _p(q), q.stride(0), q.stride(1), q.stride(2), _p(k), k.stride(0), k.stride(1), k.stride(2),
+        _p(v), v.stride(0), v.stride(1), v.stride(2), _p(o), o.stride(0), o.stride(1), o.stride(2),
+        B, H, Tq, Tk, D, scale, _p(relk), scramble, o_cs, _stream()), "xd_attention_bf16")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ norms
+@_op("groupnorm(Tensor x, Tensor gamma, Tensor beta, Tensor? scale_shift, int ss_div, float eps, int silu, "
+     "Tensor(a!) stats, Tensor(b!) out) -> ()")
+def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, stats, out):
+    """x [nsamples, P, C] bf16 view (channel stride 1, dense rows); 32 groups."""
+    _cuda(x, gamma, beta, scale_shift, stats, out)
+    ns, P, C = x.shape
+    assert x.stride(2) == 1 and x.stride(0) == P * x.stride(1) and out.stride(2) == 1
+    assert out.stride(0) == P * out.stride(1) and stats.numel() >= ns * 64 and stats.dtype == torch.float32
+    l = _lib.lib()
+    _lib.check(l.xd_groupnorm_stats(_p(x), x.stride(1), ns, P, C, 32, _p(stats), _stream()), "xd_groupnorm_stats")
+    _lib.check(l.xd_groupnorm_apply(_p(x), x.stride(1), ns, P, C, 32, _p(stats), _p(gamma), _p(beta),
+                                    _p(scale_shift), 0 if scale_shift is None else scale_shift.stride(0), ss_div,
+                                    eps, silu, _p(out), out.stride(1), _stream()), "xd_groupnorm_apply")
+    _count(3)
+
+
+@_op("layernorm_modulate(Tensor x, Tensor? shift, Tensor? scale, int rows_per_mod, float eps, Tensor(a!) out) -> ()")
+def _layernorm_modulate(x, shift, scale, rows_per_mod, eps, out):
+    _cuda(x, shift, scale, out)
+    M, D = x.shape
+    mod_ld = 0
+    for t in (shift, scale):
+        if t is not None:
+            assert t.stride(-1) == 1 and t.dtype == torch.float32
+            mod_ld = t.stride(0)
+    if shift is not None and scale is not None:
+        assert shift.stride(0) == scale.stride(0)
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and out.dtype == torch.bfloat16
+    _lib.check(_lib.lib().xd_layernorm_modulate(_p(x), x.stride(0), M, D, _p(shift), _p(scale), mod_ld,
+                                                rows_per_mod, eps, _p(out), out.stride(0), _stream()),
+               "xd_layernorm_modulate")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ small kernels
+@_op("timestep_embed(Tensor t, Tensor freq, int mode, float max_time, float clip_lo, float clip_hi, int order, "
+     "Tensor(a!) out) -> ()")
+def _timestep_embed(t, freq, mode, max_time, clip_lo, clip_hi, order, out):
+    _cuda(t, freq, out)
+    assert t.dtype in (torch.int64, torch.float32) and t.is_contiguous() and out.is_contiguous()
+    of, ob = (_p(out), None) if out.dtype == torch.float32 else (None, _p(out))
+    _lib.check(_lib.lib().xd_timestep_embed(_p(t), int(t.dtype == torch.int64), t.shape[0], _p(freq),
+                                            freq.shape[0], mode, max_time, clip_lo, clip_hi, order, of, ob,
+                                            _stream()), "xd_timestep_embed")
+    _count()
+
+
+@_op("act_cast(Tensor x, int act, Tensor(a!) out) -> ()")
+def _act_cast(x, act, out):
+    _cuda(x, out)
+    assert x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
+    _lib.check(_lib.lib().xd_act_cast(_p(x), _dt(x), _p(out), _dt(out), act, x.numel(), _stream()), "xd_act_cast")
+    _count()
+
+
+@_op("class_combine(Tensor? table, Tensor? labels, Tensor temb, Tensor(a!)? c_out, Tensor(b!)? silu_out) -> ()")
+def _class_combine(table, labels, temb, c_out, silu_out):
+    _cuda(table, labels, temb, c_out, silu_out)
+    B, D = temb.shape
+    assert temb.is_contiguous() and (labels is None or labels.dtype == torch.int64)
+    _lib.check(_lib.lib().xd_class_combine(_p(table), _p(labels), _p(temb), B, D, _p(c_out), _p(silu_out),
+                                           _stream()), "xd_class_combine")
+    _count()
+
+
+@_op("patchify(Tensor x, int p, Tensor(a!) out) -> ()")
+def _patchify(x, p, out):
+    _cuda(x, out)
+    B, C, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32 and out.is_contiguous() and out.dtype == torch.bfloat16
+    _lib.check(_lib.lib().xd_patchify(_p(x), B, C, H, W, p, _p(out), _stream()), "xd_patchify")
+    _count()
+
+
+@_op("unpatchify(Tensor y, int p, Tensor(a!) out) -> ()")
+def _unpatchify(y, p, out):
+    _cuda(y, out)
+    B, C, H, W = out.shape
+    assert out.is_contiguous() and y.dtype == torch.float32 and y.stride(1) == 1
+    _lib.check(_lib.lib().xd_unpatchify(_p(y), y.stride(0), B, C, H, W, p, _p(out), _stream()), "xd_unpatchify")
+    _count()
+
+
+@_op("add_rows_periodic(Tensor a, Tensor b, int period, Tensor(a!) out) -> ()")
+def _add_rows_periodic(a, b, period, out):
+    _cuda(a, b, out)
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
+    _lib.check(_lib.lib().xd_add_rows_periodic(_p(a), _p(b), a.shape[0], a.shape[1], period, _p(out), _stream()),
+               "xd_add_rows_periodic")
+    _count()
+
+
+@_op("add_table(Tensor a, Tensor tab, Tensor(a!) out) -> ()")
+def _add_table(a, tab, out):
+    _cuda(a, tab, out)
+    G, C = tab.shape
+    R = a.shape[0]
+    assert a.is_contiguous() and tab.is_contiguous() and out.is_contiguous() and a.shape[1] == C
+    _lib.check(_lib.lib().xd_add_table(_p(a), _p(tab), G, R, C, _p(out), _stream()), "xd_add_table")
+    _count()
+
+
+@_op("avgpool2x2(Tensor x, Tensor(a!) out) -> ()")
+def _avgpool2x2(x, out):
+    _cuda(x, out)
+    nimg, H, W, C = x.shape
+    _lib.check(_lib.lib().xd_avgpool2x2_nhwc(_p(x), x.stride(2), nimg, H, W, C, _p(out), out.stride(2), _stream()),
+               "xd_avgpool2x2_nhwc")
+    _count()
+
+
+@_op("upsample2x(Tensor x, Tensor(a!) out) -> ()")
+def _upsample2x(x, out):
+    _cuda(x, out)
+    nimg, H, W, C = x.shape
+    _lib.check(_lib.lib().xd_upsample2x_nhwc(_p(x), x.stride(2), nimg, H, W, C, _p(out), out.stride(2), _stream()),
+               "xd_upsample2x_nhwc")
+    _count()
+
+
+@_op("copy_rows(Tensor x, Tensor(a!) out) -> ()")
+def _copy_rows(x, out):
+    _cuda(x, out)
+    rows, C = x.shape
+    _lib.check(_lib.lib().xd_copy_rows_bf16(_p(x), x.stride(0), rows, C, _p(out), out.stride(0), _stream()),
+               "xd_copy_rows_bf16")
+    _count()
+
+
+@_op("cfg_combine(Tensor cond, Tensor uncond, float w, Tensor(a!) out) -> ()")
+def _cfg_combine(cond, uncond, w, out):
+    _cuda(cond, uncond, out)
+    assert cond.is_contiguous() and uncond.is_contiguous() and out.is_contiguous()
+    _lib.check(_lib.lib().xd_cfg_combine(_p(cond), _p(uncond), w, _p(out), cond.numel(), _stream()),
+               "xd_cfg_combine")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ sampler step
+@_op("sampler_step(int mode, int form, int pred_v, Tensor x, Tensor o, Tensor? z, int z_step_stride, "
+     "Tensor(a!) out, Tensor coefs, Tensor? idx_dev, int idx_host, int threshold, int thr_k, float thr_w, "
+     "float thr_c, int seed) -> ()")
+def _sampler_step(mode, form, pred_v, x, o, z, z_step_stride, out, coefs, idx_dev, idx_host, threshold, thr_k,
+                  thr_w, thr_c, seed):
+    _cuda(x, o, z, out, coefs, idx_dev)
+    assert x.is_contiguous() and o.is_contiguous() and out.is_contiguous() and coefs.is_contiguous()
+    assert x.dtype == torch.float32 and o.dtype == torch.float32 and coefs.dtype == torch.float32
+    assert idx_dev is None or idx_dev.dtype == torch.int32
+    n = x.numel()
+    _lib.check(_lib.lib().xd_sampler_step(mode, form, pred_v, _p(x), _p(o), _p(z), z_step_stride, _p(out),
+                                          _p(coefs), _p(idx_dev), idx_host, n, n // x.shape[0], threshold, thr_k,
+                                          thr_w, thr_c, seed, _stream()), "xd_sampler_step")
+    _count()
+
+
+@_op("schedule_advance(Tensor(a!) idx_dev, int set_to, Tensor? tab_i64, Tensor? tab_a, Tensor? tab_b, "
+     "Tensor(b!)? out_i64, Tensor(c!)? out_a, Tensor(d!)? out_b, int B) -> ()")
+def _schedule_advance(idx_dev, set_to, tab_i64, tab_a, tab_b, out_i64, out_a, out_b, B):
+    _cuda(idx_dev, tab_i64, tab_a, tab_b, out_i64, out_a, out_b)
+    _lib.check(_lib.lib().xd_schedule_advance(_p(idx_dev), set_to, _p(tab_i64), _p(tab_a), _p(tab_b), _p(out_i64),
+                                              _p(out_a), _p(out_b), B, _stream()), "xd_schedule_advance")
+    _count()
+
+
+@_op("unnormalize(Tensor x, Tensor(a!) out) -> ()")
+def _unnormalize(x, out):
+    _cuda(x, out)
+    assert x.is_contiguous() and out.is_contiguous()
+    _lib.check(_lib.lib().xd_unnormalize(_p(x), _p(out), x.numel(), _stream()), "xd_unnormalize")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ registration
+_library = torch.library.Library("xdb200", "DEF")
+for _schema, _fn in _defs:
+    _library.define(_schema)
+    _library.impl(_schema.split("(", 1)[0], _fn, "CUDA")
+_ops = torch.ops.xdb200
+
+
+# ------------------------------------------------------------------------------------ functional helpers
+def linear(a, w, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16, gate=None, gate_rows=1, residual=None,
+           out=None, a2=None, force_bn=0):
+    """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K(+K2)]."""
+    if out is None:
+        out = torch.empty((a.shape[0], w.shape[0]), device=a.device, dtype=out_dtype)
+    _ops.gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn)
+    return out
+
+
+def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, force_bn=0):
+    if out is None:
+        out = torch.empty(x.shape[:3] + (wp.shape[0],), device=x.device, dtype=torch.bfloat16)
+    _ops.conv3x3(x, xs, wp, bias, act, residual, out, force_bn)
+    return out
+
+
+def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, out=None):
+    """x [nsamples, P, C] bf16."""
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(x.shape[0] * 64, device=x.device, dtype=torch.float32)
+    _ops.groupnorm(x, gamma, beta, scale_shift, ss_div, eps, int(silu), stats, out)
+    return out
+
+
+def layernorm_modulate(x, shift, scale, rows_per_mod, eps=1e-6):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _ops.layernorm_modulate(x, shift, scale, rows_per_mod, eps, out)
+    return out
+
+
+def attention(q, k, v, scale, out=None, relk=None, scramble=False, o_cs=0):
+    if out is None:
+        B, H, Tq, D = q.shape
+        out = torch.empty((B, Tq, H, D), device=q.device, dtype=torch.bfloat16).permute(0, 2, 1, 3)
+    _ops.attention(q, k, v, out, float(scale), relk, int(scramble), o_cs)
+    return out
