@@ -131,7 +131,7 @@ int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float*
                     long long z_step_stride, float* out, const float* coefs, const int* idx_dev, int idx_host,
                     long long n_total, int n_per_sample, int threshold, int thr_k, float thr_w, float thr_c,
                     unsigned long long seed, void* stream);
-/* *idx_dev <- set_to (>= 0) or *idx_dev - 1; then out_*[b] = tab_*[*idx_dev] for b < B
+/* *idx_dev <- set_to (>= 0), *idx_dev - 1 (set_to == -1) or unchanged (-2); then out_*[b] = tab_*[*idx_dev], b < B
  * (the per-step `t = torch.tensor([idx]*B)` / logsnr lookups of diffusion/ddpm.py:928-955). */
 int xd_schedule_advance(int* idx_dev, int set_to, const long long* tab_i64, const float* tab_f32a,
                         const float* tab_f32b, long long* out_i64, float* out_f32a, float* out_f32b, int B,

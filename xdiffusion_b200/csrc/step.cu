@@ -170,7 +170,7 @@ __global__ void advance_kernel(int* idx, int set_to, const long long* tab_i64, c
                                const float* tab_f32b, long long* out_i64, float* out_f32a, float* out_f32b, int B) {
     __shared__ int s_i;
     if (threadIdx.x == 0) {
-        int i = set_to >= 0 ? set_to : *idx - 1;
+        int i = set_to >= 0 ? set_to : (set_to == -1 ? *idx - 1 : *idx);   // -2: refresh outputs only
         if (i < 0) i = 0;
         s_i = i;
     }

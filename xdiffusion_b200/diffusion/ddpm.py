@@ -1,0 +1,333 @@
+"""``GaussianDiffusion_DDPM``: the config-driven diffusion model whose ``sample()`` is the hot path.
+
+Drop-in for ``xdiffusion.diffusion.ddpm.GaussianDiffusion_DDPM`` (reference: diffusion/ddpm.py:40-144,
+544-669, 795-987): same constructor, ``sample()`` signature and return value, ``predict_score``,
+``process_input``, accessors, ``load_checkpoint`` and ``state_dict`` layout (``_score_network.*`` +
+``_noise_scheduler.*``).  The reverse-process loop runs entirely on the device: the per-step
+network inputs and the loop index live in device memory, one step (score network + fused sampler
+step + schedule advance) is captured in a CUDA graph and replayed ``num_sampling_steps`` times.
+Training (``forward`` / ``loss_on_batch``) is out of scope.
+"""
+from enum import Enum
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .. import ops
+from ..samplers.base import ReverseProcessSampler
+from ..utils import (DotConfig, get_obj_from_str, instantiate_from_config, normalize_to_neg_one_to_one,
+                     unnormalize_to_zero_to_one)
+
+
+class PredictionType(Enum):
+    EPSILON = "epsilon"
+    V = "v"
+    RECTIFIED_FLOW = "rectified_flow"
+
+
+class DiffusionModel(torch.nn.Module):
+    """Interface kept from the reference (diffusion/__init__.py:19-98)."""
+
+
+class GaussianDiffusion_DDPM(DiffusionModel):
+    def __init__(self, config: DotConfig, vae: Optional[torch.nn.Module] = None):
+        super().__init__()
+        self._config = config
+        d = config.diffusion
+        try:
+            self._prediction_type = PredictionType(d.parameterization)
+        except ValueError:
+            raise NotImplementedError(f"Parameterization {d.parameterization} not implemented.")
+        self._score_network = instantiate_from_config(d.score_network, use_config_struct=True)
+        params = d.score_network.params
+        self._is_learned_sigma = params.is_learned_sigma
+        self._is_class_conditional = params.is_class_conditional if "is_class_conditional" in params else False
+        self._num_classes = config.data.num_classes
+        self._unconditional_guidance_probability = d.classifier_free_guidance.unconditional_guidance_probability
+        self._classifier_free_guidance = d.classifier_free_guidance.classifier_free_guidance
+        self._noise_scheduler = instantiate_from_config(d.noise_scheduler.to_dict())
+        self._context_preprocessors = torch.nn.ModuleList(
+            [instantiate_from_config(c) for c in d.context_preprocessing])
+        self._input_preprocessor = instantiate_from_config(d.input_preprocessing.to_dict())
+        self._unconditional_context = instantiate_from_config(d.classifier_free_guidance.unconditional_context.to_dict())
+        self._reverse_process_sampler: ReverseProcessSampler = instantiate_from_config(d.sampling.to_dict())
+        self._sde = instantiate_from_config(d.sde.to_dict()) if "sde" in d else None
+        self._normalize = get_obj_from_str(config.data.normalize) if "normalize" in config.data \
+            else normalize_to_neg_one_to_one
+        self._unnormalize = get_obj_from_str(config.data.unnormalize) if "unnormalize" in config.data \
+            else unnormalize_to_zero_to_one
+        if vae is not None or "latent_encoder" in d:
+            raise NotImplementedError("latent (VAE) diffusion is outside the covered hot path")
+        self._latent_encoder = None
+        self._coef_cache = {}
+        self._loops = {}
+
+    # ------------------------------------------------------------------ accessors (reference API)
+    def models(self):
+        return [self]
+
+    def sde(self):
+        return self._sde
+
+    def config(self) -> DotConfig:
+        return self._config
+
+    def is_learned_sigma(self) -> bool:
+        return self._is_learned_sigma
+
+    def noise_scheduler(self):
+        return self._noise_scheduler
+
+    def classifier_free_guidance(self) -> float:
+        return self._classifier_free_guidance
+
+    def prediction_type(self) -> PredictionType:
+        return self._prediction_type
+
+    def forward(self, images, context: Dict, **kwargs):
+        raise NotImplementedError("training (loss_on_batch) is outside the sampling hot path")
+
+    loss_on_batch = forward
+
+    def process_input(self, x: torch.Tensor, context: Dict) -> torch.Tensor:
+        return self._input_preprocessor(x=x, context=context, noise_scheduler=self._noise_scheduler)
+
+    def predict_score(self, x: torch.Tensor, context: Dict) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        return self._score_network(x, context=context)
+
+    def load_checkpoint(self, checkpoint_path: str, strict: bool = False):
+        """reference: diffusion/ddpm.py:795-814"""
+        checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        state_dict = checkpoint["model_state_dict"]
+        if hasattr(self._score_network, "load_model_weights"):
+            ns = "_score_network."
+            self._score_network.load_model_weights({k[len(ns):]: v for k, v in state_dict.items() if k.startswith(ns)})
+        else:
+            missing, _ = self.load_state_dict(state_dict, strict=strict)
+            for k in missing:
+                assert "temporal" in k or "motion_module" in k, k
+
+    # ------------------------------------------------------------------ schedule glue for the fused kernels
+    def step_coefficients(self, sampler_name: str, num_sampling_steps: int):
+        """Device copy of the per-loop-index coefficient rows for csrc/step.cu (cached)."""
+        dev = next(self.parameters()).device
+        key = (sampler_name, num_sampling_steps, str(dev))
+        if key not in self._coef_cache:
+            if sampler_name == "euler":
+                N = self._sde.N
+                c = torch.zeros(self._noise_scheduler.steps(), 8)
+                c[:, 0] = 1.0 / N            # python double -> fp32, as `pred_sigma * dt` (rectified_flow.py:80)
+                form = 0
+            else:
+                c, form = self._noise_scheduler.step_coefficients(self._prediction_type.value, num_sampling_steps,
+                                                                  sampler_name)
+            self._coef_cache[key] = (c.to(dev).contiguous(), form)
+        return self._coef_cache[key]
+
+    def dynamic_threshold(self, n_per_sample: int):
+        """(floor(rank), frac(rank), c) with torch.quantile's fp32 rank arithmetic, or None
+        (reference: samplers/ancestral.py:252-267, utils.py:379-396)."""
+        d = self._config.diffusion
+        if "dynamic_thresholding" in d and d.dynamic_thresholding.enable:
+            ranks = torch.tensor(d.dynamic_thresholding.p, dtype=torch.float32) * (n_per_sample - 1)
+            lo = ranks.floor()
+            return int(lo), float(ranks - lo), float(d.dynamic_thresholding.c)
+        return None
+
+    def _time_tables(self, N: int, device):
+        """Per-loop-index network inputs (context["timestep"], logsnr_s/t) as device tables."""
+        if self._prediction_type == PredictionType.RECTIFIED_FLOW:
+            from ..samplers.rectified_flow import AncestralSampler as Flow
+            sde = self._sde
+            # python-double times rounded once to fp32, like `torch.ones(B) * num_t` (rectified_flow.py:56-57)
+            t = torch.tensor([Flow.network_time(i, sde.N, sde.T) for i in range(self._noise_scheduler.steps())],
+                             dtype=torch.float64).to(torch.float32)
+            tabs = {"timestep": t}
+        else:
+            tabs = self._noise_scheduler.network_time_tables(N)
+        return {k: v.to(device).contiguous() for k, v in tabs.items()}
+
+    # ------------------------------------------------------------------ sampling
+    def _output_shape(self, num_samples: int):
+        s = self._config.diffusion.sampling
+        size = s.output_spatial_size
+        hw = [size[0], size[1]] if isinstance(size, list) else [size, size]
+        if "output_frames" in s:
+            return (num_samples, s.output_channels, s.output_frames, hw[0], hw[1])
+        return (num_samples, s.output_channels, hw[0], hw[1])
+
+    def sample(self, context: Optional[Dict] = None, num_samples: int = 16, guidance_fn: Optional[Callable] = None,
+               classifier_free_guidance: Optional[float] = None, num_sampling_steps: Optional[int] = None,
+               sampler: Optional[ReverseProcessSampler] = None, initial_noise: Optional[torch.Tensor] = None,
+               context_preprocessor: Optional[torch.nn.Module] = None, noise: Optional[torch.Tensor] = None,
+               use_cuda_graph: bool = True, seed: Optional[int] = None,
+               ) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
+        """Same contract as the reference's ``sample()`` (diffusion/ddpm.py:544-669).  Extras:
+        ``noise`` [N, *shape] injects the per-step Gaussian noise (row = loop index) for parity runs,
+        ``seed`` keys the in-kernel Philox noise otherwise, ``use_cuda_graph=False`` runs the loop eagerly."""
+        if guidance_fn is not None:
+            raise NotImplementedError("classifier guidance needs autograd through the network (out of scope)")
+        shape = self._output_shape(num_samples)
+        device = next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("xdiffusion_b200 runs on CUDA (sm_100a) only; move the model with .to('cuda')")
+        self.eval()
+        context = {} if context is None else context
+        if classifier_free_guidance is not None:
+            unconditional_context = self._unconditional_context(context)
+            if context_preprocessor is not None:
+                unconditional_context = context_preprocessor(unconditional_context, device)
+            for pre in self._context_preprocessors:
+                unconditional_context = pre(unconditional_context, device)
+        else:
+            unconditional_context = None
+        if "super_resolution" in self._config:
+            raise NotImplementedError("cascade / super-resolution stages are a 'next' row (SURVEY 8f)")
+        if context_preprocessor is not None:
+            context = context_preprocessor(context, device)
+        for pre in self._context_preprocessors:
+            context = pre(context, device)
+        steps = num_sampling_steps if num_sampling_steps is not None else self._noise_scheduler.steps()
+        latents, intermediates = self._p_sample_loop(
+            shape, context=context, unconditional_context=unconditional_context, guidance_fn=guidance_fn,
+            classifier_free_guidance=classifier_free_guidance, num_sampling_steps=steps, sampler=sampler,
+            initial_noise=initial_noise, noise=noise, use_cuda_graph=use_cuda_graph, seed=seed)
+        samples = self._unnormalize(latents)
+        self.train()                         # the reference leaves the module in train mode (ddpm.py:668)
+        return samples, intermediates
+
+    def _p_sample_loop(self, shape, context: Dict, unconditional_context: Optional[Dict], num_sampling_steps: int,
+                       guidance_fn=None, classifier_free_guidance: Optional[float] = None,
+                       sampler: Optional[ReverseProcessSampler] = None, initial_noise: Optional[torch.Tensor] = None,
+                       save_intermediate_outputs: bool = False, noise: Optional[torch.Tensor] = None,
+                       use_cuda_graph: bool = True, seed: Optional[int] = None):
+        device = next(self.parameters()).device
+        if "video_mask" in context:
+            raise NotImplementedError("video_mask blending (autoregressive extension) is a 'next' row")
+        s = self._config.diffusion.sampling
+        initial_timestep = s.initial_timestep if "initial_timestep" in s else 0
+        if initial_timestep != 0:
+            raise NotImplementedError("initial_timestep != 0")
+        sampler = sampler if sampler is not None else self._reverse_process_sampler
+        N, B = num_sampling_steps, shape[0]
+        x0 = initial_noise.to(device=device, dtype=torch.float32) if initial_noise is not None \
+            else torch.randn(shape, device=device)
+        if noise is not None:
+            noise = noise.to(device=device, dtype=torch.float32).contiguous()
+            assert noise.shape == (N,) + tuple(shape), "noise must be [num_sampling_steps, *shape]"
+        seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+        key = (tuple(shape), N, id(sampler), classifier_free_guidance, use_cuda_graph,
+               _ctx_signature(context), _ctx_signature(unconditional_context))
+        loop = self._loops.get(key) if noise is None else None
+        if loop is None:
+            loop = _DeviceLoop(self, sampler, tuple(shape), N, context, unconditional_context,
+                               classifier_free_guidance)
+            if noise is None:
+                self._loops = {key: loop}        # keep one captured loop alive (its buffers are static)
+        else:
+            loop.load_context(context, unconditional_context)
+        x = loop.run(x0, noise, seed, use_cuda_graph)
+        return x, []
+
+
+def _ctx_signature(ctx):
+    if ctx is None:
+        return None
+    return tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in ctx.items() if torch.is_tensor(v)))
+
+
+class _DeviceLoop:
+    """Everything one reverse-process step needs, resident on the device, so that the step can be
+    captured once and replayed: x_t, the loop index, the per-step network inputs (refreshed from
+    host-built tables by xd_schedule_advance) and static copies of the conditioning tensors."""
+
+    def __init__(self, model, sampler, shape, N, context, uncond_context, cfg):
+        self.model, self.sampler, self.shape, self.N = model, sampler, shape, N
+        dev = next(model.parameters()).device
+        B = shape[0]
+        self.cfg = cfg
+        self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.tabs = model._time_tables(N, dev)
+        t = self.tabs["timestep"]
+        self.timestep = torch.empty(B, dtype=t.dtype, device=dev)
+        self.logsnr_t = torch.empty(B, dtype=torch.float32, device=dev) if "logsnr_t" in self.tabs else None
+        self.logsnr_s = torch.empty(B, dtype=torch.float32, device=dev) if "logsnr_s" in self.tabs else None
+        self.x = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.context = self._static(context, dev)
+        self.uncond = self._static(uncond_context, dev) if uncond_context is not None else None
+        self.noise = None
+        self.seed = 0
+        self.graph = None
+
+    @staticmethod
+    def _static(ctx, dev):
+        return {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in ctx.items()}
+
+    def load_context(self, context, uncond_context):
+        """Refresh the static conditioning buffers of an already captured loop."""
+        for static, new in ((self.context, context), (self.uncond, uncond_context)):
+            if static is None:
+                continue
+            for k, v in new.items():
+                if torch.is_tensor(v):
+                    static[k].copy_(v)
+                else:
+                    static[k] = v
+
+    def _advance(self, set_to):
+        t = self.tabs["timestep"]
+        ti, tf = (t, None) if t.dtype == torch.int64 else (None, t)
+        oi, of = (self.timestep, None) if t.dtype == torch.int64 else (None, self.timestep)
+        torch.ops.xdb200.schedule_advance(self.idx, set_to, ti, tf, self.tabs.get("logsnr_t"), oi, of, self.logsnr_t,
+                                          self.shape[0])
+        if self.logsnr_s is not None:
+            torch.ops.xdb200.schedule_advance(self.idx, -2, None, self.tabs["logsnr_s"], None, None, self.logsnr_s,
+                                              None, self.shape[0])
+
+    def _ctx(self, base):
+        c = dict(base)
+        c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep, self.idx, self.N
+        if self.logsnr_t is not None:
+            c["logsnr_t"], c["logsnr_s"] = self.logsnr_t, self.logsnr_s
+        return c
+
+    def _step(self):
+        c = self._ctx(self.context)
+        c["out"], c["seed"] = self.x, self.seed
+        if self.noise is not None:
+            c["noise"] = self.noise
+        u = self._ctx(self.uncond) if self.uncond is not None else None
+        self.sampler.p_sample(self.x, context=c, unconditional_context=u, diffusion_model=self.model,
+                              classifier_free_guidance=self.cfg)
+        self._advance(-1)
+
+    def run(self, x0, noise, seed, use_graph):
+        self.noise, self.seed = noise, seed
+        self.x.copy_(x0)
+        self._advance(self.N - 1)
+        if not use_graph:
+            for _ in range(self.N):
+                self._step()
+            return self.x.clone()
+        if self.graph is not None and noise is None:
+            for _ in range(self.N):
+                self.graph.replay()
+            return self.x.clone()
+        # warm-up (lazy kernel attribute setup, weight repacks, allocator pools) on a side stream,
+        # then restore the state the warm-up step consumed
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.x.copy_(x0)
+        self._advance(self.N - 1)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        # capture does not execute: state is still (x0, N-1)
+        for _ in range(self.N):
+            g.replay()
+        self.graph = g
+        return self.x.clone()

@@ -1,0 +1,151 @@
+"""Attention blocks on the xdb200 kernels.  Parameter names / constructor arguments follow the
+reference (xdiffusion/layers/attention.py) for YAML + checkpoint compatibility."""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops
+from .utils import ContextBlock, Packed, bf16_weight, zero_module
+
+
+class MultiHeadSelfAttention(torch.nn.Module, Packed):
+    """DiT / PixArt self-attention over token rows: qkv [Q|K|V]-major, softmax(q k^T / sqrt(d)) v, proj
+    (reference: attention.py:313-380, unfused branch)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = False, **kwargs):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = torch.nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = torch.nn.Linear(dim, dim)
+
+    def forward(self, x_bf16, tokens: int, **epilogue):
+        """x bf16 [B*T, D]; ``epilogue`` (gate / residual / out) is fused into the proj GEMM."""
+        wq, wp = self.packed("w", (self.qkv.weight, self.proj.weight),
+                             lambda: (bf16_weight(self.qkv.weight), bf16_weight(self.proj.weight)))
+        M, D = x_bf16.shape
+        B, H, d = M // tokens, self.num_heads, self.head_dim
+        qkv = ops.linear(x_bf16, wq, self.qkv.bias).view(B, tokens, 3, H, d)
+        q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        a = ops.attention(q, k, v, self.scale)                       # [B,H,T,d] view of [B,T,H*d]
+        a2 = a.permute(0, 2, 1, 3).reshape(M, D)
+        return ops.linear(a2, wp, self.proj.bias, **epilogue)
+
+
+class LastChannelCrossAttention(torch.nn.Module, Packed):
+    """PixArt cross-attention: q from x, k/v from the context tokens, no mask, no q/k/v bias
+    (reference: attention.py:191-228)."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner = dim_head * heads
+        context_dim = context_dim if context_dim is not None else query_dim
+        self.scale, self.heads, self.dim_head = dim_head ** -0.5, heads, dim_head
+        self.to_q = torch.nn.Linear(query_dim, inner, bias=False)
+        self.to_k = torch.nn.Linear(context_dim, inner, bias=False)
+        self.to_v = torch.nn.Linear(context_dim, inner, bias=False)
+        self.to_out = torch.nn.Linear(inner, query_dim)
+
+    def project_context(self, y_bf16):
+        """k|v for the context tokens: y bf16 [B, L, C] -> bf16 [B, L, 2, H, d].  Timestep-invariant."""
+        wkv = self.packed("wkv", (self.to_k.weight, self.to_v.weight),
+                          lambda: torch.cat([bf16_weight(self.to_k.weight), bf16_weight(self.to_v.weight)], 0))
+        B, L, C = y_bf16.shape
+        return ops.linear(y_bf16.reshape(B * L, C), wkv).view(B, L, 2, self.heads, self.dim_head)
+
+    def forward(self, x_bf16, tokens: int, kv, **epilogue):
+        wq, wo = self.packed("w", (self.to_q.weight, self.to_out.weight),
+                             lambda: (bf16_weight(self.to_q.weight), bf16_weight(self.to_out.weight)))
+        M, D = x_bf16.shape
+        B, H, d = M // tokens, self.heads, self.dim_head
+        q = ops.linear(x_bf16, wq).view(B, tokens, H, d).permute(0, 2, 1, 3)
+        k, v = kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3)
+        a = ops.attention(q, k, v, self.scale)
+        return ops.linear(a.permute(0, 2, 1, 3).reshape(M, H * d), wo, self.to_out.bias, **epilogue)
+
+
+class QKVAttention(torch.nn.Module):
+    def __init__(self, num_heads, disable_self_attention: bool = False):
+        super().__init__()
+        self.num_heads = num_heads
+
+
+class SpatialCrossAttention(ContextBlock, Packed):
+    """UNet attention block over pixels (reference: attention.py:20-141 with context_dim = -1, i.e.
+    pure self-attention): GN32 -> qkv (1x1) -> per-head-interleaved softmax attention with
+    ch^-1/4 on q and k -> proj_out (1x1, zero-init) -> residual."""
+
+    def __init__(self, in_channels, context_dim=None, heads=8, dim_head=64, dropout=0.0, **kwargs):
+        super().__init__()
+        if context_dim not in (None, -1):
+            raise NotImplementedError("encoder (cross-attention) context in the UNet is a 'next' row (SURVEY 8f)")
+        for k in ("pre_layer_norm", "post_layer_norm", "context_layer_norm", "disable_self_attention"):
+            if kwargs.get(k):
+                raise NotImplementedError(k)
+        self._channels = in_channels
+        if dim_head == -1:
+            self._num_heads = heads
+        else:
+            assert in_channels % dim_head == 0
+            self._num_heads = in_channels // dim_head
+        self._norm = torch.nn.GroupNorm(num_groups=32, num_channels=in_channels)
+        self._qkv = torch.nn.Conv1d(in_channels, in_channels * 3, 1)
+        self._attention = QKVAttention(self._num_heads)
+        self._proj_out = zero_module(torch.nn.Conv1d(in_channels, in_channels, 1))
+
+    def forward(self, x, context: Optional[Dict] = None, out=None):
+        """x bf16 NHWC [nimg, H, W, C] (a channel slice of a wider buffer is fine) -> same shape."""
+        nimg, H, W, C = x.shape
+        T, heads = H * W, self._num_heads
+        ch = C // heads
+        if ch != 64:
+            raise NotImplementedError("attention head dim != 64")
+        wq, wp = self.packed("w", (self._qkv.weight, self._proj_out.weight),
+                             lambda: (bf16_weight(self._qkv.weight), bf16_weight(self._proj_out.weight)))
+        xs = x.as_strided((nimg, T, C), (x.stride(0), x.stride(2), 1))
+        n = ops.groupnorm(xs, self._norm.weight, self._norm.bias, eps=self._norm.eps)          # dense [nimg,T,C]
+        qkv = ops.linear(n.view(nimg * T, C), wq, self._qkv.bias).view(nimg, T, heads, 3, ch)
+        q, k, v = (qkv[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+        a = ops.attention(q, k, v, 1.0 / math.sqrt(ch))             # (ch^-1/4)^2 on the logits
+        a2 = a.permute(0, 2, 1, 3).reshape(nimg * T, C)
+        if out is None:
+            out = torch.empty((nimg, H, W, C), device=x.device, dtype=torch.bfloat16)
+        x2 = x.as_strided((nimg * T, C), (x.stride(2), 1))
+        o2 = out.as_strided((nimg * T, C), (out.stride(2), 1))
+        ops.linear(a2, wp, self._proj_out.bias, residual=x2, out=o2)
+        return out
+
+
+class QKVAttentionWithRelativePosition(torch.nn.Module):
+    """Holds the relative-position tables (reference: attention.py:490-549)."""
+
+    def __init__(self, num_heads: int, max_relative_position: int, dim_head: int, sequence_length: int):
+        super().__init__()
+        self.num_heads = num_heads
+        n = 2 * max_relative_position - 1
+        self._max_relative_position = max_relative_position
+        self._k_embeddings_table = torch.nn.Parameter(torch.randn(num_heads, n, dim_head) * dim_head ** -0.5)
+        self._v_embeddings_table = torch.nn.Parameter(torch.randn(num_heads, n, dim_head) * dim_head ** -0.5)
+
+
+class TemporalSelfAttention(ContextBlock, Packed):
+    """Attention over frames at each pixel with relative-position logits (reference:
+    attention.py:383-487, 551-676): GN over (C/32 x F) per pixel, no 1/sqrt(d) scale, and the
+    reference's raw (B,H,L,D) -> (B,H*D,L) reinterpretation of the result."""
+
+    def __init__(self, in_channels, temporal_sequence_length, max_relative_position, context_dim=None, heads=8,
+                 dim_head=64, dropout=0.0, **kwargs):
+        super().__init__()
+        if context_dim not in (None, -1):
+            raise NotImplementedError("temporal attention with encoder context")
+        self._channels = in_channels
+        self._num_heads = heads if dim_head == -1 else in_channels // dim_head
+        self._dim_head = in_channels // self._num_heads
+        self._length = temporal_sequence_length
+        self._norm = torch.nn.GroupNorm(num_groups=32, num_channels=in_channels)
+        self._qkv = torch.nn.Conv1d(in_channels, in_channels * 3, 1)
+        self._attention = QKVAttentionWithRelativePosition(self._num_heads, max_relative_position, self._dim_head,
+                                                           temporal_sequence_length)
+        self._proj_out = zero_module(torch.nn.Conv1d(in_channels, in_channels, 1))

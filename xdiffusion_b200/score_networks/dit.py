@@ -1,0 +1,125 @@
+"""DiT (adaLN-Zero) score network on the xdb200 kernels.
+
+Drop-in for ``xdiffusion.score_networks.dit.DiT`` (reference: score_networks/dit.py:77-229): same
+constructor (a DotConfig), same ``forward(x, context) -> Tensor`` and identical ``state_dict`` keys.
+Per forward: patchify+GEMM, ONE batched adaLN GEMM for all blocks (the conditioning vector is
+block-independent), then per block LayerNorm+modulate -> QKV GEMM -> fused attention -> proj GEMM
+with gate*+residual epilogue -> LayerNorm+modulate -> fc1 GEMM (+GELU) -> fc2 GEMM (gate*+residual).
+The token residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation in TMEM.
+"""
+from typing import Dict
+
+import torch
+
+from .. import ops
+from ..layers.attention import MultiHeadSelfAttention
+from ..layers.embedding import PatchEmbed
+from ..layers.mlp import Mlp
+from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
+from ..utils import instantiate_from_config, instantiate_partial_from_config
+
+
+class DiTBlock(torch.nn.Module):
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.attn = MultiHeadSelfAttention(hidden_size, num_heads=num_heads, qkv_bias=True)
+        self.mlp = Mlp(in_features=hidden_size, hidden_features=int(hidden_size * mlp_ratio))
+        self.adaLN_modulation = torch.nn.Sequential(torch.nn.SiLU(),
+                                                    torch.nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+
+
+class FinalLayer(torch.nn.Module):
+    def __init__(self, hidden_size, patch_size, out_channels):
+        super().__init__()
+        self.linear = torch.nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
+        self.adaLN_modulation = torch.nn.Sequential(torch.nn.SiLU(),
+                                                    torch.nn.Linear(hidden_size, 2 * hidden_size, bias=True))
+
+
+def build_conditioning(net, config):
+    """Projections + context-transformer head, shared by DiT / PixArt / UNets
+    (reference: score_networks/dit.py:105-130, unet.py:73-98)."""
+    net._projections = torch.nn.ModuleDict()
+    for name in config.conditioning.signals:
+        net._projections[name] = instantiate_from_config(config.conditioning.projections[name].to_dict())
+    head = config.conditioning.context_transformer_head
+    head = head if isinstance(head, list) else [head.to_dict()]
+    net._context_transformers = torch.nn.ModuleList(
+        [instantiate_partial_from_config(c)(projections=net._projections) for c in head])
+
+
+def run_custom_initializers(net):
+    for m in net.modules():
+        if hasattr(m, "custom_initializer"):
+            m.custom_initializer()
+
+
+class DiT(torch.nn.Module, Packed):
+    def __init__(self, config):
+        super().__init__()
+        hidden, depth = config.hidden_size, config.depth
+        self.learn_sigma = config.is_learned_sigma
+        if self.learn_sigma:
+            raise NotImplementedError("learned sigma")
+        self.in_channels = config.input_channels
+        self.out_channels = config.input_channels
+        self.patch_size, self.num_heads, self.hidden_size = config.patch_size, config.num_heads, hidden
+        self.x_embedder = PatchEmbed(config.input_spatial_size, config.patch_size, config.input_channels, hidden)
+        build_conditioning(self, config)
+        self.pos_embed = torch.nn.Parameter(torch.zeros(1, self.x_embedder.num_patches, hidden), requires_grad=False)
+        self.blocks = torch.nn.ModuleList([DiTBlock(hidden, config.num_heads, config.mlp_ratio) for _ in range(depth)])
+        self.final_layer = FinalLayer(hidden, config.patch_size, self.out_channels)
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        """Same scheme as the reference (dit.py:148-185), incl. the zero-initialised adaLN / final layers."""
+        for m in self.modules():
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    torch.nn.init.constant_(m.bias, 0)
+        grid = int(self.x_embedder.num_patches ** 0.5)
+        self.pos_embed.data.copy_(torch.from_numpy(get_2d_sincos_pos_embed(self.hidden_size, grid)).float()[None])
+        w = self.x_embedder.proj.weight.data
+        torch.nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        torch.nn.init.constant_(self.x_embedder.proj.bias, 0)
+        for lin in [b.adaLN_modulation[-1] for b in self.blocks] + [self.final_layer.adaLN_modulation[-1],
+                                                                   self.final_layer.linear]:
+            torch.nn.init.constant_(lin.weight, 0)
+            torch.nn.init.constant_(lin.bias, 0)
+        run_custom_initializers(self)
+
+    # ------------------------------------------------------------------ kernels
+    def _adaln(self):
+        """All adaLN linears stacked: one [sum(6D..)+2D, D] GEMM per step instead of depth+1."""
+        lins = [b.adaLN_modulation[1] for b in self.blocks] + [self.final_layer.adaLN_modulation[1]]
+        params = tuple(l.weight for l in lins) + tuple(l.bias for l in lins)
+        return self.packed("adaln", params, lambda: (
+            torch.cat([bf16_weight(l.weight) for l in lins], 0), torch.cat([l.bias.detach().float() for l in lins], 0)))
+
+    def forward(self, x, context: Dict):
+        context = context.copy()
+        for ct in self._context_transformers:
+            context = ct(context, device=x.device)
+        c = context["timestep_embedding"]                              # fp32 [B, D]
+        B, D, T = x.shape[0], self.hidden_size, self.x_embedder.num_patches
+        h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
+        silu_c = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
+        torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
+        w_ada, b_ada = self._adaln()
+        mod = ops.linear(silu_c, w_ada, b_ada, out_dtype=torch.float32)           # [B, depth*6D + 2D]
+        for n, blk in enumerate(self.blocks):
+            m = mod[:, n * 6 * D:(n + 1) * 6 * D]
+            s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
+            a = ops.layernorm_modulate(h, s1, sc1, T)
+            blk.attn(a, T, gate=g1, gate_rows=T, residual=h, out=h)               # h += g1 * attn(...)
+            a = ops.layernorm_modulate(h, s2, sc2, T)
+            blk.mlp(a, gate=g2, gate_rows=T, residual=h, out=h)                   # h += g2 * mlp(...)
+        base = len(self.blocks) * 6 * D
+        a = ops.layernorm_modulate(h, mod[:, base:base + D], mod[:, base + D:base + 2 * D], T)
+        w_lin = self.packed("final", (self.final_layer.linear.weight,),
+                            lambda: bf16_weight(self.final_layer.linear.weight))
+        y = ops.linear(a, w_lin, self.final_layer.linear.bias, out_dtype=torch.float32)
+        out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
+        torch.ops.xdb200.unpatchify(y, self.patch_size, out)
+        return out
