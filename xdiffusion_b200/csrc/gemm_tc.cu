@@ -2,14 +2,18 @@
 //
 //   D[m, n] = sum_k A[m, k] * Wt[n, k]            (A bf16 row-major, Wt bf16 [N, K] row-major)
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+// Persistent kernel: one CTA per SM loops over 128 x BN output tiles (n fastest, so concurrently
+// running CTAs share A tiles and all of Wt through L2).  Warp roles (320 threads):
 //   warp 0      TMA producer: per 64-wide k-block one A box (128 rows x 128 B) and one B box
-//               (BN rows x 128 B) into a STAGES-deep ring, 128-byte swizzle, mbarrier complete_tx
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 UMMA K=16 steps per k-block),
-//               tcgen05.commit releases ring slots and finally signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias / activation / gate /
-//               residual -> fp32 or bf16 global stores
-// Two CTAs are co-resident per SM (BN <= 128) so one CTA's epilogue overlaps the other's MMAs.
+//               (BN rows x 128 B) into a STAGES-deep ring (128-byte swizzle, mbarrier complete_tx);
+//               the ring runs ahead across tile boundaries
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 UMMA K=16 steps per k-block)
+//               into one of TWO TMEM accumulators, so tile i+1 is computed while tile i drains
+//   warps 2..9  epilogue, two warps per TMEM lane quadrant (each takes half of the columns):
+//               tcgen05.ld 32x32b.x32 -> +bias, activation in registers -> per-warp padded smem
+//               transpose -> row-contiguous 16-byte global accesses for gate / residual / output
+// The epilogue never touches local memory and every global access is a full 128-byte (fp32) or
+// 64-byte (bf16) row segment per 8 lanes.
 //
 // Implicit conv3x3 (NHWC, pad 1): the A operand of k-block (tap, 64-channel chunk) is a 4-D TMA
 // box (64 ch, W, TH rows, TN images) of the activation tensor shifted by the tap offset; TMA's
@@ -18,6 +22,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <mutex>
 #include <stdio.h>
 
@@ -26,7 +31,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int STAGE_LD = 36;    // padded row (words) of the per-warp 32x32 transpose buffer
 
 struct TcParams {
     int M, N;
@@ -34,36 +41,51 @@ struct TcParams {
     int conv;           // 0: plain rows, 1: conv3x3 geometry
     int cpb;            // conv: 64-channel chunks per tap
     int H, W;           // conv: image height / width
-    int vec_ok;         // epilogue pointers/strides allow 16-byte accesses
+    int vec_ok;         // unused by the kernel (all accesses are 16-byte; checked on the host)
     Epilogue epi;
 };
 
 template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN <= 128) ? 3 : 4;
+    static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int MIN_CTAS = (BN <= 128) ? 2 : 1;
+    static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + XPOSE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;                       // 128 / 256 / 512: powers of two
+    static constexpr int CHUNKS = BN / 32;
+    static constexpr int CHUNKS_PER_GROUP = CHUNKS / 2;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, Cfg<BN>::MIN_CTAS)
+// fast activations for the hot epilogue (ex2.approx + rcp.approx; error << bf16 resolution)
+template <int ACT> __device__ __forceinline__ float act_fast(float x) {
+    if constexpr (ACT == XD_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+    if constexpr (ACT == XD_ACT_GELU_TANH) {
+        const float u = x * (1.5957691216057308f + 0.07135481627260025f * x * x);   // 2*sqrt(2/pi)*(x+0.044715x^3)
+        return __fdividef(x, 1.0f + __expf(-u));
+    }
+    return x;
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::XPOSE_BYTES);
     uint64_t* empty_bar = full_bar + C::STAGES;
-    uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + C::STAGES;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * BM;
     const int nk = p.nk0 + p.nk1;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int total_tiles = n_tiles * ((p.M + BM - 1) / BM);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
@@ -73,144 +95,174 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
-        ptx::mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&tmem_full_bar[b], 1);
+            ptx::mbar_init(&tmem_empty_bar[b], EPI_WARPS);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr, BN);
+        ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr;
+    const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            int img = 0, h0 = 0;
-            if (p.conv) {
-                const int hw = p.H * p.W;
-                img = m0 / hw;
-                h0 = (m0 - img * hw) / p.W;
-            }
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* sA = smem + s * C::STAGE_BYTES;
-                uint8_t* sB = sA + C::A_BYTES;
-                ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-                if (kb < p.nk0) {
-                    if (!p.conv) {
-                        ptx::tma_load_4d(sA, &tmA0, &full_bar[s], kb * BK, m0, 0, 0);
-                    } else {
-                        const int tap = kb / p.cpb;
-                        const int cc = kb - tap * p.cpb;
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        ptx::tma_load_4d(sA, &tmA0, &full_bar[s], cc * BK, dx, h0 + dy, img);
-                    }
-                } else {
-                    const int k1 = kb - p.nk0;
-                    if (!p.conv) ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, m0, 0, 0);
-                    else ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, 0, h0, img);
+            uint32_t kbg = 0;                                   // ring position, continuous across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM;
+                const int n0 = (tile % n_tiles) * BN;
+                int img = 0, h0 = 0;
+                if (p.conv) {
+                    const int hw = p.H * p.W;
+                    img = m0 / hw;
+                    h0 = (m0 - img * hw) / p.W;
                 }
-                ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n_tile0);
+                for (int kb = 0; kb < nk; ++kb, ++kbg) {
+                    const int s = kbg % C::STAGES;
+                    const uint32_t ph = (kbg / C::STAGES) & 1;
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sA = smem + s * C::STAGE_BYTES;
+                    uint8_t* sB = sA + C::A_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                    if (kb < p.nk0) {
+                        if (!p.conv) {
+                            ptx::tma_load_4d(sA, &tmA0, &full_bar[s], kb * BK, m0, 0, 0);
+                        } else {
+                            const int tap = kb / p.cpb;
+                            const int cc = kb - tap * p.cpb;
+                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                            ptx::tma_load_4d(sA, &tmA0, &full_bar[s], cc * BK, dx, h0 + dy, img);
+                        }
+                    } else {
+                        const int k1 = kb - p.nk0;
+                        if (!p.conv) ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, m0, 0, 0);
+                        else ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, 0, h0, img);
+                    }
+                    ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
-        for (int kb = 0; kb < nk; ++kb) {
-            const int s = kb % C::STAGES;
-            const uint32_t ph = (kb / C::STAGES) & 1;
-            ptx::mbar_wait(&full_bar[s], ph);
+        uint32_t kbg = 0, it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
             ptx::tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = ptx::smem_u32(smem + s * C::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + C::A_BYTES;
-                const uint64_t da = ptx::smem_desc_sw128(a_addr);
-                const uint64_t db = ptx::smem_desc_sw128(b_addr);
+            const uint32_t tmem_d = tmem_base + buf * BN;
+            for (int kb = 0; kb < nk; ++kb, ++kbg) {
+                const int s = kbg % C::STAGES;
+                const uint32_t ph = (kbg / C::STAGES) & 1;
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = ptx::smem_u32(smem + s * C::STAGE_BYTES);
+                    const uint64_t da = ptx::smem_desc_sw128(a_addr);
+                    const uint64_t db = ptx::smem_desc_sw128(a_addr + C::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
-                    ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
+                        ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[buf]);
                 }
-                ptx::umma_commit(&empty_bar[s]);
-                if (kb == nk - 1) ptx::umma_commit(tmem_full_bar);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
+        const int e_warp = warp - 2;
+        const int grp = e_warp >> 2;                    // which half of the tile's columns
         const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-        const long long m = (long long)m0 + q * 32 + lane;
-        ptx::mbar_wait(tmem_full_bar, 0);
-        ptx::tc_fence_after();
+        float* st = xpose + e_warp * 32 * STAGE_LD;     // private 32 x 32 (+pad) transpose buffer
         const Epilogue& e = p.epi;
-        const long long gate_row = e.gate ? (m / e.gate_rows) * e.gate_ld : 0;
+        const int sub_row = lane >> 3;                  // coalesced pass: 4 rows x 8 lanes x 4 columns
+        const int sub_col = (lane & 7) * 4;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / n_tiles) * BM;
+            const int n0 = (tile % n_tiles) * BN;
+            const uint32_t buf = it & 1;
+            ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            __syncwarp();                                // tcgen05.ld is warp-collective (.sync.aligned)
-            ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + c * 32, r);
-            ptx::tmem_ld_wait();
-            const int n = n_tile0 + c * 32;
-            if (n >= p.N) break;                         // warp-uniform
-            if (m >= p.M) continue;                      // row tail: nothing to store
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.vec_ok && n + 32 <= p.N) {
-                if (e.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
+            for (int ci = 0; ci < (C::CHUNKS_PER_GROUP > 0 ? C::CHUNKS_PER_GROUP : 1); ++ci) {
+                const int c = grp * C::CHUNKS_PER_GROUP + ci;
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_addr + c * 32, r);
+                ptx::tmem_ld_wait();
+                if (ci == C::CHUNKS_PER_GROUP - 1) {    // last TMEM read of this tile by this warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
                 }
-                if (e.act != XD_ACT_NONE) {
+                const int nc = n0 + c * 32;             // first global column of this chunk
+                // ---- column-wise part on the row-per-thread fragment: bias, activation
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias && nc + j < p.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + nc + j));
+                    float4 v;
+                    v.x = act_fast<ACT>(__uint_as_float(r[j]) + b.x);
+                    v.y = act_fast<ACT>(__uint_as_float(r[j + 1]) + b.y);
+                    v.z = act_fast<ACT>(__uint_as_float(r[j + 2]) + b.z);
+                    v.w = act_fast<ACT>(__uint_as_float(r[j + 3]) + b.w);
+                    *reinterpret_cast<float4*>(st + lane * STAGE_LD + j) = v;
                 }
-                if (e.gate) {
+                __syncwarp();
+                // ---- row-contiguous part: gate, residual, store (8 lanes cover one 32-column row segment)
+                const int col = nc + sub_col;
+                const bool col_ok = col < p.N;
+                float4 v[8], g[8], rs[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + gate_row + n + j));
-                        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-                    }
-                }
-                if (e.residual) {
-                    if (e.res_dtype == XD_F32) {
-                        const float* rp = (const float*)e.residual + m * e.res_ld + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = *reinterpret_cast<const float4*>(rp + j);
-                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + sub_row;
+                    const long long m = (long long)m0 + q * 32 + rr;
+                    const bool ok = col_ok && m < p.M;
+                    v[i] = *reinterpret_cast<const float4*>(st + rr * STAGE_LD + sub_col);
+                    g[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && e.gate)
+                        g[i] = __ldg(reinterpret_cast<const float4*>(e.gate + (m / e.gate_rows) * e.gate_ld + col));
+                    if (ok && e.residual) {
+                        if (e.res_dtype == XD_F32) {
+                            rs[i] = *reinterpret_cast<const float4*>((const float*)e.residual + m * e.res_ld + col);
+                        } else {
+                            const uint2 u = *reinterpret_cast<const uint2*>((const bf16*)e.residual + m * e.res_ld + col);
+                            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                            rs[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
                         }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + sub_row;
+                    const long long m = (long long)m0 + q * 32 + rr;
+                    if (!(col_ok && m < p.M)) continue;
+                    float4 o;
+                    o.x = fmaf(v[i].x, g[i].x, rs[i].x); o.y = fmaf(v[i].y, g[i].y, rs[i].y);
+                    o.z = fmaf(v[i].z, g[i].z, rs[i].z); o.w = fmaf(v[i].w, g[i].w, rs[i].w);
+                    if (e.out_dtype == XD_F32) {
+                        *reinterpret_cast<float4*>((float*)e.out + m * e.out_ld + col) = o;
                     } else {
-                        const bf16* rp = (const bf16*)e.residual + m * e.res_ld + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float f[8];
-                            unpack8(*reinterpret_cast<const bf16x8*>(rp + j), f);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[j + i] += f[i];
-                        }
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                        uint2 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&lo);
+                        u.y = *reinterpret_cast<uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>((bf16*)e.out + m * e.out_ld + col) = u;
                     }
                 }
-                if (e.out_dtype == XD_F32) {
-                    float* op = (float*)e.out + m * e.out_ld + n;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    bf16* op = (bf16*)e.out + m * e.out_ld + n;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(op + j) = pack8(v + j);
-                }
-            } else {
-                for (int j = 0; j < 32 && n + j < p.N; ++j) epi_store(e, epi_value(e, v[j], m, n + j), m, n + j);
+                __syncwarp();                           // transpose buffer is reused by the next chunk
             }
         }
     }
@@ -218,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_d, BN);
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -287,44 +339,62 @@ int tmap_nhwc(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, l
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int epilogue_vec_ok(const Epilogue& e) {
+// The kernel's epilogue uses 16-byte (fp32) / 8-byte (bf16) accesses on 4-column groups.
+int epilogue_vec_ok(const Epilogue& e, int N) {
     bool ok = aligned16(e.out) && aligned16(e.bias) && aligned16(e.gate) && aligned16(e.residual);
-    ok = ok && (e.out_ld % 8 == 0) && (e.res_ld % 8 == 0) && (e.gate_ld % 4 == 0);
+    ok = ok && (N % 4 == 0) && (e.out_ld % 4 == 0) && (e.res_ld % 4 == 0) && (e.gate_ld % 4 == 0);
     return ok ? 1 : 0;
 }
 
-template <int BN>
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int ACT>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM) !=
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM) !=
             cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
             return XD_ERR_CUDA;
         }
         configured = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(a0, a1, b, p);
+    const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());      // persistent: <= one CTA per SM
+    gemm_tc_kernel<BN, ACT><<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(a0, a1, b, p);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
 
 int pick_bn(int N, int M) {
-    if (N <= 64) return 64;
-    // fill the machine: prefer 128-wide tiles, go to 256 only when there are plenty of tiles
-    const long long tiles128 = (long long)((N + 127) / 128) * ((M + BM - 1) / BM);
-    if (N % 256 == 0 && tiles128 >= 4 * 148 * 2) return 256;
-    return 128;
+    (void)M;
+    return N <= 64 ? 64 : 128;
 }
 
 int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p,
              cudaStream_t st) {
+#define XD_TC_CASE(BN_)                                                                    \
+    case BN_:                                                                              \
+        switch (p.epi.act) {                                                               \
+            case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE>(a0, a1, b, p, st);           \
+            case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU>(a0, a1, b, p, st);           \
+            case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH>(a0, a1, b, p, st); \
+        }                                                                                  \
+        break;
     switch (bn) {
-        case 64: return launch<64>(a0, a1, b, p, st);
-        case 128: return launch<128>(a0, a1, b, p, st);
-        case 256: return launch<256>(a0, a1, b, p, st);
+        XD_TC_CASE(64)
+        XD_TC_CASE(128)
+        XD_TC_CASE(256)
     }
+#undef XD_TC_CASE
     return XD_ERR_ARG;
 }
 
@@ -345,7 +415,8 @@ extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, lon
     TcParams p{};
     p.M = M; p.N = N; p.nk0 = K / BK; p.nk1 = K2 / BK; p.conv = 0;
     p.epi = Epilogue{bias, gate, residual, out, gate_ld, res_ld, out_ld, act, gate_rows, res_dtype, out_dtype};
-    p.vec_ok = epilogue_vec_ok(p.epi);
+    p.vec_ok = epilogue_vec_ok(p.epi, N);
+    XD_CHECK_ARG(p.vec_ok);
     const int bn = force_bn ? force_bn : pick_bn(N, M);
     CUtensorMap ta0, ta1, tb;
     int rc;
@@ -369,7 +440,8 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     TcParams p{};
     p.M = nimg * hw; p.N = Cout; p.conv = 1; p.cpb = C / BK; p.nk0 = 9 * p.cpb; p.nk1 = Cs / BK; p.H = H; p.W = W;
     p.epi = Epilogue{bias, nullptr, residual, out, 0, res_ld, out_ld, act, 1, res_dtype, out_dtype};
-    p.vec_ok = epilogue_vec_ok(p.epi);
+    p.vec_ok = epilogue_vec_ok(p.epi, Cout);
+    XD_CHECK_ARG(p.vec_ok);
     const int bn = force_bn ? force_bn : pick_bn(Cout, p.M);
     CUtensorMap ta0, ta1, tb;
     int rc;
