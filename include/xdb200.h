@@ -81,16 +81,18 @@ int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q
 
 /* ---- bandwidth-bound kernels ------------------------------------------------------------------ */
 
-/* GroupNorm over NHWC bf16: a "sample" is P consecutive pixels of C channels.  stats fp32
+/* GroupNorm over NHWC bf16: a "sample" is P pixel rows of C channels; row(s, p) = (s / inner)*P*inner +
+ * s % inner + p*inner  (inner = 1: P consecutive pixels; inner = H*W, P = F: the frames of one pixel of
+ * a clip, i.e. the temporal block's GroupNorm over (C/32 x F), layers/attention.py:457-462).  stats fp32
  * [nsamples][groups][2] (sum, sum of squares), zeroed inside.  apply: y = GN(x)*gamma+beta, then
  * y = y*(1+scale)+shift with [scale | shift] = scale_shift[(sample / ss_div)*ss_ld + ...] if non-NULL,
  * then SiLU if silu.  (torch.nn.GroupNorm(32,C) + SiLU: layers/resnet.py:126-128,151-153,193-197;
  * layers/attention.py:64; score_networks/unet.py:246-247.) */
-int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, float* stats,
-                       void* stream);
+int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
+                       float* stats, void* stream);
 int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* stats,
                        const float* gamma, const float* beta, const float* scale_shift, long long ss_ld,
-                       int ss_div, float eps, int silu, void* out, long long ldo, void* stream);
+                       int ss_div, float eps, int silu, int inner, void* out, long long ldo, void* stream);
 
 /* out(bf16)[m,:] = LayerNorm(x[m,:]; no affine) * (1 + scale[r,:]) + shift[r,:], r = (m / rows_per_mod)*mod_ld.
  * (score_networks/dit.py:16-17,46-51,70-72; pixart.py:20-21,82-92) */

@@ -11,7 +11,8 @@ namespace {
 // stats[sample][group] = (sum, sum of squares) accumulated with atomics from pixel slabs.
 // "sample" = P consecutive pixels (rows of C channels, stride ld).
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, float* __restrict__ stats) {
+gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, int inner,
+                float* __restrict__ stats) {
     __shared__ float acc[64][2];
     const int V = C >> 3;                       // 16-byte vectors per pixel
     const int ppb = 256 / V;                    // pixels per block iteration
@@ -24,10 +25,11 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, f
     const int j = threadIdx.x % V, po = threadIdx.x / V;
     if (po < ppb) {
         float s[8] = {}, q[8] = {};
-        const bf16* base = x + ((long long)sample * P) * ld + j * 8;
+        // row(sample, p) = (sample / inner) * P * inner + sample % inner + p * inner
+        const bf16* base = x + ((long long)(sample / inner) * P * inner + sample % inner) * ld + j * 8;
         for (int p = p0 + po; p < p1; p += ppb) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * ld), f);
+            unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * inner * ld), f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
         }
@@ -54,7 +56,7 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, f
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
-                long long ss_ld, int ss_div, float eps, int silu, bf16* __restrict__ out, long long ldo) {
+                long long ss_ld, int ss_div, float eps, int silu, int inner, bf16* __restrict__ out, long long ldo) {
     extern __shared__ float coef[];             // [2][C]
     const int sample = blockIdx.y;
     const int cpg = C / G;
@@ -81,7 +83,7 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
     const long long n = (long long)(p1 - p0) * V;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
         const int j = (int)(i % V);
-        const long long p = (long long)sample * P + p0 + i / V;
+        const long long p = (long long)(sample / inner) * P * inner + sample % inner + (p0 + i / V) * inner;
         float f[8];
         unpack8(*reinterpret_cast<const bf16x8*>(x + p * ld + j * 8), f);
 #pragma unroll
@@ -138,29 +140,31 @@ ln_modulate_kernel(const float* __restrict__ x, long long ld, int M, const float
 
 }  // namespace
 
-extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, float* stats,
-                                  void* stream) {
+extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
+                                  float* stats, void* stream) {
     XD_CHECK_ARG(x && stats && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0 && ld % 8 == 0);
+    XD_CHECK_ARG(inner >= 1 && nsamples % inner == 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(stats, 0, sizeof(float) * 2 * nsamples * groups, st) != cudaSuccess) return XD_ERR_CUDA;
     int slabs = (2 * 148 + nsamples - 1) / nsamples;
     const int ppb = 256 / (C / 8);
     slabs = max(1, min(slabs, (P + ppb * 4 - 1) / (ppb * 4)));
-    gn_stats_kernel<<<dim3(slabs, nsamples), 256, 0, st>>>((const bf16*)x, ld, P, C, groups, stats);
+    gn_stats_kernel<<<dim3(slabs, nsamples), 256, 0, st>>>((const bf16*)x, ld, P, C, groups, inner, stats);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
 
 extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups,
                                   const float* stats, const float* gamma, const float* beta, const float* scale_shift,
-                                  long long ss_ld, int ss_div, float eps, int silu, void* out, long long ldo,
-                                  void* stream) {
+                                  long long ss_ld, int ss_div, float eps, int silu, int inner, void* out,
+                                  long long ldo, void* stream) {
     XD_CHECK_ARG(x && stats && gamma && beta && out && C % 8 == 0 && C % groups == 0 && ld % 8 == 0 && ldo % 8 == 0);
+    XD_CHECK_ARG(inner >= 1 && nsamples % inner == 0);
     int slabs = (4 * 148 + nsamples - 1) / nsamples;
     slabs = max(1, min(slabs, (P + 15) / 16));
     gn_apply_kernel<<<dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
         (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
-        (bf16*)out, ldo);
+        inner, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

@@ -274,6 +274,16 @@ class _DeviceLoop:
                     static[k].copy_(v)
                 else:
                     static[k] = v
+        self._precompute()
+
+    def _precompute(self):
+        """Timestep-invariant conditioning (e.g. PixArt cross-attention K/V) is refreshed eagerly,
+        in place, so that graph replays read the new values."""
+        net = self.model._score_network
+        if hasattr(net, "precompute_context"):
+            for ctx in (self.context, self.uncond):
+                if ctx is not None:
+                    net.precompute_context(ctx)
 
     def _advance(self, set_to):
         t = self.tabs["timestep"]

@@ -149,3 +149,35 @@ class TemporalSelfAttention(ContextBlock, Packed):
         self._attention = QKVAttentionWithRelativePosition(self._num_heads, max_relative_position, self._dim_head,
                                                            temporal_sequence_length)
         self._proj_out = zero_module(torch.nn.Conv1d(in_channels, in_channels, 1))
+
+    def forward(self, x, frames: int, out=None):
+        """x bf16 [B*F, H, W, C] (frames folded into the image count) -> same layout."""
+        nimg, H, W, C = x.shape
+        B, F, HW = nimg // frames, frames, H * W
+        heads, d = self._num_heads, self._dim_head
+        if d != 64:
+            raise NotImplementedError("attention head dim != 64")
+        wq, wp = self.packed("w", (self._qkv.weight, self._proj_out.weight),
+                             lambda: (bf16_weight(self._qkv.weight), bf16_weight(self._proj_out.weight)))
+        relk = self.packed("relk", (self._attention._k_embeddings_table,),
+                           lambda: self._attention._k_embeddings_table.detach().float().contiguous())
+        if relk.shape[1] != 2 * F - 1:
+            raise NotImplementedError("temporal_sequence_length != max_relative_position")
+        # GroupNorm over (C/32 x F) for every pixel of every clip: samples (b, hw), rows = frames
+        rows = x.as_strided((nimg * HW, C), (x.stride(2), 1))
+        n = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
+        stats = torch.empty(B * HW * 64, device=x.device, dtype=torch.float32)
+        torch.ops.xdb200.groupnorm(rows, self._norm.weight, self._norm.bias, None, 1, self._norm.eps, 0, HW, B * HW,
+                                   stats, n)
+        qkv = ops.linear(n, wq, self._qkv.bias)                              # rows (b, f, hw) x 3C
+        a = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
+        q5 = qkv.view(B, F, HW, heads, 3, d)
+        a4 = a.view(B, F, HW, heads, d)
+        for b in range(B):                                                   # batch index of the kernel = pixel
+            q, k, v = (q5[b, :, :, :, i].permute(1, 2, 0, 3) for i in range(3))     # [HW, heads, F, d]
+            ops.attention(q, k, v, 1.0, out=a4[b].permute(1, 2, 0, 3), relk=relk, scramble=True, o_cs=1)
+        if out is None:
+            out = torch.empty((nimg, H, W, C), device=x.device, dtype=torch.bfloat16)
+        o2 = out.as_strided((nimg * HW, C), (out.stride(2), 1))
+        ops.linear(a, wp, self._proj_out.bias, residual=rows, out=o2)
+        return out

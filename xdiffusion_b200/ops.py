@@ -138,18 +138,21 @@ def _attention(q, k, v, o, scale, relk, scramble, o_cs):
 
 # ------------------------------------------------------------------------------------ norms
 @_op("groupnorm(Tensor x, Tensor gamma, Tensor beta, Tensor? scale_shift, int ss_div, float eps, int silu, "
-     "Tensor(a!) stats, Tensor(b!) out) -> ()")
-def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, stats, out):
-    """x [nsamples, P, C] bf16 view (channel stride 1, dense rows); 32 groups."""
+     "int inner, int nsamples, Tensor(a!) stats, Tensor(b!) out) -> ()")
+def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, stats, out):
+    """x [rows, C] bf16 view (channel stride 1) holding nsamples samples of P = rows / nsamples rows
+    each; row(s, p) = (s / inner)*P*inner + s % inner + p*inner; 32 groups; stats fp32 [nsamples*64]."""
     _cuda(x, gamma, beta, scale_shift, stats, out)
-    ns, P, C = x.shape
-    assert x.stride(2) == 1 and x.stride(0) == P * x.stride(1) and out.stride(2) == 1
-    assert out.stride(0) == P * out.stride(1) and stats.numel() >= ns * 64 and stats.dtype == torch.float32
+    rows, C = x.shape
+    ns, P = nsamples, rows // nsamples
+    assert x.stride(1) == 1 and out.stride(1) == 1 and ns * P == rows and stats.dtype == torch.float32
+    assert stats.numel() >= ns * 64 and stats.is_contiguous()
     l = _lib.lib()
-    _lib.check(l.xd_groupnorm_stats(_p(x), x.stride(1), ns, P, C, 32, _p(stats), _stream()), "xd_groupnorm_stats")
-    _lib.check(l.xd_groupnorm_apply(_p(x), x.stride(1), ns, P, C, 32, _p(stats), _p(gamma), _p(beta),
+    _lib.check(l.xd_groupnorm_stats(_p(x), x.stride(0), ns, P, C, 32, inner, _p(stats), _stream()),
+               "xd_groupnorm_stats")
+    _lib.check(l.xd_groupnorm_apply(_p(x), x.stride(0), ns, P, C, 32, _p(stats), _p(gamma), _p(beta),
                                     _p(scale_shift), 0 if scale_shift is None else scale_shift.stride(0), ss_div,
-                                    eps, silu, _p(out), out.stride(1), _stream()), "xd_groupnorm_apply")
+                                    eps, silu, inner, _p(out), out.stride(0), _stream()), "xd_groupnorm_apply")
     _count(3)
 
 
@@ -334,12 +337,18 @@ def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, fo
     return out
 
 
-def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, out=None):
-    """x [nsamples, P, C] bf16."""
+def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, out=None, inner=1):
+    """x [nsamples, P, C] bf16 view with uniformly strided rows (x.stride(0) == P * x.stride(1));
+    ``inner`` > 1 selects the interleaved sample layout described in include/xdb200.h."""
+    ns, P, C = x.shape
+    assert x.stride(2) == 1 and x.stride(0) == P * x.stride(1)
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    stats = torch.empty(x.shape[0] * 64, device=x.device, dtype=torch.float32)
-    _ops.groupnorm(x, gamma, beta, scale_shift, ss_div, eps, int(silu), stats, out)
+    assert out.stride(2) == 1 and out.stride(0) == P * out.stride(1)
+    x2 = x.as_strided((ns * P, C), (x.stride(1), 1))
+    o2 = out.as_strided((ns * P, C), (out.stride(1), 1))
+    stats = torch.empty(ns * 64, device=x.device, dtype=torch.float32)
+    _ops.groupnorm(x2, gamma, beta, scale_shift, ss_div, eps, int(silu), inner, ns, stats, o2)
     return out
 
 

@@ -172,12 +172,17 @@ class Unet(torch.nn.Module, Packed):
         h = cats[0][..., h_w[n_skip - 1]:]
         torch.ops.xdb200.conv3x3_in(x4.contiguous(), self._initial_convolution.weight, None, h)
         hh, ww = H, W
+        taps = context.get("_taps")                    # debugging aid: {name: activation} (tools/taps_compare.py)
         for j, entry in enumerate(self.downs, start=1):
             if isinstance(entry[0], Downsample):
                 hh, ww = hh // 2, ww // 2
             cats[j] = cat_buffer(j, hh, ww)
             h = self._run_entry(entry, h, emb_of, samples, frames, cats[j][..., h_w[n_skip - 1 - j]:])
+            if taps is not None:
+                taps[f"downs.{j - 1}"] = h.float().clone()
         h = self._run_entry(self.middle, h, emb_of, samples, frames, cats[n_skip - 1][..., :h_w[0]])
+        if taps is not None:
+            taps["middle"] = h.float().clone()
         for k, entry in enumerate(self.ups):
             if k + 1 < n_skip:
                 nxt = cats[n_skip - 2 - k]
@@ -185,6 +190,8 @@ class Unet(torch.nn.Module, Packed):
             else:
                 dst = None
             h = self._run_entry(entry, cats[n_skip - 1 - k], emb_of, samples, frames, dst)
+            if taps is not None:
+                taps[f"ups.{k}"] = h.float().clone()
         gn = self.final_projection[0]
         hs = h.as_strided((samples, h.shape[0] // samples * h.shape[1] * h.shape[2], h.shape[3]),
                           (h.stride(0) * (h.shape[0] // samples), h.stride(2), 1))
