@@ -29,6 +29,124 @@ struct AttnParams {
     long long o_cs;             // scramble: element stride between "channels" of the (C, L) view
 };
 
+// q . k over 64 dims with four independent accumulators (a single 64-long FMA chain is latency-bound)
+__device__ __forceinline__ float dot64(const float* q, const float4* k) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 t = k[d4];
+        a0 = fmaf(q[4 * d4], t.x, a0); a1 = fmaf(q[4 * d4 + 1], t.y, a1);
+        a2 = fmaf(q[4 * d4 + 2], t.z, a2); a3 = fmaf(q[4 * d4 + 3], t.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ float dot64_ldg(const float* q, const float4* k) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 t = __ldg(k + d4);
+        a0 = fmaf(q[4 * d4], t.x, a0); a1 = fmaf(q[4 * d4 + 1], t.y, a1);
+        a2 = fmaf(q[4 * d4 + 2], t.z, a2); a3 = fmaf(q[4 * d4 + 3], t.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+__device__ __forceinline__ void store_row(const AttnParams& p, int b, int h, int row, const float* o, float inv) {
+    if (!p.scramble) {
+        bf16* op = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_rs;
+#pragma unroll
+        for (int d = 0; d < D; d += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = o[d + i] * inv;
+            *reinterpret_cast<bf16x8*>(op + d) = pack8(f);
+        }
+    } else {
+        // a[b, h, row, d] is element (h*L + row)*64 + d of a flat buffer that the reference then
+        // views as (C = H*64, L): flat = c*L + l.
+        const int L = p.Tq;
+        bf16* ob = p.o + b * p.o_bs;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int flat = (h * L + row) * D + d;
+            const int c = flat / L, lpos = flat % L;
+            ob[(long long)lpos * p.o_rs + (long long)c * p.o_cs] = __float2bfloat16_rn(o[d] * inv);
+        }
+    }
+}
+
+// Tq == Tk == 16 (DiT / PixArt tokens, video frames): 8 (batch, head) pairs per CTA, thread = query
+// row; the same thread also fetches key row / value row `row` of its pair, so all 24 16-byte loads
+// of a thread are in flight together, and the 16 logits of a row live in registers (exact softmax).
+constexpr int T16 = 16;
+constexpr int RS16 = D + 4;                  // padded key/value row: 8 consecutive rows cover all 32 banks
+constexpr int PAIR_LD = 2 * T16 * RS16 + 4;  // +16 B: the two pairs of a warp hit different banks
+__global__ void __launch_bounds__(ROWS)
+attention16_kernel(const AttnParams p) {
+    extern __shared__ float smem[];             // [8][2][16][64] (+pad)
+    const int tid = threadIdx.x;
+    const int pl = tid >> 4, row = tid & 15;
+    const long long bh = (long long)blockIdx.x * 8 + pl;
+    const bool active = bh < (long long)p.B * p.H;
+    const int b = active ? (int)(bh / p.H) : 0, h = active ? (int)(bh % p.H) : 0;
+    float* sK = smem + pl * PAIR_LD;
+    float* sV = sK + T16 * RS16;
+    float q[D];
+    {
+        bf16x8 rq[8], rk[8], rv[8];
+        const bf16* qp = p.q + b * p.q_bs + h * p.q_hs + (long long)row * p.q_rs;
+        const bf16* kp = p.k + b * p.k_bs + h * p.k_hs + (long long)row * p.k_rs;
+        const bf16* vp = p.v + b * p.v_bs + h * p.v_hs + (long long)row * p.v_rs;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            rq[i] = *reinterpret_cast<const bf16x8*>(qp + i * 8);
+            rk[i] = *reinterpret_cast<const bf16x8*>(kp + i * 8);
+            rv[i] = *reinterpret_cast<const bf16x8*>(vp + i * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float f[8];
+            unpack8(rq[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[i * 8 + j] = f[j] * p.scale;
+            unpack8(rk[i], f);
+            *reinterpret_cast<float4*>(sK + row * RS16 + i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(sK + row * RS16 + i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            unpack8(rv[i], f);
+            *reinterpret_cast<float4*>(sV + row * RS16 + i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(sV + row * RS16 + i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+    }
+    __syncthreads();
+    float s[T16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < T16; ++j) {
+        float acc = dot64(q, reinterpret_cast<const float4*>(sK + j * RS16));
+        if (p.relk)
+            acc += dot64_ldg(q, reinterpret_cast<const float4*>(p.relk + ((long long)h * (2 * T16 - 1) + (j - row + T16 - 1)) * D));
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < T16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
+    float o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < T16; ++j) {
+        const float4* vr = reinterpret_cast<const float4*>(sV + j * RS16);
+#pragma unroll
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+            const float4 t = vr[d4];
+            o[4 * d4] = fmaf(s[j], t.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(s[j], t.y, o[4 * d4 + 1]);
+            o[4 * d4 + 2] = fmaf(s[j], t.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(s[j], t.w, o[4 * d4 + 3]);
+        }
+    }
+    if (active) store_row(p, b, h, row, o, 1.0f / l);
+}
+
 __global__ void __launch_bounds__(ROWS)
 attention_kernel(const AttnParams p) {
     extern __shared__ float smem[];             // [pairs][2][KC][D]
@@ -98,23 +216,10 @@ attention_kernel(const AttnParams p) {
         for (int kk = 0; kk < KC; ++kk) {
             float acc = 0.f;
             if (kk < kn) {
-                const float4* kr = reinterpret_cast<const float4*>(sK + kk * D);
-#pragma unroll
-                for (int d4 = 0; d4 < D / 4; ++d4) {
-                    const float4 t = kr[d4];
-                    acc = fmaf(q[4 * d4], t.x, acc); acc = fmaf(q[4 * d4 + 1], t.y, acc);
-                    acc = fmaf(q[4 * d4 + 2], t.z, acc); acc = fmaf(q[4 * d4 + 3], t.w, acc);
-                }
-                if (p.relk) {
-                    const float4* er = reinterpret_cast<const float4*>(
-                        p.relk + ((long long)h * (2 * p.Tk - 1) + (k0 + kk - row + p.Tk - 1)) * D);
-#pragma unroll
-                    for (int d4 = 0; d4 < D / 4; ++d4) {
-                        const float4 t = __ldg(er + d4);
-                        acc = fmaf(q[4 * d4], t.x, acc); acc = fmaf(q[4 * d4 + 1], t.y, acc);
-                        acc = fmaf(q[4 * d4 + 2], t.z, acc); acc = fmaf(q[4 * d4 + 3], t.w, acc);
-                    }
-                }
+                acc = dot64(q, reinterpret_cast<const float4*>(sK + kk * D));
+                if (p.relk)
+                    acc += dot64_ldg(q, reinterpret_cast<const float4*>(
+                        p.relk + ((long long)h * (2 * p.Tk - 1) + (k0 + kk - row + p.Tk - 1)) * D));
             } else {
                 acc = -INFINITY;
             }
@@ -142,32 +247,15 @@ attention_kernel(const AttnParams p) {
         }
         mx = nmx;
     }
-    if (!active) return;
-    const float inv = 1.0f / l;
-    if (!p.scramble) {
-        bf16* op = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_rs;
-#pragma unroll
-        for (int d = 0; d < D; d += 8) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = o[d + i] * inv;
-            *reinterpret_cast<bf16x8*>(op + d) = pack8(f);
-        }
-    } else {
-        // a[b, h, row, d] is element (h*L + row)*64 + d of a flat buffer that the reference then
-        // views as (C = H*64, L): flat = c*L + l.
-        const int L = p.Tq;
-        bf16* ob = p.o + b * p.o_bs;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int flat = (h * L + row) * D + d;
-            const int c = flat / L, lpos = flat % L;
-            ob[(long long)lpos * p.o_rs + (long long)c * p.o_cs] = __float2bfloat16_rn(o[d] * inv);
-        }
-    }
+    if (active) store_row(p, b, h, row, o, 1.0f / l);
 }
 
 }  // namespace
+
+int xd_attention_tc256_try(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
+                           long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
+                           long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs, long long o_rs,
+                           int B, int H, float scale, cudaStream_t st);
 
 extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
                                  long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
@@ -182,6 +270,23 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
     XD_CHECK_ARG(!relk || Tq == Tk);
     AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, q_bs, q_hs, q_rs, k_bs, k_hs, k_rs,
                  v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs};
+    if (Tq == 256 && Tk == 256 && !relk && !scramble) {           // tcgen05 path (csrc/attention_tc.cu)
+        const int rc = xd_attention_tc256_try(q, q_bs, q_hs, q_rs, k, k_bs, k_hs, k_rs, v, v_bs, v_hs, v_rs, o, o_bs,
+                                              o_hs, o_rs, B, H, scale, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    if (Tq == T16 && Tk == T16) {
+        static bool configured16 = false;
+        const size_t smem16 = (size_t)8 * PAIR_LD * sizeof(float);
+        if (!configured16) {
+            cudaFuncSetAttribute(attention16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            configured16 = true;
+        }
+        const long long nb = ((long long)B * H + 7) / 8;
+        attention16_kernel<<<(unsigned)nb, ROWS, smem16, (cudaStream_t)stream>>>(p);
+        XD_CHECK_LAUNCH();
+        return XD_OK;
+    }
     const int pairs = Tq >= ROWS ? 1 : ROWS / Tq;
     const long long nbh = (long long)B * H;
     const long long blocks = Tq >= ROWS ? nbh * (Tq / ROWS) : (nbh + pairs - 1) / pairs;

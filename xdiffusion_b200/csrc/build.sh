@@ -4,11 +4,10 @@ set -e
 cd "$(dirname "$0")"
 OUT=../libxdb200.so
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --use_fast_math=false"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 mkdir -p ../../build/obj
 pids=()
-for f in abi gemm_tc simt norm attention elementwise step; do
+for f in abi gemm_tc simt norm attention attention_tc elementwise step; do
   $NVCC $FLAGS -c $f.cu -o ../../build/obj/$f.o &
   pids+=($!)
 done

@@ -42,16 +42,27 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// 8 x bf16 <-> 8 x float through one 16-byte access
-struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+// 8 x bf16 <-> 8 x float through ONE 16-byte access.  The payload is a uint4 on purpose: a struct of
+// four __nv_bfloat162 is copied with four 32-bit LDG/STG (measured: 32 sectors per request), a uint4
+// member compiles to LDG.128 / STG.128.
+struct __align__(16) bf16x8 { uint4 u; };
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    float2 t;
+    t = bf2_to_f2(p.u.x); f[0] = t.x; f[1] = t.y;
+    t = bf2_to_f2(p.u.y); f[2] = t.x; f[3] = t.y;
+    t = bf2_to_f2(p.u.z); f[4] = t.x; f[5] = t.y;
+    t = bf2_to_f2(p.u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
     bf16x8 p;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    p.u = make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]), f2_to_bf2(f[6], f[7]));
     return p;
 }
 
