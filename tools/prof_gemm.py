@@ -12,6 +12,7 @@ from xdiffusion_b200 import ops  # noqa: E402
 def main():
     dev = "cuda"
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    bn = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     torch.manual_seed(0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     for (n, k, name, kw) in [(1152, 384, "qkv", {}), (384, 384, "proj", {"res": True}),
@@ -23,10 +24,10 @@ def main():
         if kw.get("res"):
             out = torch.randn(M, n, device=dev)
             gate = torch.randn(M // 16, n, device=dev)
-            call = lambda: ops.linear(a, w, bias, gate=gate, gate_rows=16, residual=out, out=out)
+            call = lambda: ops.linear(a, w, bias, gate=gate, gate_rows=16, residual=out, out=out, force_bn=bn)
         else:
             out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
-            call = lambda: ops.linear(a, w, bias, act=kw.get("act", 0), out=out)
+            call = lambda: ops.linear(a, w, bias, act=kw.get("act", 0), out=out, force_bn=bn)
         for _ in range(2):
             call()
         torch.cuda.synchronize()

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -42,6 +43,8 @@ struct TcParams {
     int cpb;            // conv: 64-channel chunks per tap
     int H, W;           // conv: image height / width
     int vec_ok;         // unused by the kernel (all accesses are 16-byte; checked on the host)
+    int direct_ok;      // bf16 out rows are 16-byte aligned: registers can be stored without the transpose
+    int debug;          // experiments only (XDB200_DEBUG): 1 = skip global stores, 2 = skip the MMAs
     Epilogue epi;
 };
 
@@ -113,7 +116,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            uint32_t kbg = 0;                                   // ring position, continuous across tiles
+            int s = 0;                                          // ring position, continuous across tiles
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * BM;
                 const int n0 = (tile % n_tiles) * BN;
@@ -123,9 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     img = m0 / hw;
                     h0 = (m0 - img * hw) / p.W;
                 }
-                for (int kb = 0; kb < nk; ++kb, ++kbg) {
-                    const int s = kbg % C::STAGES;
-                    const uint32_t ph = (kbg / C::STAGES) & 1;
+                for (int kb = 0; kb < nk; ++kb) {
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sA = smem + s * C::STAGE_BYTES;
                     uint8_t* sB = sA + C::A_BYTES;
@@ -145,36 +147,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         else ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, 0, h0, img);
                     }
                     ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                    if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
-        uint32_t kbg = 0, it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1;
-            ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
-            ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + buf * BN;
-            for (int kb = 0; kb < nk; ++kb, ++kbg) {
-                const int s = kbg % C::STAGES;
-                const uint32_t ph = (kbg / C::STAGES) & 1;
-                ptx::mbar_wait(&full_bar[s], ph);
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
+            const uint64_t desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem));
+            uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = it & 1;
+                ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                 ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = ptx::smem_u32(smem + s * C::STAGE_BYTES);
-                    const uint64_t da = ptx::smem_desc_sw128(a_addr);
-                    const uint64_t db = ptx::smem_desc_sw128(a_addr + C::A_BYTES);
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    // descriptors differ between stages only in the start-address field (16-byte units)
+                    const uint64_t da = desc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
+                    const uint64_t db = da + (C::A_BYTES >> 4);
+                    if (p.debug != 2 && p.debug != 4) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
-                        ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
+                            ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[s]);
                     if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[buf]);
+                    if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -186,17 +192,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const Epilogue& e = p.epi;
         const int sub_row = lane >> 3;                  // coalesced pass: 4 rows x 8 lanes x 4 columns
         const int sub_col = (lane & 7) * 4;
+        const bool res_f32 = e.res_dtype == XD_F32, out_f32 = e.out_dtype == XD_F32;
+        const bool direct_bf16 = C::CHUNKS_PER_GROUP % 2 == 0 && !out_f32 && !e.gate && !e.residual && (p.N % 8 == 0) && p.direct_ok;
+        const int res_ld = (int)e.res_ld, out_ld = (int)e.out_ld;     // per-tile row offsets fit 32 bits
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / n_tiles) * BM;
+            const int m0 = (tile / n_tiles) * BM + q * 32;             // first row of this warp's 32-row band
             const int n0 = (tile % n_tiles) * BN;
             const uint32_t buf = it & 1;
+            // per-tile row bookkeeping, hoisted out of the chunk loop (all 32-bit)
+            const int rows_left = p.M - m0;                             // rows rr < rows_left are valid
+            unsigned gate_row[8];
+            if (e.gate) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gate_row[i] = (unsigned)(m0 + i * 4 + sub_row) / (unsigned)e.gate_rows;
+            }
+            const char* res_band = (const char*)e.residual + (long long)m0 * e.res_ld * (res_f32 ? 4 : 2);
+            char* out_band = (char*)e.out + (long long)m0 * e.out_ld * (out_f32 ? 4 : 2);
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+            if (p.debug >= 3) {                         // experiment: mainloop only
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                continue;
+            }
 #pragma unroll 1
             for (int ci = 0; ci < (C::CHUNKS_PER_GROUP > 0 ? C::CHUNKS_PER_GROUP : 1); ++ci) {
                 const int c = grp * C::CHUNKS_PER_GROUP + ci;
+                const int nc = n0 + c * 32;             // first global column of this chunk
+                // bias for this thread's 32 columns is requested before the TMEM load so that both
+                // latencies overlap
+                float4 bv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias && nc + 4 * j < p.N) bv[j] = __ldg(reinterpret_cast<const float4*>(e.bias + nc) + j);
+                }
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(t_addr + c * 32, r);
                 ptx::tmem_ld_wait();
@@ -205,18 +238,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
                 }
-                const int nc = n0 + c * 32;             // first global column of this chunk
+                if (direct_bf16) {
+                    // No gate / residual, bf16 out.  Convert in registers, stage the warp's 32 rows x 64
+                    // columns as bf16 (128-byte rows, XOR-swizzled 16-byte chunks: conflict-free both ways)
+                    // and write full 128-byte lines: 8 lanes x 16 B per row, 4 rows per instruction.
+                    uint8_t* sb = reinterpret_cast<uint8_t*>(st);
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        uint4 u;
+                        u.x = f2_to_bf2(act_fast<ACT>(__uint_as_float(r[4 * j]) + bv[j].x),
+                                        act_fast<ACT>(__uint_as_float(r[4 * j + 1]) + bv[j].y));
+                        u.y = f2_to_bf2(act_fast<ACT>(__uint_as_float(r[4 * j + 2]) + bv[j].z),
+                                        act_fast<ACT>(__uint_as_float(r[4 * j + 3]) + bv[j].w));
+                        u.z = f2_to_bf2(act_fast<ACT>(__uint_as_float(r[4 * j + 4]) + bv[j + 1].x),
+                                        act_fast<ACT>(__uint_as_float(r[4 * j + 5]) + bv[j + 1].y));
+                        u.w = f2_to_bf2(act_fast<ACT>(__uint_as_float(r[4 * j + 6]) + bv[j + 1].z),
+                                        act_fast<ACT>(__uint_as_float(r[4 * j + 7]) + bv[j + 1].w));
+                        const int chunk16 = (ci & 1) * 4 + (j >> 1);           // 16-byte chunk inside the 128-byte row
+                        *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = u;
+                    }
+                    if (ci & 1) {                                              // 64 columns staged: flush
+                        __syncwarp();
+                        const int col = nc - 32 + (lane & 7) * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + sub_row;
+                            const uint4 u = *reinterpret_cast<const uint4*>(sb + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                            if (rr < rows_left && col < p.N && p.debug != 1)
+                                *reinterpret_cast<uint4*>(out_band + (unsigned)(rr * out_ld + col) * 2u) = u;
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 // ---- column-wise part on the row-per-thread fragment: bias, activation
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e.bias && nc + j < p.N) b = __ldg(reinterpret_cast<const float4*>(e.bias + nc + j));
+                for (int j = 0; j < 8; ++j) {
                     float4 v;
-                    v.x = act_fast<ACT>(__uint_as_float(r[j]) + b.x);
-                    v.y = act_fast<ACT>(__uint_as_float(r[j + 1]) + b.y);
-                    v.z = act_fast<ACT>(__uint_as_float(r[j + 2]) + b.z);
-                    v.w = act_fast<ACT>(__uint_as_float(r[j + 3]) + b.w);
-                    *reinterpret_cast<float4*>(st + lane * STAGE_LD + j) = v;
+                    v.x = act_fast<ACT>(__uint_as_float(r[4 * j]) + bv[j].x);
+                    v.y = act_fast<ACT>(__uint_as_float(r[4 * j + 1]) + bv[j].y);
+                    v.z = act_fast<ACT>(__uint_as_float(r[4 * j + 2]) + bv[j].z);
+                    v.w = act_fast<ACT>(__uint_as_float(r[4 * j + 3]) + bv[j].w);
+                    *reinterpret_cast<float4*>(st + lane * STAGE_LD + 4 * j) = v;
                 }
                 __syncwarp();
                 // ---- row-contiguous part: gate, residual, store (8 lanes cover one 32-column row segment)
@@ -226,20 +289,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + sub_row;
-                    const long long m = (long long)m0 + q * 32 + rr;
-                    const bool ok = col_ok && m < p.M;
+                    const bool ok = col_ok && rr < rows_left;
                     v[i] = *reinterpret_cast<const float4*>(st + rr * STAGE_LD + sub_col);
                     g[i] = make_float4(1.f, 1.f, 1.f, 1.f);
                     rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && e.gate)
-                        g[i] = __ldg(reinterpret_cast<const float4*>(e.gate + (m / e.gate_rows) * e.gate_ld + col));
+                    if (ok && e.gate) g[i] = __ldg(reinterpret_cast<const float4*>(e.gate + (long long)gate_row[i] * e.gate_ld + col));
                     if (ok && e.residual) {
-                        if (e.res_dtype == XD_F32) {
-                            rs[i] = *reinterpret_cast<const float4*>((const float*)e.residual + m * e.res_ld + col);
+                        if (res_f32) {
+                            rs[i] = *reinterpret_cast<const float4*>(res_band + (unsigned)(rr * res_ld + col) * 4u);
                         } else {
-                            const uint2 u = *reinterpret_cast<const uint2*>((const bf16*)e.residual + m * e.res_ld + col);
-                            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-                            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                            const uint2 u = *reinterpret_cast<const uint2*>(res_band + (unsigned)(rr * res_ld + col) * 2u);
+                            const float2 lo = bf2_to_f2(u.x), hi = bf2_to_f2(u.y);
                             rs[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
                         }
                     }
@@ -247,19 +307,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + sub_row;
-                    const long long m = (long long)m0 + q * 32 + rr;
-                    if (!(col_ok && m < p.M)) continue;
+                    if (!(col_ok && rr < rows_left)) continue;
                     float4 o;
                     o.x = fmaf(v[i].x, g[i].x, rs[i].x); o.y = fmaf(v[i].y, g[i].y, rs[i].y);
                     o.z = fmaf(v[i].z, g[i].z, rs[i].z); o.w = fmaf(v[i].w, g[i].w, rs[i].w);
-                    if (e.out_dtype == XD_F32) {
-                        *reinterpret_cast<float4*>((float*)e.out + m * e.out_ld + col) = o;
+                    if (out_f32) {
+                        *reinterpret_cast<float4*>(out_band + (unsigned)(rr * out_ld + col) * 4u) = o;
                     } else {
-                        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                        uint2 u;
-                        u.x = *reinterpret_cast<uint32_t*>(&lo);
-                        u.y = *reinterpret_cast<uint32_t*>(&hi);
-                        *reinterpret_cast<uint2*>((bf16*)e.out + m * e.out_ld + col) = u;
+                        *reinterpret_cast<uint2*>(out_band + (unsigned)(rr * out_ld + col) * 2u) =
+                            make_uint2(f2_to_bf2(o.x, o.y), f2_to_bf2(o.z, o.w));
                     }
                 }
                 __syncwarp();                           // transpose buffer is reused by the next chunk
@@ -343,6 +399,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 int epilogue_vec_ok(const Epilogue& e, int N) {
     bool ok = aligned16(e.out) && aligned16(e.bias) && aligned16(e.gate) && aligned16(e.residual);
     ok = ok && (N % 4 == 0) && (e.out_ld % 4 == 0) && (e.res_ld % 4 == 0) && (e.gate_ld % 4 == 0);
+    ok = ok && e.out_ld < (1 << 22) && e.res_ld < (1 << 22);      // 32-bit byte offsets inside a 128-row tile
     return ok ? 1 : 0;
 }
 
@@ -417,6 +474,8 @@ extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, lon
     p.epi = Epilogue{bias, gate, residual, out, gate_ld, res_ld, out_ld, act, gate_rows, res_dtype, out_dtype};
     p.vec_ok = epilogue_vec_ok(p.epi, N);
     XD_CHECK_ARG(p.vec_ok);
+    p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
+    p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
     const int bn = force_bn ? force_bn : pick_bn(N, M);
     CUtensorMap ta0, ta1, tb;
     int rc;
@@ -442,6 +501,8 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     p.epi = Epilogue{bias, nullptr, residual, out, 0, res_ld, out_ld, act, 1, res_dtype, out_dtype};
     p.vec_ok = epilogue_vec_ok(p.epi, Cout);
     XD_CHECK_ARG(p.vec_ok);
+    p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
+    p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
     const int bn = force_bn ? force_bn : pick_bn(Cout, p.M);
     CUtensorMap ta0, ta1, tb;
     int rc;
