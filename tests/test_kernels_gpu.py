@@ -64,7 +64,7 @@ def test_gemm_plain(ops, backend, M, N, K, monkeypatch):
     assert rel_l2(out, _gemm_ref(a, w, bias, 2, None, 1, None)) < 3e-3
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 192, 256, 1128, 1256])      # 1xxx = CTA-pair (cta_group::2) 256 x xxx tiles
 def test_gemm_tile_widths_and_epilogues(ops, bn):
     g = torch.Generator().manual_seed(bn)
     M, N, K, rows = 512, 512, 256, 16

@@ -48,14 +48,15 @@ struct TcParams {
     Epilogue epi;
 };
 
-template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
+template <int BN, int CG = 1> struct Cfg {
+    static constexpr int B_ROWS = BN / CG;                       // B rows staged by one CTA
+    static constexpr int STAGES = (B_ROWS <= 64) ? 6 : (B_ROWS <= 128 ? 5 : (B_ROWS <= 192 ? 4 : 3));
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
     static constexpr int SMEM = STAGES * STAGE_BYTES + XPOSE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;                       // 128 / 256 / 512: powers of two
+    static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // power of two
     static constexpr int CHUNKS = BN / 32;
     static constexpr int CHUNKS_PER_GROUP = CHUNKS / 2;
 };
@@ -64,17 +65,26 @@ template <int BN> struct Cfg {
 template <int ACT> __device__ __forceinline__ float act_fast(float x) {
     if constexpr (ACT == XD_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
     if constexpr (ACT == XD_ACT_GELU_TANH) {
-        const float u = x * (1.5957691216057308f + 0.07135481627260025f * x * x);   // 2*sqrt(2/pi)*(x+0.044715x^3)
-        return __fdividef(x, 1.0f + __expf(-u));
+        // 0.5 x (1 + tanh(sqrt(2/pi)(x + 0.044715 x^3))) with ONE MUFU op (tanh.approx): the exp + rcp form
+        // is MUFU-bound in the fc1 epilogue (2 MUFU x 25 M elements per launch)
+        const float u = x * (0.7978845608028654f + 0.035677408136300125f * x * x);
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+        const float hx = 0.5f * x;
+        return fmaf(hx, t, hx);
     }
     return x;
 }
 
-template <int BN, int ACT>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
+// 256 x BN tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one
+// M = 256 MMA that reads both CTAs' shared memory and writes both CTAs' TMEM -- half the shared-memory
+// and L2 operand traffic per FLOP, which is what bounds the 1-CTA kernel (see profiles/README.md).
+template <int BN, int ACT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -88,28 +98,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int nk = p.nk0 + p.nk1;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = n_tiles * ((p.M + BM - 1) / BM);
+    const int total_tiles = n_tiles * ((p.M + BM * CG - 1) / (BM * CG));
+    const int rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;     // 0 = leader (issues the MMAs)
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmB);
         if (p.nk1) ptx::prefetch_tmap(&tmA1);
         for (int s = 0; s < C::STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], CG);                // one arrive.expect_tx per CTA of the group
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&tmem_full_bar[b], 1);
-            ptx::mbar_init(&tmem_empty_bar[b], EPI_WARPS);
+            ptx::mbar_init(&tmem_empty_bar[b], EPI_WARPS * CG);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if constexpr (CG == 2) {
+            ptx::tmem_alloc_2sm(tmem_ptr, C::TMEM_COLS);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();             // peer barriers initialised before any remote arrive
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -118,9 +136,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             int s = 0;                                          // ring position, continuous across tiles
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM;
-                const int n0 = (tile % n_tiles) * BN;
+            for (int tile = first_tile; tile < total_tiles && p.debug != 7; tile += tile_step) {
+                const int m0 = (tile / n_tiles) * (BM * CG) + rank * BM;     // this CTA's 128 rows of A
+                const int n0 = (tile % n_tiles) * BN + rank * C::B_ROWS;     // this CTA's share of the B tile
                 int img = 0, h0 = 0;
                 if (p.conv) {
                     const int hw = p.H * p.W;
@@ -131,54 +149,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sA = smem + s * C::STAGE_BYTES;
                     uint8_t* sB = sA + C::A_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                    const CUtensorMap* tm = &tmA0;
+                    int c0, c1, c2, c3;
                     if (kb < p.nk0) {
                         if (!p.conv) {
-                            ptx::tma_load_4d(sA, &tmA0, &full_bar[s], kb * BK, m0, 0, 0);
+                            c0 = kb * BK; c1 = m0; c2 = 0; c3 = 0;
                         } else {
                             const int tap = kb / p.cpb;
                             const int cc = kb - tap * p.cpb;
-                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                            ptx::tma_load_4d(sA, &tmA0, &full_bar[s], cc * BK, dx, h0 + dy, img);
+                            c0 = cc * BK; c1 = tap % 3 - 1; c2 = h0 + tap / 3 - 1; c3 = img;
                         }
                     } else {
+                        tm = &tmA1;
                         const int k1 = kb - p.nk0;
-                        if (!p.conv) ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, m0, 0, 0);
-                        else ptx::tma_load_4d(sA, &tmA1, &full_bar[s], k1 * BK, 0, h0, img);
+                        if (!p.conv) { c0 = k1 * BK; c1 = m0; c2 = 0; c3 = 0; }
+                        else { c0 = k1 * BK; c1 = 0; c2 = h0; c3 = img; }
                     }
-                    ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                    if (p.debug >= 5) {                          // experiment: no operand traffic at all
+                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&full_bar[s]);
+                        else ptx::mbar_arrive(&full_bar[s]);
+                    } else if constexpr (CG == 2) {
+                        ptx::mbar_arrive_expect_tx_leader(&full_bar[s], C::STAGE_BYTES);
+                        ptx::tma_load_4d_2sm(sA, tm, &full_bar[s], c0, c1, c2, c3);
+                        ptx::tma_load_2d_2sm(sB, &tmB, &full_bar[s], kb * BK, n0);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                        ptx::tma_load_4d(sA, tm, &full_bar[s], c0, c1, c2, c3);
+                        ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                    }
                     if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
+        // ------------------------------------------------------------ MMA issuer
+        // The whole warp runs the (warp-uniform) loop so that descriptors, stage and phase live in
+        // uniform registers; one elected lane issues the tcgen05 instructions.
+        if (rank == 0) {
+            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM * CG, BN);
             const uint64_t desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem));
             uint32_t it = 0;
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
                 const uint32_t buf = it & 1;
                 ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * BN;
                 for (int kb = 0; kb < nk; ++kb) {
-                    ptx::mbar_wait(&full_bar[s], ph);
-                    ptx::tc_fence_after();
+                    if (p.debug != 7) {
+                        ptx::mbar_wait(&full_bar[s], ph);
+                        ptx::tc_fence_after();
+                    }
                     // descriptors differ between stages only in the start-address field (16-byte units)
                     const uint64_t da = desc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
                     const uint64_t db = da + (C::A_BYTES >> 4);
-                    if (p.debug != 2 && p.debug != 4) {
+                    if (ptx::elect_one()) {
+                        if (p.debug != 2 && p.debug != 4) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
-                            ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
+                                if constexpr (CG == 2) ptx::umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                                else ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            }
+                        }
+                        if constexpr (CG == 2) {
+                            if (p.debug != 7) ptx::umma_commit_2sm(&empty_bar[s]);
+                            if (kb == nk - 1) ptx::umma_commit_2sm(&tmem_full_bar[buf]);
+                        } else {
+                            if (p.debug != 7) ptx::umma_commit(&empty_bar[s]);
+                            if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[buf]);
                         }
                     }
-                    ptx::umma_commit(&empty_bar[s]);
-                    if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[buf]);
+                    __syncwarp();
                     if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -193,11 +236,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int sub_row = lane >> 3;                  // coalesced pass: 4 rows x 8 lanes x 4 columns
         const int sub_col = (lane & 7) * 4;
         const bool res_f32 = e.res_dtype == XD_F32, out_f32 = e.out_dtype == XD_F32;
-        const bool direct_bf16 = C::CHUNKS_PER_GROUP % 2 == 0 && !out_f32 && !e.gate && !e.residual && (p.N % 8 == 0) && p.direct_ok;
+        const bool direct_bf16 = C::CHUNKS_PER_GROUP >= 2 && !out_f32 && !e.gate && !e.residual && (p.N % 8 == 0) && p.direct_ok;
         const int res_ld = (int)e.res_ld, out_ld = (int)e.out_ld;     // per-tile row offsets fit 32 bits
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / n_tiles) * BM + q * 32;             // first row of this warp's 32-row band
+        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+            const int m0 = (tile / n_tiles) * (BM * CG) + rank * BM + q * 32;   // first row of this warp's 32-row band
             const int n0 = (tile % n_tiles) * BN;
             const uint32_t buf = it & 1;
             // per-tile row bookkeeping, hoisted out of the chunk loop (all 32-bit)
@@ -212,10 +255,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-            if (p.debug >= 3) {                         // experiment: mainloop only
+            if (p.debug >= 3 && p.debug != 6) {         // experiment: mainloop only
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                if (lane == 0) {
+                    if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
+                    else ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                }
                 continue;
             }
 #pragma unroll 1
@@ -236,7 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (ci == C::CHUNKS_PER_GROUP - 1) {    // last TMEM read of this tile by this warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                    if (lane == 0) {
+                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
+                        else ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                    }
                 }
                 if (direct_bf16) {
                     // No gate / residual, bf16 out.  Convert in registers, stage the warp's 32 rows x 64
@@ -257,14 +306,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const int chunk16 = (ci & 1) * 4 + (j >> 1);           // 16-byte chunk inside the 128-byte row
                         *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = u;
                     }
-                    if (ci & 1) {                                              // 64 columns staged: flush
+                    const bool last = ci == C::CHUNKS_PER_GROUP - 1;
+                    if ((ci & 1) || last) {                                    // 64 (or a trailing 32) columns staged: flush
                         __syncwarp();
-                        const int col = nc - 32 + (lane & 7) * 8;
+                        const int staged = (ci & 1) ? 64 : 32;
+                        const int col = nc - (staged - 32) + (lane & 7) * 8;
+                        const bool lane_ok = (lane & 7) * 8 < staged && col < p.N;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = i * 4 + sub_row;
                             const uint4 u = *reinterpret_cast<const uint4*>(sb + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-                            if (rr < rows_left && col < p.N && p.debug != 1)
+                            if (rr < rows_left && lane_ok && p.debug != 1)
                                 *reinterpret_cast<uint4*>(out_band + (unsigned)(rr * out_ld + col) * 2u) = u;
                         }
                         __syncwarp();
@@ -323,10 +375,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();             // no remote arrive / peer smem read after a CTA exits
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if constexpr (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -413,45 +467,78 @@ int sm_count() {
     return n;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, int CG>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
     static bool configured = false;
+    auto kernel = gemm_tc_kernel<BN, ACT, CG>;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM) !=
-            cudaSuccess) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
             return XD_ERR_CUDA;
         }
         configured = true;
     }
-    const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());      // persistent: <= one CTA per SM
-    gemm_tc_kernel<BN, ACT><<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(a0, a1, b, p);
-    XD_CHECK_LAUNCH();
+    const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM * CG - 1) / (BM * CG));
+    // persistent: <= one CTA (pair) per SM (pair)
+    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count() / CG) * CG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, a0, a1, b, p) != cudaSuccess) {
+        xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        return XD_ERR_CUDA;
+    }
     return XD_OK;
 }
 
-int pick_bn(int N, int M) {
-    (void)M;
-    return N <= 64 ? 64 : 128;
+// Tile shape: (bn, cg).  force: 0 = auto; 64/128/256 = 1-CTA tiles; 1128/1256 = CTA-pair 256 x 128 / 256 x 256.
+void pick_tile(int N, int M, int force, int* bn, int* cg) {
+    if (force >= 1000) { *cg = 2; *bn = force - 1000; return; }
+    if (force) { *cg = 1; *bn = force; return; }
+    // tcgen05.mma 128 x N x 16 from shared memory runs at ~half rate for N = 128 (operand reads
+    // saturate the shared-memory port) and at ~75% of peak for N >= 192 (measured, profiles/README.md),
+    // so take the widest tile that divides N; a CTA pair for the N = 128 leftovers.
+    static const int mode = getenv("XDB200_CG") ? atoi(getenv("XDB200_CG")) : 1;
+    *cg = 1;
+    if (N <= 64) { *bn = 64; return; }
+    const long long m_tiles = (M + BM - 1) / BM;
+    auto fills = [&](int w) { return m_tiles * ((N + w - 1) / w) >= sm_count(); };   // at least one full wave
+    if (N % 192 == 0 && fills(192)) *bn = 192;          // measured: 192 beats 256 when both divide N
+    else if (N % 256 == 0 && fills(256)) *bn = 256;
+    else if (N > 1024 && fills(256)) *bn = 256;
+    else {
+        *bn = 128;
+        if (mode == 2 && M > BM) *cg = 2;
+    }
 }
 
-int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p,
+int dispatch(int bn, int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p,
              cudaStream_t st) {
-#define XD_TC_CASE(BN_)                                                                    \
-    case BN_:                                                                              \
-        switch (p.epi.act) {                                                               \
-            case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE>(a0, a1, b, p, st);           \
-            case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU>(a0, a1, b, p, st);           \
-            case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH>(a0, a1, b, p, st); \
-        }                                                                                  \
-        break;
-    switch (bn) {
-        XD_TC_CASE(64)
-        XD_TC_CASE(128)
-        XD_TC_CASE(256)
+#define XD_TC_CASE(BN_, CG_)                                                                    \
+    if (bn == BN_ && cg == CG_) {                                                               \
+        switch (p.epi.act) {                                                                    \
+            case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE, CG_>(a0, a1, b, p, st);           \
+            case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU, CG_>(a0, a1, b, p, st);           \
+            case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH, CG_>(a0, a1, b, p, st); \
+        }                                                                                       \
     }
+    XD_TC_CASE(64, 1)
+    XD_TC_CASE(128, 1)
+    XD_TC_CASE(192, 1)
+    XD_TC_CASE(256, 1)
+    XD_TC_CASE(128, 2)
+    XD_TC_CASE(256, 2)
 #undef XD_TC_CASE
+    xd_set_error(__FILE__, __LINE__, "unsupported tile shape");
     return XD_ERR_ARG;
 }
 
@@ -476,14 +563,15 @@ extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, lon
     XD_CHECK_ARG(p.vec_ok);
     p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
     p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
-    const int bn = force_bn ? force_bn : pick_bn(N, M);
+    int bn, cg;
+    pick_tile(N, M, force_bn, &bn, &cg);
     CUtensorMap ta0, ta1, tb;
     int rc;
     if ((rc = tmap_rows(&ta0, A, M, K, lda, BM))) return rc;
     ta1 = ta0;
     if (A2 && (rc = tmap_rows(&ta1, A2, M, K2, lda2, BM))) return rc;
-    if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, bn))) return rc;
-    return dispatch(bn, ta0, ta1, tb, p, (cudaStream_t)stream);
+    if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, bn / cg))) return rc;
+    return dispatch(bn, cg, ta0, ta1, tb, p, (cudaStream_t)stream);
 }
 
 extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
@@ -503,13 +591,14 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     XD_CHECK_ARG(p.vec_ok);
     p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
     p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
-    const int bn = force_bn ? force_bn : pick_bn(Cout, p.M);
+    int bn, cg;
+    pick_tile(Cout, p.M, force_bn, &bn, &cg);
     CUtensorMap ta0, ta1, tb;
     int rc;
     if ((rc = tmap_nhwc(&ta0, X, nimg, H, W, C, ldx))) return rc;
     ta1 = ta0;
     if (Xs && (rc = tmap_nhwc(&ta1, Xs, nimg, H, W, Cs, lds))) return rc;
     const long long ktot = 9LL * C + Cs;
-    if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, bn))) return rc;
-    return dispatch(bn, ta0, ta1, tb, p, (cudaStream_t)stream);
+    if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, bn / cg))) return rc;
+    return dispatch(bn, cg, ta0, ta1, tb, p, (cudaStream_t)stream);
 }
