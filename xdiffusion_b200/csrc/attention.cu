@@ -83,6 +83,7 @@ constexpr int RS16 = D + 4;                  // padded key/value row: 8 consecut
 constexpr int PAIR_LD = 2 * T16 * RS16 + 4;  // +16 B: the two pairs of a warp hit different banks
 __global__ void __launch_bounds__(ROWS)
 attention16_kernel(const AttnParams p) {
+    pdl_prologue();
     extern __shared__ float smem[];             // [8][2][16][64] (+pad)
     const int tid = threadIdx.x;
     const int pl = tid >> 4, row = tid & 15;
@@ -149,6 +150,7 @@ attention16_kernel(const AttnParams p) {
 
 __global__ void __launch_bounds__(ROWS)
 attention_kernel(const AttnParams p) {
+    pdl_prologue();
     extern __shared__ float smem[];             // [pairs][2][KC][D]
     const int pairs = p.Tq >= ROWS ? 1 : ROWS / p.Tq;
     const int slabs = p.Tq >= ROWS ? p.Tq / ROWS : 1;
@@ -283,7 +285,7 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
             configured16 = true;
         }
         const long long nb = ((long long)B * H + 7) / 8;
-        attention16_kernel<<<(unsigned)nb, ROWS, smem16, (cudaStream_t)stream>>>(p);
+        xd_launch(attention16_kernel, (unsigned)nb, ROWS, smem16, (cudaStream_t)stream, p);
         XD_CHECK_LAUNCH();
         return XD_OK;
     }
@@ -296,7 +298,7 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
         cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * KC * D * 4);
         configured = true;
     }
-    attention_kernel<<<(unsigned)blocks, ROWS, smem, (cudaStream_t)stream>>>(p);
+    xd_launch(attention_kernel, (unsigned)blocks, ROWS, smem, (cudaStream_t)stream, p);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

@@ -38,6 +38,7 @@ __device__ __forceinline__ uint32_t idesc(int M, int N, bool b_mn_major) {
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -75,6 +76,7 @@ attention_tc256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t tmem_s = tmem, tmem_o = tmem + 256;
+    pdl_wait();                                          // prologue above overlaps the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -232,7 +234,7 @@ int xd_attention_tc256_try(const void* q, long long q_bs, long long q_hs, long l
         configured = true;
     }
     Params p{(bf16*)o, o_bs, o_hs, o_rs, H, (int)q_hs, (int)k_hs, (int)v_hs, scale * 1.4426950408889634f};
-    attention_tc256_kernel<<<(unsigned)(B * H * 2), THREADS, SMEM, st>>>(tq, tk, tv, p);
+    xd_launch(attention_tc256_kernel, (unsigned)(B * H * 2), THREADS, SMEM, st, tq, tk, tv, p);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

@@ -14,6 +14,34 @@
 
 void xd_set_error(const char* file, int line, const char* msg);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// pdl_launch_dependents() + pdl_wait(): the NEXT kernel of the stream (or CUDA graph) may be scheduled
+// as soon as all CTAs of this one have started, does its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) and then blocks in griddepcontrol.wait until this kernel has completed and its
+// memory is visible.  This removes the launch gap between the ~100-230 kernels of a sampling step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+bool xd_pdl_enabled();      // XDB200_PDL=0 disables (abi.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t xd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = xd_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum { XD_F32 = 0, XD_BF16 = 1 };
 enum { XD_ACT_NONE = 0, XD_ACT_SILU = 1, XD_ACT_GELU_TANH = 2 };
 

@@ -17,6 +17,7 @@ __device__ __forceinline__ float load_time(const void* t, int is_i64, long long 
 __global__ void sinusoid_kernel(const void* t, int is_i64, int B, const float* __restrict__ freq, int half, int mode,
                                 float max_time, float clip_lo, float clip_hi, int order, float* out_f32,
                                 bf16* out_bf16) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, j = i % half;
@@ -37,6 +38,7 @@ __global__ void sinusoid_kernel(const void* t, int is_i64, int B, const float* _
 
 // act + cast, n elements
 __global__ void act_cast_kernel(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = in_dtype == XD_F32 ? ((const float*)in)[i] : __bfloat162float(((const bf16*)in)[i]);
@@ -48,6 +50,7 @@ __global__ void act_cast_kernel(const void* in, int in_dtype, void* out, int out
 // c = table[label] + temb ; optionally also silu(c) as bf16 (input of every adaLN GEMM)
 __global__ void class_combine_kernel(const float* __restrict__ table, const long long* __restrict__ labels,
                                      const float* __restrict__ temb, int B, int Dm, float* c_out, bf16* silu_out) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Dm) return;
     const int b = i / Dm, d = i % Dm;
@@ -59,6 +62,7 @@ __global__ void class_combine_kernel(const float* __restrict__ table, const long
 
 // x fp32 NCHW -> bf16 [B*gh*gw, C*p*p], column order (c, py, px) = flattened Conv2d weight
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p, bf16* out) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int gh = H / p, gw = W / p, K = C * p * p;
     const long long total = (long long)B * gh * gw * K;
@@ -74,6 +78,7 @@ __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H
 // y fp32 [B*gh*gw, p*p*c] -> fp32 NCHW : img[n, c, h*p+py, w*p+px] = y[n, h, w, py, px, c]  (dit.py:187-204)
 __global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy, int B, int C, int H, int W, int p,
                                   float* out) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * C * H * W;
     if (i >= total) return;
@@ -87,6 +92,7 @@ __global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy, in
 // out[r, c] = a[r, c] + b[(r % period), c]   (fp32; token position embeddings: period = tokens per sample)
 __global__ void add_rows_periodic_kernel(const float* a, const float* b, long long rows, int cols, int period,
                                          float* out) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const long long r = i / cols;
@@ -96,6 +102,7 @@ __global__ void add_rows_periodic_kernel(const float* a, const float* b, long lo
 
 // out[g, r, c] = a[r, c] + tab[g, c]    (PixArt adaLN-single: table(6*D) + t0, for all blocks at once)
 __global__ void add_table_kernel(const float* a, const float* tab, int G, int R, int Ccols, float* out) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)G * R * Ccols;
     if (i >= total) return;
@@ -108,6 +115,7 @@ __global__ void add_table_kernel(const float* a, const float* tab, int G, int R,
 // 2x2 average pool / nearest 2x upsample over NHWC bf16 (8 channels per thread)
 __global__ void avgpool2_kernel(const bf16* __restrict__ x, long long ldx, int nimg, int H, int W, int C, bf16* out,
                                 long long ldo) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int V = C / 8, Ho = H / 2, Wo = W / 2;
     const long long total = (long long)nimg * Ho * Wo * V;
@@ -133,6 +141,7 @@ __global__ void avgpool2_kernel(const bf16* __restrict__ x, long long ldx, int n
 
 __global__ void upsample2_kernel(const bf16* __restrict__ x, long long ldx, int nimg, int H, int W, int C, bf16* out,
                                  long long ldo) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int V = C / 8, Ho = H * 2, Wo = W * 2;
     const long long total = (long long)nimg * Ho * Wo * V;
@@ -148,6 +157,7 @@ __global__ void upsample2_kernel(const bf16* __restrict__ x, long long ldx, int 
 // rows x C bf16 copy between strided buffers (skip-connection concat slots)
 __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int C, bf16* out,
                                  long long ldo) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int V = C / 8;
     if (i >= rows * V) return;
@@ -159,6 +169,7 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long
 // eps = u + w (c - u)   (samplers/ancestral.py:229-231), float4 vectorised
 __global__ void cfg_kernel(const float4* __restrict__ c, const float4* __restrict__ u, float w, float4* out,
                            long long n4) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 a = c[i], b = u[i];
@@ -178,7 +189,7 @@ extern "C" int xd_timestep_embed(const void* t, int t_is_i64, int B, const float
                                  float max_time, float clip_lo, float clip_hi, int order, float* out_f32,
                                  void* out_bf16, void* stream) {
     XD_CHECK_ARG(t && freq && B > 0 && half > 0 && (out_f32 || out_bf16) && mode >= 0 && mode <= 2);
-    sinusoid_kernel<<<blocks_for((long long)B * half), 256, 0, (cudaStream_t)stream>>>(
+    xd_launch(sinusoid_kernel, blocks_for((long long)B * half), 256, 0, (cudaStream_t)stream, 
         t, t_is_i64, B, freq, half, mode, max_time, clip_lo, clip_hi, order, out_f32, (bf16*)out_bf16);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -187,7 +198,7 @@ extern "C" int xd_timestep_embed(const void* t, int t_is_i64, int B, const float
 extern "C" int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n,
                            void* stream) {
     XD_CHECK_ARG(in && out && n > 0);
-    act_cast_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(in, in_dtype, out, out_dtype, act, n);
+    xd_launch(act_cast_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, in, in_dtype, out, out_dtype, act, n);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
@@ -195,7 +206,7 @@ extern "C" int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtyp
 extern "C" int xd_class_combine(const float* table, const long long* labels, const float* temb, int B, int Dm,
                                 float* c_out, void* silu_out, void* stream) {
     XD_CHECK_ARG(temb && (c_out || silu_out) && (table == nullptr) == (labels == nullptr));
-    class_combine_kernel<<<blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream>>>(table, labels, temb, B, Dm,
+    xd_launch(class_combine_kernel, blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream, table, labels, temb, B, Dm,
                                                                                         c_out, (bf16*)silu_out);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -203,7 +214,7 @@ extern "C" int xd_class_combine(const float* table, const long long* labels, con
 
 extern "C" int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out, void* stream) {
     XD_CHECK_ARG(x && out && p > 0 && H % p == 0 && W % p == 0);
-    patchify_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, p,
+    xd_launch(patchify_kernel, blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream, x, B, C, H, W, p,
                                                                                            (bf16*)out);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -212,7 +223,7 @@ extern "C" int xd_patchify(const float* x, int B, int C, int H, int W, int p, vo
 extern "C" int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out,
                              void* stream) {
     XD_CHECK_ARG(y && out && p > 0 && H % p == 0 && W % p == 0);
-    unpatchify_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(y, ldy, B, C, H, W, p,
+    xd_launch(unpatchify_kernel, blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream, y, ldy, B, C, H, W, p,
                                                                                              out);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -221,14 +232,14 @@ extern "C" int xd_unpatchify(const float* y, long long ldy, int B, int C, int H,
 extern "C" int xd_add_rows_periodic(const float* a, const float* b, long long rows, int cols, int period, float* out,
                                     void* stream) {
     XD_CHECK_ARG(a && b && out && period > 0);
-    add_rows_periodic_kernel<<<blocks_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, b, rows, cols, period, out);
+    xd_launch(add_rows_periodic_kernel, blocks_for(rows * cols), 256, 0, (cudaStream_t)stream, a, b, rows, cols, period, out);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
 
 extern "C" int xd_add_table(const float* a, const float* tab, int G, int R, int C, float* out, void* stream) {
     XD_CHECK_ARG(a && tab && out);
-    add_table_kernel<<<blocks_for((long long)G * R * C), 256, 0, (cudaStream_t)stream>>>(a, tab, G, R, C, out);
+    xd_launch(add_table_kernel, blocks_for((long long)G * R * C), 256, 0, (cudaStream_t)stream, a, tab, G, R, C, out);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
@@ -236,7 +247,7 @@ extern "C" int xd_add_table(const float* a, const float* tab, int G, int R, int 
 extern "C" int xd_avgpool2x2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out,
                                   long long ldo, void* stream) {
     XD_CHECK_ARG(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
-    avgpool2_kernel<<<blocks_for((long long)nimg * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+    xd_launch(avgpool2_kernel, blocks_for((long long)nimg * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream, 
         (const bf16*)x, ldx, nimg, H, W, C, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -245,7 +256,7 @@ extern "C" int xd_avgpool2x2_nhwc(const void* x, long long ldx, int nimg, int H,
 extern "C" int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out,
                                   long long ldo, void* stream) {
     XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
-    upsample2_kernel<<<blocks_for((long long)nimg * H * 2 * W * 2 * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+    xd_launch(upsample2_kernel, blocks_for((long long)nimg * H * 2 * W * 2 * (C / 8)), 256, 0, (cudaStream_t)stream, 
         (const bf16*)x, ldx, nimg, H, W, C, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -254,7 +265,7 @@ extern "C" int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H,
 extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, int C, void* out, long long ldo,
                                  void* stream) {
     XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
-    copy_rows_kernel<<<blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, rows, C,
+    xd_launch(copy_rows_kernel, blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, rows, C,
                                                                                    (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -263,7 +274,7 @@ extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, i
 extern "C" int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, long long n,
                               void* stream) {
     XD_CHECK_ARG(cond && uncond && out && n % 4 == 0);
-    cfg_kernel<<<blocks_for(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)cond, (const float4*)uncond, w,
+    xd_launch(cfg_kernel, blocks_for(n / 4), 256, 0, (cudaStream_t)stream, (const float4*)cond, (const float4*)uncond, w,
                                                                     (float4*)out, n / 4);
     XD_CHECK_LAUNCH();
     return XD_OK;

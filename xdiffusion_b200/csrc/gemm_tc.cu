@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using C = Cfg<BN, CG>;
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -130,6 +131,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped with the tail
+    // of the previous kernel; global memory is only touched after this point
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -486,13 +490,15 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = xd_pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kernel, a0, a1, b, p) != cudaSuccess) {
         xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
         return XD_ERR_CUDA;

@@ -13,6 +13,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, int inner,
                 float* __restrict__ stats) {
+    pdl_prologue();
     __shared__ float acc[64][2];
     const int V = C >> 3;                       // 16-byte vectors per pixel
     const int ppb = 256 / V;                    // pixels per block iteration
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
                 long long ss_ld, int ss_div, float eps, int silu, int inner, bf16* __restrict__ out, long long ldo) {
+    pdl_prologue();
     extern __shared__ float coef[];             // [2][C]
     const int sample = blockIdx.y;
     const int cpg = C / G;
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, long long ld, int M, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_ld, int rows_per_mod, float eps,
                    bf16* __restrict__ out, long long ldo) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (m >= M) return;
@@ -149,7 +152,7 @@ extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int
     int slabs = (2 * 148 + nsamples - 1) / nsamples;
     const int ppb = 256 / (C / 8);
     slabs = max(1, min(slabs, (P + ppb * 4 - 1) / (ppb * 4)));
-    gn_stats_kernel<<<dim3(slabs, nsamples), 256, 0, st>>>((const bf16*)x, ld, P, C, groups, inner, stats);
+    xd_launch(gn_stats_kernel, dim3(slabs, nsamples), 256, 0, st, (const bf16*)x, ld, P, C, groups, inner, stats);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
@@ -162,7 +165,7 @@ extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int
     XD_CHECK_ARG(inner >= 1 && nsamples % inner == 0);
     int slabs = (4 * 148 + nsamples - 1) / nsamples;
     slabs = max(1, min(slabs, (P + 15) / 16));
-    gn_apply_kernel<<<dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    xd_launch(gn_apply_kernel, dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream, 
         (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
         inner, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
@@ -176,7 +179,7 @@ extern "C" int xd_layernorm_modulate(const float* x, long long ld, int M, int D,
     XD_CHECK_ARG(rows_per_mod > 0);
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((M + 7) / 8);
-#define XD_LN(NV) ln_modulate_kernel<NV><<<grid, 256, 0, st>>>(x, ld, M, shift, scale, mod_ld, rows_per_mod, eps, (bf16*)out, ldo)
+#define XD_LN(NV) xd_launch(ln_modulate_kernel<NV>, grid, 256, 0, st, x, ld, M, shift, scale, mod_ld, rows_per_mod, eps, (bf16*)out, ldo)
     switch (D / 128) {
         case 1: XD_LN(1); break;
         case 2: XD_LN(2); break;

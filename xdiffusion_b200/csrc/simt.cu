@@ -10,6 +10,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const bf16* __restrict__ A, long long lda, const bf16* __restrict__ A2, long long lda2, int K2,
                  const bf16* __restrict__ Wt, long long ldw, int M, int N, int K, Epilogue e) {
+    pdl_prologue();
     __shared__ float sA[16][65];
     __shared__ float sB[16][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -55,6 +56,7 @@ gemm_simt_kernel(const bf16* __restrict__ A, long long lda, const bf16* __restri
 __global__ void conv3x3_simt_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
                                     const bf16* __restrict__ Xs, long long lds, int Cs,
                                     const bf16* __restrict__ Wp, int Cout, Epilogue e) {
+    pdl_prologue();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)nimg * H * W * Cout;
     if (idx >= total) return;
@@ -85,6 +87,7 @@ __global__ void conv3x3_simt_kernel(const bf16* __restrict__ X, long long ldx, i
 __global__ void conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin, int H, int W,
                                   const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                   bf16* __restrict__ out, long long ldo) {
+    pdl_prologue();
     const int cg = Cout / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)nimg * H * W * cg;
@@ -114,6 +117,7 @@ __global__ void conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin
 __global__ void conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
                                    const float* __restrict__ w /*[Cout][C][3][3]*/, const float* __restrict__ bias,
                                    int Cout, float* __restrict__ out) {
+    pdl_prologue();
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)nimg * H * W;
@@ -148,7 +152,7 @@ extern "C" int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, l
     XD_CHECK_ARG(!gate || gate_rows > 0);
     Epilogue e{bias, gate, residual, out, gate_ld, res_ld, out_ld, act, gate_rows > 0 ? gate_rows : 1, res_dtype, out_dtype};
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)A, lda, (const bf16*)A2, lda2, K2,
+    xd_launch(gemm_simt_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)A, lda, (const bf16*)A2, lda2, K2,
                                                              (const bf16*)Wt, ldw, M, N, K, e);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -161,7 +165,7 @@ extern "C" int xd_conv3x3_bf16_simt(const void* X, long long ldx, int nimg, int 
     XD_CHECK_ARG(X && Wp && out && nimg > 0 && (Xs != nullptr) == (Cs > 0));
     Epilogue e{bias, nullptr, residual, out, 0, res_ld, out_ld, act, 1, res_dtype, out_dtype};
     const long long total = (long long)nimg * H * W * Cout;
-    conv3x3_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    xd_launch(conv3x3_simt_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, 
         (const bf16*)X, ldx, nimg, H, W, C, (const bf16*)Xs, lds, Cs, (const bf16*)Wp, Cout, e);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -171,7 +175,7 @@ extern "C" int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, 
                                       const float* bias, int Cout, void* out, long long ldo, void* stream) {
     XD_CHECK_ARG(x && w && out && Cout % 8 == 0 && ldo % 8 == 0);
     const long long total = (long long)nimg * H * W * (Cout / 8);
-    conv3x3_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, nimg, Cin, H, W, w, bias,
+    xd_launch(conv3x3_in_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, x, nimg, Cin, H, W, w, bias,
                                                                                         Cout, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -181,7 +185,7 @@ extern "C" int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, i
                                        const float* bias, int Cout, float* out, void* stream) {
     XD_CHECK_ARG(X && w && out && C % 8 == 0 && ldx % 8 == 0);
     const long long warps = (long long)nimg * H * W;
-    conv3x3_out_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    xd_launch(conv3x3_out_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream, 
         (const bf16*)X, ldx, nimg, H, W, C, w, bias, Cout, out);
     XD_CHECK_LAUNCH();
     return XD_OK;

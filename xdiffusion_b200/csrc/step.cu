@@ -71,6 +71,7 @@ __device__ __forceinline__ float finish(const StepParams& p, const float* cf, in
 
 // ------------------------------------------------------------------ elementwise variant (clamp / euler)
 __global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
+    pdl_prologue();
     const int i = p.idx_dev ? *p.idx_dev : p.idx_host;
     float cf[8];
 #pragma unroll
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
 // One CTA per sample.  |x0| is sorted in shared memory (bitonic, padded with +inf) to read the two
 // order statistics torch.quantile's 'linear' interpolation uses.
 __global__ void __launch_bounds__(256) step_threshold_kernel(const StepParams p, int npow2) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* s_x0 = sm;                // [n_per_sample]
     float* s_sort = sm + p.n_per_sample;   // [npow2]
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256) step_threshold_kernel(const StepParams p,
 // i <- i - 1 (or set), then refresh the per-step network inputs from host-built tables.
 __global__ void advance_kernel(int* idx, int set_to, const long long* tab_i64, const float* tab_f32a,
                                const float* tab_f32b, long long* out_i64, float* out_f32a, float* out_f32b, int B) {
+    pdl_prologue();
     __shared__ int s_i;
     if (threadIdx.x == 0) {
         int i = set_to >= 0 ? set_to : (set_to == -1 ? *idx - 1 : *idx);   // -2: refresh outputs only
@@ -187,6 +190,7 @@ __global__ void advance_kernel(int* idx, int set_to, const long long* tab_i64, c
 
 // samples = (clamp(x,-1,1)+1)*0.5   (utils.py:62-64)
 __global__ void unnormalize_kernel(const float* x, float* out, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __fmul_rn(__fadd_rn(fminf(fmaxf(x[i], -1.0f), 1.0f), 1.0f), 0.5f);
 }
@@ -212,11 +216,11 @@ extern "C" int xd_sampler_step(int mode, int form, int pred_v, const float* x, c
             cudaFuncSetAttribute(step_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
             configured = true;
         }
-        step_threshold_kernel<<<(unsigned)(n_total / n_per_sample), 256, smem, st>>>(p, npow2);
+        xd_launch(step_threshold_kernel, (unsigned)(n_total / n_per_sample), 256, smem, st, p, npow2);
     } else {
         const long long n4 = n_total / 4;
         const unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 148LL * 8);
-        step_kernel<<<grid, 256, 0, st>>>(p);
+        xd_launch(step_kernel, grid, 256, 0, st, p);
     }
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -226,7 +230,7 @@ extern "C" int xd_schedule_advance(int* idx_dev, int set_to, const long long* ta
                                    const float* tab_f32b, long long* out_i64, float* out_f32a, float* out_f32b,
                                    int B, void* stream) {
     XD_CHECK_ARG(idx_dev && B > 0 && (!out_i64 || tab_i64) && (!out_f32a || tab_f32a) && (!out_f32b || tab_f32b));
-    advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(idx_dev, set_to, tab_i64, tab_f32a, tab_f32b, out_i64,
+    xd_launch(advance_kernel, 1, 256, 0, (cudaStream_t)stream, idx_dev, set_to, tab_i64, tab_f32a, tab_f32b, out_i64,
                                                         out_f32a, out_f32b, B);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -234,7 +238,7 @@ extern "C" int xd_schedule_advance(int* idx_dev, int set_to, const long long* ta
 
 extern "C" int xd_unnormalize(const float* x, float* out, long long n, void* stream) {
     XD_CHECK_ARG(x && out && n > 0);
-    unnormalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    xd_launch(unnormalize_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, x, out, n);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
