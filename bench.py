@@ -86,11 +86,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core the process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_port_images_per_sec(workload, batch, denoise_steps=2):
     """The oracle = CPU restatement of the reference path, all host threads, fp32.  Times
     `denoise_steps` reverse-process steps at the full batch and scales to the 1000-step loop (every
     step has identical cost)."""
     from tests.helpers import oracle_model
+    use_all_host_threads()
     fx = load_fixture(workload)
     om = oracle_model(fx)
     g = torch.Generator().manual_seed(0)
@@ -117,7 +125,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     batch = args.batch
     vals = []
     for _ in range(args.warmup if args.warmup < 1 else 1):

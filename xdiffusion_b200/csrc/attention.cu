@@ -148,6 +148,126 @@ attention16_kernel(const AttnParams p) {
     if (active) store_row(p, b, h, row, o, 1.0f / l);
 }
 
+
+// ---- Tq == Tk == 16 without relative positions: one WARP per (batch, head) on mma.sync m16n8k16 ----
+// The problem is 16x16x64 twice: far too small for a 128-row tcgen05 tile, and on CUDA cores it costs
+// ~3000 instructions per (batch, head).  Here a warp stages Q, K, V (2 KB each, XOR-swizzled 16-byte
+// chunks) with coalesced 16-byte loads, runs 8 + 8 warp-level MMAs (S = Q K^T; O = P V with the S
+// accumulator fragments re-used as the P operand), does the softmax on fragments with quad shuffles
+// and writes O through shared memory as full 128-byte rows: ~150 instructions per (batch, head),
+// which leaves the kernel bandwidth-bound.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr int W16 = 4;                       // warps (= (batch, head) pairs) per CTA
+__global__ void __launch_bounds__(32 * W16)
+attention16_mma_kernel(const AttnParams p) {
+    pdl_prologue();
+    __shared__ __align__(128) uint8_t sm[W16][3][16 * 128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bh = (long long)blockIdx.x * W16 + warp;
+    if (bh >= (long long)p.B * p.H) return;
+    const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+    uint8_t* sQ = sm[warp][0];
+    uint8_t* sK = sm[warp][1];
+    uint8_t* sV = sm[warp][2];
+    const bf16* qp = p.q + b * p.q_bs + h * p.q_hs;
+    const bf16* kp = p.k + b * p.k_bs + h * p.k_hs;
+    const bf16* vp = p.v + b * p.v_bs + h * p.v_hs;
+    {   // 16 rows x 8 chunks of 16 B per tile: 4 chunks per lane per tile, all 12 loads in flight
+        uint4 rq[4], rk[4], rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            rq[i] = *reinterpret_cast<const uint4*>(qp + (long long)row * p.q_rs + c * 8);
+            rk[i] = *reinterpret_cast<const uint4*>(kp + (long long)row * p.k_rs + c * 8);
+            rv[i] = *reinterpret_cast<const uint4*>(vp + (long long)row * p.v_rs + c * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            const int off = row * 128 + ((c ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(sQ + off) = rq[i];
+            *reinterpret_cast<uint4*>(sK + off) = rk[i];
+            *reinterpret_cast<uint4*>(sV + off) = rv[i];
+        }
+    }
+    __syncwarp();
+    const uint32_t aQ = (uint32_t)__cvta_generic_to_shared(sQ), aK = (uint32_t)__cvta_generic_to_shared(sK),
+                   aV = (uint32_t)__cvta_generic_to_shared(sV);
+    // S = Q K^T: two 8-key n-tiles, four 16-wide k-steps over d
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        {   // A: Q rows (lane%8) + 8*((lane/8)%2), chunk 2*ks + lane/16
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8, c = 2 * ks + (lane >> 4);
+            ldsm_x4(aQ + row * 128 + ((c ^ (row & 7)) << 4), a0, a1, a2, a3);
+        }
+        {   // B: K rows (keys) (lane%8) + 8*(lane/16), chunk 2*ks + (lane/8)%2
+            const int row = (lane & 7) + (lane >> 4) * 8, c = 2 * ks + ((lane >> 3) & 1);
+            ldsm_x4(aK + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
+        }
+        mma_bf16_16816(s0, a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s1, a0, a1, a2, a3, b2, b3);
+    }
+    // softmax over the 16 keys of rows r = lane/4 (c0, c1) and r + 8 (c2, c3); a row lives in one quad
+    float m_lo = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])), m_hi = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    const float c = p.scale * 1.4426950408889634f;
+    s0[0] = exp2f((s0[0] - m_lo) * c); s0[1] = exp2f((s0[1] - m_lo) * c); s1[0] = exp2f((s1[0] - m_lo) * c); s1[1] = exp2f((s1[1] - m_lo) * c);
+    s0[2] = exp2f((s0[2] - m_hi) * c); s0[3] = exp2f((s0[3] - m_hi) * c); s1[2] = exp2f((s1[2] - m_hi) * c); s1[3] = exp2f((s1[3] - m_hi) * c);
+    float l_lo = s0[0] + s0[1] + s1[0] + s1[1], l_hi = s0[2] + s0[3] + s1[2] + s1[3];
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    // P as the A operand of the second MMA: the accumulator fragments are already in A layout
+    const uint32_t pa0 = f2_to_bf2(s0[0], s0[1]), pa1 = f2_to_bf2(s0[2], s0[3]);
+    const uint32_t pa2 = f2_to_bf2(s1[0], s1[1]), pa3 = f2_to_bf2(s1[2], s1[3]);
+    // O = P V: eight 8-wide n-tiles over d, one k-step (16 keys); V^T fragments via ldmatrix.trans
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t b0, b1, b2, b3;
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8, cc = nt + (lane >> 4);
+        ldsm_x4_trans(aV + row * 128 + ((cc ^ (row & 7)) << 4), b0, b1, b2, b3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { o[nt][j] = 0.f; o[nt + 1][j] = 0.f; }
+        mma_bf16_16816(o[nt], pa0, pa1, pa2, pa3, b0, b1);
+        mma_bf16_16816(o[nt + 1], pa0, pa1, pa2, pa3, b2, b3);
+    }
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+    __syncwarp();                                         // everyone is done reading sQ: reuse it for O
+    {
+        const int r = lane >> 2, q4 = (lane & 3) * 4;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(sQ + r * 128 + ((nt ^ (r & 7)) << 4) + q4) = f2_to_bf2(o[nt][0] * i_lo, o[nt][1] * i_lo);
+            *reinterpret_cast<uint32_t*>(sQ + (r + 8) * 128 + ((nt ^ ((r + 8) & 7)) << 4) + q4) =
+                f2_to_bf2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+        }
+    }
+    __syncwarp();
+    bf16* op = p.o + b * p.o_bs + h * p.o_hs;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i, row = idx >> 3, cch = idx & 7;
+        *reinterpret_cast<uint4*>(op + (long long)row * p.o_rs + cch * 8) =
+            *reinterpret_cast<const uint4*>(sQ + row * 128 + ((cch ^ (row & 7)) << 4));
+    }
+}
+
 __global__ void __launch_bounds__(ROWS)
 attention_kernel(const AttnParams p) {
     pdl_prologue();
@@ -276,6 +396,14 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
         const int rc = xd_attention_tc256_try(q, q_bs, q_hs, q_rs, k, k_bs, k_hs, k_rs, v, v_bs, v_hs, v_rs, o, o_bs,
                                               o_hs, o_rs, B, H, scale, (cudaStream_t)stream);
         if (rc >= 0) return rc;
+    }
+    if (Tq == T16 && Tk == T16 && !relk && !scramble) {           // warp-level tensor-core path
+        const long long nb = ((long long)B * H + W16 - 1) / W16;
+        if (xd_launch(attention16_mma_kernel, (unsigned)nb, 32 * W16, 0, (cudaStream_t)stream, p) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+            return XD_ERR_CUDA;
+        }
+        return XD_OK;
     }
     if (Tq == T16 && Tk == T16) {
         static bool configured16 = false;
