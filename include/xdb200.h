@@ -94,6 +94,13 @@ int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, 
                        const float* gamma, const float* beta, const float* scale_shift, long long ss_ld,
                        int ss_div, float eps, int silu, int inner, void* out, long long ldo, void* stream);
 
+/* Same result in ONE launch when a sample fits a thread-block cluster's shared memory (<= 8 CTAs x ~96 KB):
+ * the slab stays in smem, group statistics are reduced across the cluster via DSMEM.  Returns -1 (and does
+ * nothing) when the sample is too large; inner == 1 layout only. */
+int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* gamma,
+                       const float* beta, const float* scale_shift, long long ss_ld, int ss_div, float eps,
+                       int silu, void* out, long long ldo, void* stream);
+
 /* out(bf16)[m,:] = LayerNorm(x[m,:]; no affine) * (1 + scale[r,:]) + shift[r,:], r = (m / rows_per_mod)*mod_ld.
  * (score_networks/dit.py:16-17,46-51,70-72; pixart.py:20-21,82-92) */
 int xd_layernorm_modulate(const float* x, long long ld, int M, int D, const float* shift, const float* scale,

@@ -5,6 +5,10 @@
 // Statistics in fp32; 16-byte vector accesses; warp-shuffle / shared-memory reductions.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace {
 
 // ----------------------------------------------------------------------------- GroupNorm
@@ -94,6 +98,113 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
             f[k] = silu ? silu_f(y) : y;
         }
         *reinterpret_cast<bf16x8*>(out + p * ldo + j * 8) = pack8(f);
+    }
+}
+
+
+// ----------------------------------------------------------------------------- fused GroupNorm (cluster)
+// One thread-block CLUSTER per sample: each CTA keeps its slab of pixels in shared memory, the 32 group
+// statistics are reduced across the cluster through distributed shared memory, and the slab is
+// normalised straight from shared memory -- one HBM/L2 read and one write per element, one launch
+// (the two-kernel path reads x twice and needs a memset + two launches).
+__global__ void __launch_bounds__(256)
+gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ ss, long long ss_ld, int ss_div, float eps,
+                int silu, bf16* __restrict__ out, long long ldo, int slab_px) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint8_t smem_gn[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int sample = blockIdx.y;
+    float* part = reinterpret_cast<float*>(smem_gn);            // [64][2] partial (sum, sumsq) of this CTA
+    float* coef = part + 128;                                   // [2][C]
+    uint4* slab = reinterpret_cast<uint4*>(coef + 2 * C);       // [slab_px][C/8]
+    const int V = C >> 3;
+    const int p0 = rank * slab_px, p1 = min(P, p0 + slab_px);
+    const int nvec = max(0, p1 - p0) * V;
+    if (threadIdx.x < 128) part[threadIdx.x] = 0.f;
+    __syncthreads();
+    // pass 1: global -> smem, per-thread channel sums.  A thread always sees the same 8 channels when
+    // blockDim is a multiple of V; otherwise it accumulates per vector slot j below.
+    const bf16* base = x + ((long long)sample * P + p0) * ld;
+    const int cpg = C / G;
+    float s[8] = {}, q[8] = {};
+    const int ppb = 256 / V;                                    // pixels per block iteration
+    const int j = threadIdx.x % V, po = threadIdx.x / V;
+    if (po < ppb) {
+        const int npx = p1 - p0;
+        int px = po;
+        for (; px + 3 * ppb < npx; px += 4 * ppb) {                // four independent 16-byte loads in flight
+            uint4 u[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const uint4*>(base + (long long)(px + r * ppb) * ld + j * 8);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                slab[(px + r * ppb) * V + j] = u[r];
+                bf16x8 t; t.u = u[r];
+                float f[8];
+                unpack8(t, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+            }
+        }
+        for (; px < npx; px += ppb) {
+            const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)px * ld + j * 8);
+            slab[px * V + j] = u;
+            bf16x8 t; t.u = u;
+            float f[8];
+            unpack8(t, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+        }
+        int g = (j * 8) / cpg;
+        float gs = 0.f, gq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int gk = (j * 8 + k) / cpg;
+            if (gk != g) { atomicAdd(&part[2 * g], gs); atomicAdd(&part[2 * g + 1], gq); g = gk; gs = 0.f; gq = 0.f; }
+            gs += s[k]; gq += q[k];
+        }
+        atomicAdd(&part[2 * g], gs);
+        atomicAdd(&part[2 * g + 1], gq);
+    }
+    cluster.sync();                                             // all partials written (also a CTA barrier)
+    // per-channel affine coefficients from the cluster-wide statistics (DSMEM reads)
+    const float inv_cnt = 1.0f / ((float)P * (float)cpg);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float sum = 0.f, sq = 0.f;
+        for (int r = 0; r < CS; ++r) {
+            const float* rp = cluster.map_shared_rank(part, r);
+            sum += rp[2 * g];
+            sq += rp[2 * g + 1];
+        }
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        float a = rstd * gamma[c], b = beta[c] - mean * rstd * gamma[c];
+        if (ss) {
+            const float* row = ss + (long long)(sample / ss_div) * ss_ld;
+            const float sc = 1.0f + row[c], sh = row[C + c];
+            a *= sc; b = b * sc + sh;
+        }
+        coef[c] = a; coef[C + c] = b;
+    }
+    cluster.sync();                                             // coefs visible; nobody exits while peers read `part`
+    // pass 2: smem -> normalise -> global
+    bf16* obase = out + ((long long)sample * P + p0) * ldo;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int jj = i % V, px = i / V;
+        bf16x8 t; t.u = slab[i];
+        float f[8];
+        unpack8(t, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float y = fmaf(f[k], coef[jj * 8 + k], coef[C + jj * 8 + k]);
+            f[k] = silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
+        }
+        *reinterpret_cast<bf16x8*>(obase + (long long)px * ldo + jj * 8) = pack8(f);
     }
 }
 
@@ -191,5 +302,49 @@ extern "C" int xd_layernorm_modulate(const float* x, long long ld, int M, int D,
     }
 #undef XD_LN
     XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+// Returns XD_OK, an error code, or -1 when the sample does not fit the cluster's shared memory
+// (the caller then uses xd_groupnorm_stats + xd_groupnorm_apply).
+extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int P, int C, int groups,
+                                  const float* gamma, const float* beta, const float* scale_shift, long long ss_ld,
+                                  int ss_div, float eps, int silu, void* out, long long ldo, void* stream) {
+    XD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0);
+    XD_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && nsamples > 0 && P > 0);
+    const size_t fixed = (128 + 2 * (size_t)C) * sizeof(float);
+    const size_t budget = 100 * 1024;                           // two CTAs per SM
+    int cs = 1;
+    while (cs <= 8 && (size_t)((P + cs - 1) / cs) * C * 2 + fixed > budget) cs *= 2;
+    if (cs > 8) return -1;
+    const int slab_px = (P + cs - 1) / cs;
+    const size_t smem = fixed + (size_t)slab_px * C * 2;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed (gn_fused)");
+            return XD_ERR_CUDA;
+        }
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs, nsamples);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = xd_pdl_enabled() ? 2 : 1;
+    if (cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x, ld, P, C, groups, gamma, beta, scale_shift, ss_ld,
+                           ss_div > 0 ? ss_div : 1, eps, silu, (bf16*)out, ldo, slab_px) != cudaSuccess) {
+        xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        return XD_ERR_CUDA;
+    }
     return XD_OK;
 }

@@ -19,6 +19,7 @@ MODE_ANCESTRAL, MODE_DDIM, MODE_EULER = 0, 1, 2
 # "tc": tcgen05/TMEM/TMA kernels (product path).  "simt": CUDA-core twins (device cross-check only).
 MATMUL_BACKEND = os.environ.get("XDB200_MATMUL", "tc")
 LAUNCHES = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+GROUPNORM_FUSED = os.environ.get("XDB200_GN_FUSED", "1") == "1"      # cluster/DSMEM single-pass GroupNorm
 
 
 def _p(t):
@@ -49,11 +50,18 @@ def _count(n=1):
 
 
 _defs = []
+# Ablation timing only (tools/ablate.py): XDB200_SKIP=groupnorm,conv3x3 turns those ops into no-ops so that
+# the in-graph cost of a kernel class can be read off the step time.  Results are garbage when set.
+_SKIP = set(filter(None, os.environ.get("XDB200_SKIP", "").split(",")))
 
 
 def _op(schema):
     def deco(fn):
-        _defs.append((schema, fn))
+        name = schema.split("(", 1)[0]
+        if name in _SKIP:
+            _defs.append((schema, lambda *a, **k: None))
+        else:
+            _defs.append((schema, fn))
         return fn
     return deco
 
@@ -148,6 +156,14 @@ def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, 
     assert x.stride(1) == 1 and out.stride(1) == 1 and ns * P == rows and stats.dtype == torch.float32
     assert stats.numel() >= ns * 64 and stats.is_contiguous()
     l = _lib.lib()
+    if inner == 1 and GROUPNORM_FUSED:
+        rc = l.xd_groupnorm_fused(_p(x), x.stride(0), ns, P, C, 32, _p(gamma), _p(beta), _p(scale_shift),
+                                  0 if scale_shift is None else scale_shift.stride(0), ss_div, eps, silu, _p(out),
+                                  out.stride(0), _stream())
+        if rc != -1:
+            _lib.check(rc, "xd_groupnorm_fused")
+            _count()
+            return
     _lib.check(l.xd_groupnorm_stats(_p(x), x.stride(0), ns, P, C, 32, inner, _p(stats), _stream()),
                "xd_groupnorm_stats")
     _lib.check(l.xd_groupnorm_apply(_p(x), x.stride(0), ns, P, C, 32, _p(stats), _p(gamma), _p(beta),
