@@ -30,7 +30,10 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_IMAGE_STEP = {"dit": 0.7081e9, "unet": 10.684e9}      # SURVEY.md section 8(d), 2*MAC
+# SURVEY.md section 8(d), 2*MAC per sample per network forward (pixart: x2 forwards under CFG; video: per clip)
+FLOP_PER_IMAGE_STEP = {"dit": 0.7081e9, "unet": 10.684e9, "rf": 10.684e9, "pixart": 2 * 1.437e9, "video": 188.22e9}
+FIXTURE = {"dit": "c2", "unet": "c1", "rf": "c3", "pixart": "c4", "video": "c5"}
+DEFAULT_BATCH = {"dit": 1024, "unet": 64, "rf": 64, "pixart": 512, "video": 2}
 SAMPLING_STEPS = 1000
 
 
@@ -44,7 +47,7 @@ def measured_peaks():
 
 def load_fixture(workload):
     from tests.conftest import load_golden
-    return load_golden({"dit": "c2", "unet": "c1"}[workload])
+    return load_golden(FIXTURE[workload])
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -149,10 +152,33 @@ def run_reference(args):
 
 def workload_config(args, n):
     name = {"dit": "DiT on MNIST (configs/image/mnist/dit.yaml), DDPM ancestral + dynamic thresholding",
-            "unet": "DDPM UNet 32x32 (configs/image/mnist/ddpm_32x32_epsilon_discrete.yaml), ancestral"}[args.workload]
-    return {"workload": name, "sampling_steps": SAMPLING_STEPS, "per_gpu_batch": args.batch,
+            "unet": "DDPM UNet 32x32 (configs/image/mnist/ddpm_32x32_epsilon_discrete.yaml), ancestral",
+            "rf": "Rectified flow UNet 32x32 (configs/image/mnist/rectified_flow_32x32.yaml), Euler",
+            "pixart": "PixArt-alpha (configs/image/mnist/pixart_alpha.yaml), synthetic 77x768 text embeddings, CFG w=2",
+            "video": "Video UNet-3D 16x32x32 (configs/video/moving_mnist/video_diffusion_models.yaml), v-pred"}[args.workload]
+    return {"workload": name, "sampling_steps": args.sampling_steps or (1024 if args.workload == "video" else 1000),
+            "per_gpu_batch": args.batch,
             "global_batch": args.batch * n, "parallelism": f"batch-sharded x{n}, one final all-gather",
             "l2": "activations per timestep exceed L2 (126 MB) at this batch; no flush between loops"}
+
+
+def ncu_dram_bytes_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one GEMM launch (qkv shape) from the committed
+    `ncu --set full` summary under profiles/, or None."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_gemm_*_summary.csv")))
+    if not files:
+        return None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        hdr = rows[0]
+        rd = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum ["))
+        wr = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum ["))
+        scale = lambda h: {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[h.split("[")[1].rstrip("]")]
+        return float(rows[1][rd]) * scale(hdr[rd]) + float(rows[1][wr]) * scale(hdr[wr])
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------ roofline of the GEMM
@@ -203,16 +229,25 @@ def run_ours(args):
     model = product_model(fx, device)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, 1, 32, 32, generator=g).pin_memory()
+    shape = (B, 1, 16, 32, 32) if args.workload == "video" else (B, 1, 32, 32)
+    x_host = torch.randn(shape, generator=g).pin_memory()
     cls_host = torch.randint(0, 10, (B,), generator=g).pin_memory()
-    out_host = torch.empty(B, 1, 32, 32).pin_memory()
+    out_host = torch.empty(shape).pin_memory()
     x_dev, cls_dev = x_host.to(device), cls_host.to(device)
-    use_ctx = args.workload == "dit"
+    extra, cfg_w = {}, None
+    if args.workload == "pixart":
+        from xdiffusion_b200.context import UnconditionalEmbeddingAdapter
+        extra["text_embeddings"] = torch.randn(B, 77, 768, generator=g).to(device)
+        model._unconditional_context = UnconditionalEmbeddingAdapter([77, 768]).to(device)
+        cfg_w = 2.0
+    n_steps = args.sampling_steps if args.sampling_steps else model.noise_scheduler().steps()
 
     def loop(x0, cls, seed):
-        ctx = {"classes": cls} if use_ctx else {}
-        s, _ = model.sample(context=ctx, num_samples=B, initial_noise=x0, num_sampling_steps=args.sampling_steps,
-                            seed=seed)
+        ctx = dict(extra)
+        if args.workload in ("dit", "pixart"):
+            ctx["classes"] = cls
+        s, _ = model.sample(context=ctx, num_samples=B, initial_noise=x0, num_sampling_steps=n_steps, seed=seed,
+                            classifier_free_guidance=cfg_w)
         return gather_rows(s, B * world) if world > 1 else s
 
     def barrier():
@@ -265,7 +300,7 @@ def run_ours(args):
         return
     burst, sustained, hbm, src = measured_peaks()
     rl_tflops, per_shape = gemm_roofline(B, device) if args.workload == "dit" else (None, {})
-    flop_img = FLOP_PER_IMAGE_STEP[args.workload] * args.sampling_steps
+    flop_img = FLOP_PER_IMAGE_STEP[args.workload] * n_steps
     line = {
         "metric": "images_per_sec_full_sampling_loop", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -273,14 +308,14 @@ def run_ours(args):
         "config": workload_config(args, world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + cls_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": ((launches_per_timestep or 0) * args.sampling_steps + 2) * args.steps,
+        "gpu_launches": ((launches_per_timestep or 0) * n_steps + 2) * args.steps,
         "launches_per_timestep": launches_per_timestep,
-        "ms_per_timestep": ms / args.steps / args.sampling_steps,
+        "ms_per_timestep": ms / args.steps / n_steps,
         "step_tensor_frac_of_sustained": value / world * flop_img / (sustained * 1e12),
     }
     if rl_tflops is not None:
         line["roofline"] = {"bound": "tensor", "achieved": rl_tflops, "peak": burst, "unit": "TFLOP/s",
-                            "frac": rl_tflops / burst, "traffic": None, "peak_source": src,
+                            "frac": rl_tflops / burst, "traffic": ncu_dram_bytes_per_launch(), "peak_source": src,
                             "kernel": "gemm_tc_kernel<128> (tcgen05), qkv+proj+fc1+fc2 of one DiT block",
                             "per_shape": per_shape}
     if world == 1 and not args.no_cpu:
@@ -299,13 +334,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dit", choices=["dit", "unet"])
+    ap.add_argument("--workload", default="dit", choices=list(FIXTURE))
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 1024 DiT, 64 UNet)")
-    ap.add_argument("--sampling-steps", type=int, default=SAMPLING_STEPS)
+    ap.add_argument("--sampling-steps", type=int, default=0, help="0 = the scheduler's full step count")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 1024 if args.workload == "dit" else 64
+        args.batch = DEFAULT_BATCH[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

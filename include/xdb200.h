@@ -84,10 +84,12 @@ int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q
 /* GroupNorm over NHWC bf16: a "sample" is P pixel rows of C channels; row(s, p) = (s / inner)*P*inner +
  * s % inner + p*inner  (inner = 1: P consecutive pixels; inner = H*W, P = F: the frames of one pixel of
  * a clip, i.e. the temporal block's GroupNorm over (C/32 x F), layers/attention.py:457-462).  stats fp32
- * [nsamples][groups][2] (sum, sum of squares), zeroed inside.  apply: y = GN(x)*gamma+beta, then
+ * [nsamples][xd_groupnorm_slabs()][groups][2] partial (sum, sum of squares), summed in fixed order (no
+ * floating-point atomics: a sample's result does not depend on the batch it is in).  apply: y = GN(x)*gamma+beta, then
  * y = y*(1+scale)+shift with [scale | shift] = scale_shift[(sample / ss_div)*ss_ld + ...] if non-NULL,
  * then SiLU if silu.  (torch.nn.GroupNorm(32,C) + SiLU: layers/resnet.py:126-128,151-153,193-197;
  * layers/attention.py:64; score_networks/unet.py:246-247.) */
+int xd_groupnorm_slabs(int nsamples, int P, int C);
 int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
                        float* stats, void* stream);
 int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* stats,
@@ -134,12 +136,12 @@ int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, 
 
 /* mode 0 ancestral (samplers/ancestral.py:21-72,189-267), 1 DDIM (samplers/ddim.py:43-123), 2 Euler
  * (samplers/rectified_flow.py:46-84).  coefs fp32 [N][8], row = loop index, read from *idx_dev when
- * non-NULL else idx_host.  z NULL -> in-kernel Philox normals.  threshold=1 -> dynamic thresholding
+ * non-NULL else idx_host.  z NULL -> in-kernel Philox normals keyed by *seed_dev when non-NULL (graph replay), else seed.  threshold=1 -> dynamic thresholding
  * (utils.py:379-396) with floor(rank)=thr_k, frac=thr_w, cap=thr_c.  In place (out == x) allowed. */
 int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float* o, const float* z,
                     long long z_step_stride, float* out, const float* coefs, const int* idx_dev, int idx_host,
                     long long n_total, int n_per_sample, int threshold, int thr_k, float thr_w, float thr_c,
-                    unsigned long long seed, void* stream);
+                    unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* *idx_dev <- set_to (>= 0), *idx_dev - 1 (set_to == -1) or unchanged (-2); then out_*[b] = tab_*[*idx_dev], b < B
  * (the per-step `t = torch.tensor([idx]*B)` / logsnr lookups of diffusion/ddpm.py:928-955). */
 int xd_schedule_advance(int* idx_dev, int set_to, const long long* tab_i64, const float* tab_f32a,

@@ -286,13 +286,13 @@ def test_sampler_step_discrete_bit_exact(ops, pred, threshold):
         ranks = torch.tensor(0.99, dtype=torch.float32) * (1024 - 1)
         out = torch.empty_like(x, device=DEV)
         torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out, coefs, None, i,
-                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0)
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None)
         assert torch.equal(out.cpu(), ref), (i, float((out.cpu() - ref).abs().max()))
         # device-resident loop index (the CUDA-graph path)
         idx = torch.tensor([i], dtype=torch.int32, device=DEV)
         out2 = torch.empty_like(out)
         torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out2, coefs, idx, -1,
-                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0)
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None)
         assert torch.equal(out2, out)
 
 
@@ -303,7 +303,7 @@ def test_sampler_step_euler_and_philox(ops):
     coefs[:, 0] = 1.0 / 1000
     out = torch.empty_like(x, device=DEV)
     torch.ops.xdb200.sampler_step(2, 0, 0, x.to(DEV), o.to(DEV), None, 0, out, coefs.to(DEV), None, 5, 0, 0, 0.0,
-                                  0.0, 0)
+                                  0.0, 0, None)
     assert torch.equal(out.cpu(), osamplers.euler_flow(x, o, 1000))
     # in-kernel noise: x0 == 0 => out = sigma * z ~ N(0, sigma^2), different per step and per seed
     n = 1 << 20
@@ -313,7 +313,7 @@ def test_sampler_step_euler_and_philox(ops):
     outs = []
     for step, seed in ((1, 1), (2, 1), (1, 2)):
         o_ = torch.empty_like(zeros)
-        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, o_, c, None, step, 0, 0, 0.0, 0.0, seed)
+        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, o_, c, None, step, 0, 0, 0.0, 0.0, seed, None)
         outs.append(o_.cpu())
     for o_ in outs:
         assert abs(float(o_.mean())) < 5e-3 and abs(float(o_.std()) - 1) < 5e-3

@@ -12,24 +12,49 @@ namespace cg = cooperative_groups;
 namespace {
 
 // ----------------------------------------------------------------------------- GroupNorm
+
+// Deterministic block reduction of per-thread channel sums to per-group (sum, sumsq): fixed summation
+// order (no floating-point atomics), so a sample's statistics do not depend on the batch it is in.
+// scratch: [256][16] floats.  part[2*g], part[2*g+1] are written (not accumulated).
+__device__ __forceinline__ void block_group_sums(const float (&s)[8], const float (&q)[8], bool active, int V, int ppb,
+                                                 int C, int G, float* scratch, float* part) {
+    float* mine = scratch + threadIdx.x * 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mine[k] = active ? s[k] : 0.f; mine[8 + k] = active ? q[k] : 0.f; }
+    __syncthreads();
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        float gs = 0.f, gq = 0.f;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+            const int j = c >> 3, k = c & 7;
+            for (int po = 0; po < ppb; ++po) {
+                const float* t = scratch + (po * V + j) * 16;
+                gs += t[k];
+                gq += t[8 + k];
+            }
+        }
+        part[2 * threadIdx.x] = gs;
+        part[2 * threadIdx.x + 1] = gq;
+    }
+    __syncthreads();
+}
 // stats[sample][group] = (sum, sum of squares) accumulated with atomics from pixel slabs.
 // "sample" = P consecutive pixels (rows of C channels, stride ld).
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, int inner,
                 float* __restrict__ stats) {
     pdl_prologue();
-    __shared__ float acc[64][2];
+    __shared__ float acc[128];
+    __shared__ float scratch[256 * 16];
     const int V = C >> 3;                       // 16-byte vectors per pixel
     const int ppb = 256 / V;                    // pixels per block iteration
     const int sample = blockIdx.y;
     const int slabs = gridDim.x;
     const int per = (P + slabs - 1) / slabs;
     const int p0 = blockIdx.x * per, p1 = min(P, p0 + per);
-    if (threadIdx.x < 64) { acc[threadIdx.x][0] = 0.f; acc[threadIdx.x][1] = 0.f; }
-    __syncthreads();
     const int j = threadIdx.x % V, po = threadIdx.x / V;
+    float s[8] = {}, q[8] = {};
     if (po < ppb) {
-        float s[8] = {}, q[8] = {};
         // row(sample, p) = (sample / inner) * P * inner + sample % inner + p * inner
         const bf16* base = x + ((long long)(sample / inner) * P * inner + sample % inner) * ld + j * 8;
         for (int p = p0 + po; p < p1; p += ppb) {
@@ -38,22 +63,12 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, i
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
         }
-        const int cpg = C / G;
-        int g = (j * 8) / cpg;
-        float gs = 0.f, gq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int gk = (j * 8 + k) / cpg;
-            if (gk != g) { atomicAdd(&acc[g][0], gs); atomicAdd(&acc[g][1], gq); g = gk; gs = 0.f; gq = 0.f; }
-            gs += s[k]; gq += q[k];
-        }
-        atomicAdd(&acc[g][0], gs);
-        atomicAdd(&acc[g][1], gq);
     }
-    __syncthreads();
-    if (threadIdx.x < G) {
-        atomicAdd(&stats[((long long)sample * G + threadIdx.x) * 2 + 0], acc[threadIdx.x][0]);
-        atomicAdd(&stats[((long long)sample * G + threadIdx.x) * 2 + 1], acc[threadIdx.x][1]);
+    block_group_sums(s, q, po < ppb, V, ppb, C, G, scratch, acc);
+    if (threadIdx.x < G) {                      // one partial per (sample, slab): summed in fixed order by gn_apply
+        float* dst = &stats[(((long long)sample * slabs + blockIdx.x) * G + threadIdx.x) * 2];
+        dst[0] = acc[2 * threadIdx.x];
+        dst[1] = acc[2 * threadIdx.x + 1];
     }
 }
 
@@ -61,7 +76,8 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, i
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
-                long long ss_ld, int ss_div, float eps, int silu, int inner, bf16* __restrict__ out, long long ldo) {
+                long long ss_ld, int ss_div, float eps, int silu, int inner, int stat_slabs, bf16* __restrict__ out,
+                long long ldo) {
     pdl_prologue();
     extern __shared__ float coef[];             // [2][C]
     const int sample = blockIdx.y;
@@ -69,7 +85,12 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
     const float inv_cnt = 1.0f / ((float)P * (float)cpg);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const float sum = stats[((long long)sample * G + g) * 2], sq = stats[((long long)sample * G + g) * 2 + 1];
+        float sum = 0.f, sq = 0.f;
+        for (int sl = 0; sl < stat_slabs; ++sl) {       // fixed order: deterministic
+            const float* st = &stats[(((long long)sample * stat_slabs + sl) * G + g) * 2];
+            sum += st[0];
+            sq += st[1];
+        }
         const float mean = sum * inv_cnt;
         const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -117,14 +138,13 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int sample = blockIdx.y;
+    __shared__ float scratch[256 * 16];
     float* part = reinterpret_cast<float*>(smem_gn);            // [64][2] partial (sum, sumsq) of this CTA
     float* coef = part + 128;                                   // [2][C]
     uint4* slab = reinterpret_cast<uint4*>(coef + 2 * C);       // [slab_px][C/8]
     const int V = C >> 3;
     const int p0 = rank * slab_px, p1 = min(P, p0 + slab_px);
     const int nvec = max(0, p1 - p0) * V;
-    if (threadIdx.x < 128) part[threadIdx.x] = 0.f;
-    __syncthreads();
     // pass 1: global -> smem, per-thread channel sums.  A thread always sees the same 8 channels when
     // blockDim is a multiple of V; otherwise it accumulates per vector slot j below.
     const bf16* base = x + ((long long)sample * P + p0) * ld;
@@ -158,17 +178,8 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
         }
-        int g = (j * 8) / cpg;
-        float gs = 0.f, gq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int gk = (j * 8 + k) / cpg;
-            if (gk != g) { atomicAdd(&part[2 * g], gs); atomicAdd(&part[2 * g + 1], gq); g = gk; gs = 0.f; gq = 0.f; }
-            gs += s[k]; gq += q[k];
-        }
-        atomicAdd(&part[2 * g], gs);
-        atomicAdd(&part[2 * g + 1], gq);
     }
+    block_group_sums(s, q, po < ppb, V, ppb, C, G, scratch, part);
     cluster.sync();                                             // all partials written (also a CTA barrier)
     // per-channel affine coefficients from the cluster-wide statistics (DSMEM reads)
     const float inv_cnt = 1.0f / ((float)P * (float)cpg);
@@ -254,15 +265,20 @@ ln_modulate_kernel(const float* __restrict__ x, long long ld, int M, const float
 
 }  // namespace
 
+// Number of pixel slabs (= partial statistics per sample) the two-kernel path uses: a pure function of the
+// problem shape, shared by xd_groupnorm_stats and xd_groupnorm_apply.
+extern "C" int xd_groupnorm_slabs(int nsamples, int P, int C) {
+    int slabs = (2 * 148 + nsamples - 1) / nsamples;
+    const int ppb = 256 / (C / 8);
+    return max(1, min(min(slabs, 32), (P + ppb * 4 - 1) / (ppb * 4)));
+}
+
 extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
                                   float* stats, void* stream) {
     XD_CHECK_ARG(x && stats && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0 && ld % 8 == 0);
     XD_CHECK_ARG(inner >= 1 && nsamples % inner == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(stats, 0, sizeof(float) * 2 * nsamples * groups, st) != cudaSuccess) return XD_ERR_CUDA;
-    int slabs = (2 * 148 + nsamples - 1) / nsamples;
-    const int ppb = 256 / (C / 8);
-    slabs = max(1, min(slabs, (P + ppb * 4 - 1) / (ppb * 4)));
+    const int slabs = xd_groupnorm_slabs(nsamples, P, C);
     xd_launch(gn_stats_kernel, dim3(slabs, nsamples), 256, 0, st, (const bf16*)x, ld, P, C, groups, inner, stats);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -278,7 +294,7 @@ extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int
     slabs = max(1, min(slabs, (P + 15) / 16));
     xd_launch(gn_apply_kernel, dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream, 
         (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
-        inner, (bf16*)out, ldo);
+        inner, xd_groupnorm_slabs(nsamples, P, C), (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
@@ -313,7 +329,7 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
     XD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0);
     XD_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && nsamples > 0 && P > 0);
     const size_t fixed = (128 + 2 * (size_t)C) * sizeof(float);
-    const size_t budget = 100 * 1024;                           // two CTAs per SM
+    const size_t budget = 110 * 1024;                           // (+ 16 KB static scratch) covers 32x32x384 with 8 CTAs
     int cs = 1;
     while (cs <= 8 && (size_t)((P + cs - 1) / cs) * C * 2 + fixed > budget) cs *= 2;
     if (cs > 8) return -1;

@@ -33,6 +33,7 @@ struct StepParams {
     int thr_k;                  // floor(rank)
     float thr_w, thr_c;         // rank - floor(rank), hard cap c
     unsigned long long seed;    // in-kernel Philox noise when z == nullptr
+    const unsigned long long* seed_dev;   // if non-null the seed is read from device memory (CUDA-graph replay)
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 + Box-Muller
@@ -73,6 +74,7 @@ __device__ __forceinline__ float finish(const StepParams& p, const float* cf, in
 __global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
     pdl_prologue();
     const int i = p.idx_dev ? *p.idx_dev : p.idx_host;
+    const unsigned long long seed = p.seed_dev ? *p.seed_dev : p.seed;
     float cf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) cf[k] = __ldg(p.coefs + (long long)i * 8 + k);
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
             r.z = __fadd_rn(x.z, __fmul_rn(o.z, cf[0])); r.w = __fadd_rn(x.w, __fmul_rn(o.w, cf[0]));
         } else {
             float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (need_noise) zz = z ? reinterpret_cast<const float4*>(z)[v] : philox_normal4(p.seed, (unsigned long long)v, (uint32_t)i);
+            if (need_noise) zz = z ? reinterpret_cast<const float4*>(z)[v] : philox_normal4(seed, (unsigned long long)v, (uint32_t)i);
             const float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, zs[4] = {zz.x, zz.y, zz.z, zz.w};
             float rs[4];
 #pragma unroll
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(256) step_threshold_kernel(const StepParams p,
     float* s_x0 = sm;                // [n_per_sample]
     float* s_sort = sm + p.n_per_sample;   // [npow2]
     const int i = p.idx_dev ? *p.idx_dev : p.idx_host;
+    const unsigned long long seed = p.seed_dev ? *p.seed_dev : p.seed;
     float cf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) cf[k] = __ldg(p.coefs + (long long)i * 8 + k);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(256) step_threshold_kernel(const StepParams p,
         float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
         if (need_noise)
             zz = z ? reinterpret_cast<const float4*>(z + base)[e4]
-                   : philox_normal4(p.seed, (unsigned long long)(base / 4 + e4), (uint32_t)i);
+                   : philox_normal4(seed, (unsigned long long)(base / 4 + e4), (uint32_t)i);
         const float zs[4] = {zz.x, zz.y, zz.z, zz.w};
         float rs[4];
 #pragma unroll
@@ -200,11 +203,12 @@ __global__ void unnormalize_kernel(const float* x, float* out, long long n) {
 extern "C" int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float* o, const float* z,
                                long long z_step_stride, float* out, const float* coefs, const int* idx_dev,
                                int idx_host, long long n_total, int n_per_sample, int threshold, int thr_k,
-                               float thr_w, float thr_c, unsigned long long seed, void* stream) {
+                               float thr_w, float thr_c, unsigned long long seed,
+                               const unsigned long long* seed_dev, void* stream) {
     XD_CHECK_ARG(x && o && out && coefs && n_total > 0 && n_per_sample > 0 && n_total % n_per_sample == 0);
     XD_CHECK_ARG(n_per_sample % 4 == 0 && mode >= 0 && mode <= 2 && (idx_dev || idx_host >= 0));
     StepParams p{x, o, z, out, coefs, idx_dev, idx_host, z_step_stride, n_total, n_per_sample, mode, form, pred_v,
-                 threshold, thr_k, thr_w, thr_c, seed};
+                 threshold, thr_k, thr_w, thr_c, seed, seed_dev};
     cudaStream_t st = (cudaStream_t)stream;
     if (threshold && mode != MODE_EULER) {
         XD_CHECK_ARG(n_per_sample <= 8192 && thr_k >= 0 && thr_k < n_per_sample);

@@ -257,7 +257,7 @@ class _DeviceLoop:
         self.context = self._static(context, dev)
         self.uncond = self._static(uncond_context, dev) if uncond_context is not None else None
         self.noise = None
-        self.seed = 0
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # Philox key, read by the step kernel
         self.graph = None
 
     @staticmethod
@@ -304,7 +304,7 @@ class _DeviceLoop:
 
     def _step(self):
         c = self._ctx(self.context)
-        c["out"], c["seed"] = self.x, self.seed
+        c["out"], c["seed_dev"] = self.x, self.seed_dev
         if self.noise is not None:
             c["noise"] = self.noise
         u = self._ctx(self.uncond) if self.uncond is not None else None
@@ -313,7 +313,8 @@ class _DeviceLoop:
         self._advance(-1)
 
     def run(self, x0, noise, seed, use_graph):
-        self.noise, self.seed = noise, seed
+        self.noise = noise
+        self.seed_dev.fill_(seed)
         self.x.copy_(x0)
         self._advance(self.N - 1)
         if not use_graph:

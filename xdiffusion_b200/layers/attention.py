@@ -5,7 +5,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from .utils import ContextBlock, Packed, bf16_weight, zero_module
 
 
@@ -166,7 +166,8 @@ class TemporalSelfAttention(ContextBlock, Packed):
         # GroupNorm over (C/32 x F) for every pixel of every clip: samples (b, hw), rows = frames
         rows = x.as_strided((nimg * HW, C), (x.stride(2), 1))
         n = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
-        stats = torch.empty(B * HW * 64, device=x.device, dtype=torch.float32)
+        stats = torch.empty(B * HW * 64 * _lib.lib().xd_groupnorm_slabs(B * HW, F, C), device=x.device,
+                            dtype=torch.float32)
         torch.ops.xdb200.groupnorm(rows, self._norm.weight, self._norm.bias, None, 1, self._norm.eps, 0, HW, B * HW,
                                    stats, n)
         qkv = ops.linear(n, wq, self._qkv.bias)                              # rows (b, f, hw) x 3C

@@ -154,7 +154,7 @@ def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, 
     rows, C = x.shape
     ns, P = nsamples, rows // nsamples
     assert x.stride(1) == 1 and out.stride(1) == 1 and ns * P == rows and stats.dtype == torch.float32
-    assert stats.numel() >= ns * 64 and stats.is_contiguous()
+    assert stats.numel() >= ns * 64 * _lib.lib().xd_groupnorm_slabs(ns, P, C) and stats.is_contiguous()
     l = _lib.lib()
     if inner == 1 and GROUPNORM_FUSED:
         rc = l.xd_groupnorm_fused(_p(x), x.stride(0), ns, P, C, 32, _p(gamma), _p(beta), _p(scale_shift),
@@ -297,17 +297,18 @@ def _cfg_combine(cond, uncond, w, out):
 # ------------------------------------------------------------------------------------ sampler step
 @_op("sampler_step(int mode, int form, int pred_v, Tensor x, Tensor o, Tensor? z, int z_step_stride, "
      "Tensor(a!) out, Tensor coefs, Tensor? idx_dev, int idx_host, int threshold, int thr_k, float thr_w, "
-     "float thr_c, int seed) -> ()")
+     "float thr_c, int seed, Tensor? seed_dev) -> ()")
 def _sampler_step(mode, form, pred_v, x, o, z, z_step_stride, out, coefs, idx_dev, idx_host, threshold, thr_k,
-                  thr_w, thr_c, seed):
-    _cuda(x, o, z, out, coefs, idx_dev)
+                  thr_w, thr_c, seed, seed_dev):
+    _cuda(x, o, z, out, coefs, idx_dev, seed_dev)
+    assert seed_dev is None or seed_dev.dtype == torch.int64
     assert x.is_contiguous() and o.is_contiguous() and out.is_contiguous() and coefs.is_contiguous()
     assert x.dtype == torch.float32 and o.dtype == torch.float32 and coefs.dtype == torch.float32
     assert idx_dev is None or idx_dev.dtype == torch.int32
     n = x.numel()
     _lib.check(_lib.lib().xd_sampler_step(mode, form, pred_v, _p(x), _p(o), _p(z), z_step_stride, _p(out),
                                           _p(coefs), _p(idx_dev), idx_host, n, n // x.shape[0], threshold, thr_k,
-                                          thr_w, thr_c, seed, _stream()), "xd_sampler_step")
+                                          thr_w, thr_c, seed, _p(seed_dev), _stream()), "xd_sampler_step")
     _count()
 
 
@@ -363,7 +364,7 @@ def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, 
     assert out.stride(2) == 1 and out.stride(0) == P * out.stride(1)
     x2 = x.as_strided((ns * P, C), (x.stride(1), 1))
     o2 = out.as_strided((ns * P, C), (out.stride(1), 1))
-    stats = torch.empty(ns * 64, device=x.device, dtype=torch.float32)
+    stats = torch.empty(ns * 64 * _lib.lib().xd_groupnorm_slabs(ns, P, C), device=x.device, dtype=torch.float32)
     _ops.groupnorm(x2, gamma, beta, scale_shift, ss_div, eps, int(silu), inner, ns, stats, o2)
     return out
 
