@@ -69,7 +69,8 @@ int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, int H, int W
                             const float* bias, int Cout, float* out, void* stream);
 
 /* Fused softmax attention, head_dim 64.  Element (b,h,row,d) at ptr + b*bs + h*hs + row*rs + d.
- * logits = scale * q.k (+ q.relk[h, j-i+Tk-1]); relk fp32 [H][2Tk-1][64] or NULL; scramble=1 stores
+ * q/k/v are bf16 (qkv_dtype 1) or, for the Tq = Tk = 16 relative-position path, fp32 (qkv_dtype 0; strides
+ * then count fp32 elements).  logits = scale * q.k (+ q.relk[h, j-i+Tk-1]); relk fp32 [H][2Tk-1][64] or NULL; scramble=1 stores
  * through the reference's raw (B,H,L,D)->(B,H*D,L) reinterpretation with channel stride o_cs.
  * Replaces bmm+softmax+bmm at layers/attention.py:182-188 (UNet), :371-375 (DiT), :219-224 (PixArt
  * cross), :551-676 (temporal, relative positions). */
@@ -77,7 +78,7 @@ int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q
                       long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
                       long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs, long long o_rs,
                       int B, int H, int Tq, int Tk, int head_dim, float scale, const float* relk, int scramble,
-                      long long o_cs, void* stream);
+                      long long o_cs, int qkv_dtype, void* stream);
 
 /* ---- bandwidth-bound kernels ------------------------------------------------------------------ */
 
@@ -87,14 +88,15 @@ int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q
  * [nsamples][xd_groupnorm_slabs()][groups][2] partial (sum, sum of squares), summed in fixed order (no
  * floating-point atomics: a sample's result does not depend on the batch it is in).  apply: y = GN(x)*gamma+beta, then
  * y = y*(1+scale)+shift with [scale | shift] = scale_shift[(sample / ss_div)*ss_ld + ...] if non-NULL,
- * then SiLU if silu.  (torch.nn.GroupNorm(32,C) + SiLU: layers/resnet.py:126-128,151-153,193-197;
+ * then SiLU if silu.  split=1 writes each row as [hi(C) | lo(C)] bf16 with hi + lo = the fp32 result to
+ * 2^-16 (operands of the split-precision temporal-attention GEMM).  (torch.nn.GroupNorm(32,C) + SiLU: layers/resnet.py:126-128,151-153,193-197;
  * layers/attention.py:64; score_networks/unet.py:246-247.) */
 int xd_groupnorm_slabs(int nsamples, int P, int C);
 int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
                        float* stats, void* stream);
 int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* stats,
                        const float* gamma, const float* beta, const float* scale_shift, long long ss_ld,
-                       int ss_div, float eps, int silu, int inner, void* out, long long ldo, void* stream);
+                       int ss_div, float eps, int silu, int inner, int split, void* out, long long ldo, void* stream);
 
 /* Same result in ONE launch when a sample fits a thread-block cluster's shared memory (<= 8 CTAs x ~96 KB):
  * the slab stays in smem, group statistics are reduced across the cluster via DSMEM.  Returns -1 (and does

@@ -38,10 +38,19 @@ def synth_tensor(key: str, shape, seed: int = 0) -> torch.Tensor:
     return 1.0 + 0.1 * r                          # norm gains
 
 
+#: The video model's temporal attention uses UNSCALED logits q.k (reference layers/attention.py:647).  With
+#: unit-gain qkv weights |logit| ~ 8 and the softmax is one-hot -- a regime no trained checkpoint is in and one
+#: that turns the test into a measurement of argmax ties.  Those qkv projections get gain 0.35 (logit std ~ 1).
+TEMPORAL_QKV_GAIN = 0.35
+
+
 def synth_state_dict(manifest, seed: int = 0):
     """manifest: {key: shape}.  Keys listed in _KEEP are skipped."""
-    return {k: synth_tensor(k, s, seed) for k, s in manifest.items()
-            if not any(t in k for t in _KEEP)}
+    out = {k: synth_tensor(k, s, seed) for k, s in manifest.items() if not any(t in k for t in _KEEP)}
+    for k in list(out):
+        if k.endswith("._qkv.weight") and k[: -len("_qkv.weight")] + "_attention._k_embeddings_table" in manifest:
+            out[k] = out[k] * TEMPORAL_QKV_GAIN
+    return out
 
 
 def canonical_manifest(state_dict, prefix="_score_network."):

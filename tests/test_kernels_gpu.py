@@ -218,6 +218,31 @@ def test_attention_relative_position_scrambled(ops):
     ops.attention(q, k, v, 1.0, out=out.view(Bp, L, H, 64).permute(0, 2, 1, 3), relk=ek.to(DEV), scramble=True,
                   o_cs=1)
     assert rel_l2(out.permute(0, 2, 1), ref) < 4e-3
+    # fp32 q/k/v (the split-precision temporal path): only the bf16 output rounding remains
+    g32 = torch.randn(Bp, L, 3 * H * 64, generator=g) * 0.3
+    ref = onets.relpos_attention(g32.permute(0, 2, 1), H, ek)
+    d = g32.to(DEV).view(Bp, L, H, 3, 64)
+    q, k, v = (d[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ops.attention(q, k, v, 1.0, out=out.view(Bp, L, H, 64).permute(0, 2, 1, 3), relk=ek.to(DEV), scramble=True,
+                  o_cs=1)
+    assert rel_l2(out.permute(0, 2, 1), ref) < 3e-3
+
+
+def test_split_precision_gemm(ops):
+    """x.W via bf16 hi/lo pairs on the tensor-core kernel: ~fp32 accuracy (used by temporal attention)."""
+    g = torch.Generator().manual_seed(33)
+    M, N, K = 512, 768, 256
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    xh = bf(x); xl = bf(x - xh.float())
+    wh = bf(w); wl = bf(w - wh.float())
+    n = torch.cat([xh, xl], 1).contiguous().to(DEV)
+    w3 = torch.cat([wh, wh, wl], 1).contiguous().to(DEV)
+    out = ops.linear(n, w3, out_dtype=torch.float32, a2=n[:, :K])
+    ref = x @ w.T
+    assert rel_l2(out, ref) < 2e-5
+    plain = ops.linear(xh.to(DEV), wh.to(DEV), out_dtype=torch.float32)
+    assert rel_l2(plain, ref) > 1e-3          # the single-bf16 product is ~100x less accurate
 
 
 def test_timestep_embeddings(ops, golden):

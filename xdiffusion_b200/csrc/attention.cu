@@ -27,6 +27,7 @@ struct AttnParams {
     const float* relk;          // optional [H][2*Tk-1][64] relative-position key table
     int scramble;               // temporal quirk: out viewed as (H*64, L) from a (H, L, 64) buffer
     long long o_cs;             // scramble: element stride between "channels" of the (C, L) view
+    int in_f32;                 // q/k/v are fp32 (T = 16 relative-position path only)
 };
 
 // q . k over 64 dims with four independent accumulators (a single 64-long FMA chain is latency-bound)
@@ -93,7 +94,18 @@ attention16_kernel(const AttnParams p) {
     float* sK = smem + pl * PAIR_LD;
     float* sV = sK + T16 * RS16;
     float q[D];
-    {
+    if (p.in_f32) {
+        const float* qp = (const float*)p.q + b * p.q_bs + h * p.q_hs + (long long)row * p.q_rs;
+        const float* kp = (const float*)p.k + b * p.k_bs + h * p.k_hs + (long long)row * p.k_rs;
+        const float* vp = (const float*)p.v + b * p.v_bs + h * p.v_hs + (long long)row * p.v_rs;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(qp + i * 4);
+            q[i * 4] = a.x * p.scale; q[i * 4 + 1] = a.y * p.scale; q[i * 4 + 2] = a.z * p.scale; q[i * 4 + 3] = a.w * p.scale;
+            *reinterpret_cast<float4*>(sK + row * RS16 + i * 4) = *reinterpret_cast<const float4*>(kp + i * 4);
+            *reinterpret_cast<float4*>(sV + row * RS16 + i * 4) = *reinterpret_cast<const float4*>(vp + i * 4);
+        }
+    } else {
         bf16x8 rq[8], rk[8], rv[8];
         const bf16* qp = p.q + b * p.q_bs + h * p.q_hs + (long long)row * p.q_rs;
         const bf16* kp = p.k + b * p.k_bs + h * p.k_hs + (long long)row * p.k_rs;
@@ -383,21 +395,23 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
                                  long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
                                  long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs,
                                  long long o_rs, int B, int H, int Tq, int Tk, int head_dim, float scale,
-                                 const float* relk, int scramble, long long o_cs, void* stream) {
+                                 const float* relk, int scramble, long long o_cs, int qkv_dtype, void* stream) {
     XD_CHECK_ARG(q && k && v && o && head_dim == D && B > 0 && H > 0 && Tq > 0 && Tk > 0);
+    const int in_f32 = qkv_dtype == XD_F32;
+    XD_CHECK_ARG(!in_f32 || (Tq == 16 && Tk == 16));            // fp32 q/k/v: SIMT T = 16 kernel only
     XD_CHECK_ARG((Tq >= ROWS && Tq % ROWS == 0) || (Tq < ROWS && ROWS % Tq == 0));
     XD_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && q_hs % 8 == 0 && k_hs % 8 == 0 && v_hs % 8 == 0 &&
                  q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0);
     XD_CHECK_ARG(scramble || (o_rs % 8 == 0 && o_hs % 8 == 0 && o_bs % 8 == 0));
     XD_CHECK_ARG(!relk || Tq == Tk);
     AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, q_bs, q_hs, q_rs, k_bs, k_hs, k_rs,
-                 v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs};
+                 v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs, in_f32};
     if (Tq == 256 && Tk == 256 && !relk && !scramble) {           // tcgen05 path (csrc/attention_tc.cu)
         const int rc = xd_attention_tc256_try(q, q_bs, q_hs, q_rs, k, k_bs, k_hs, k_rs, v, v_bs, v_hs, v_rs, o, o_bs,
                                               o_hs, o_rs, B, H, scale, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
-    if (Tq == T16 && Tk == T16 && !relk && !scramble) {           // warp-level tensor-core path
+    if (Tq == T16 && Tk == T16 && !relk && !scramble && !in_f32) { // warp-level tensor-core path
         const long long nb = ((long long)B * H + W16 - 1) / W16;
         if (xd_launch(attention16_mma_kernel, (unsigned)nb, 32 * W16, 0, (cudaStream_t)stream, p) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));

@@ -76,8 +76,8 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, i
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
-                long long ss_ld, int ss_div, float eps, int silu, int inner, int stat_slabs, bf16* __restrict__ out,
-                long long ldo) {
+                long long ss_ld, int ss_div, float eps, int silu, int inner, int stat_slabs, int split,
+                bf16* __restrict__ out, long long ldo) {
     pdl_prologue();
     extern __shared__ float coef[];             // [2][C]
     const int sample = blockIdx.y;
@@ -118,7 +118,15 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
             float y = fmaf(f[k], coef[j * 8 + k], coef[C + j * 8 + k]);
             f[k] = silu ? silu_f(y) : y;
         }
-        *reinterpret_cast<bf16x8*>(out + p * ldo + j * 8) = pack8(f);
+        const bf16x8 hi = pack8(f);
+        *reinterpret_cast<bf16x8*>(out + p * ldo + j * 8) = hi;
+        if (split) {                            // out row = [hi(C) | lo(C)], hi + lo ~ fp32 value (2^-16 relative)
+            float h[8];
+            unpack8(hi, h);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] -= h[k];
+            *reinterpret_cast<bf16x8*>(out + p * ldo + C + j * 8) = pack8(f);
+        }
     }
 }
 
@@ -286,7 +294,7 @@ extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int
 
 extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups,
                                   const float* stats, const float* gamma, const float* beta, const float* scale_shift,
-                                  long long ss_ld, int ss_div, float eps, int silu, int inner, void* out,
+                                  long long ss_ld, int ss_div, float eps, int silu, int inner, int split, void* out,
                                   long long ldo, void* stream) {
     XD_CHECK_ARG(x && stats && gamma && beta && out && C % 8 == 0 && C % groups == 0 && ld % 8 == 0 && ldo % 8 == 0);
     XD_CHECK_ARG(inner >= 1 && nsamples % inner == 0);
@@ -294,7 +302,7 @@ extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int
     slabs = max(1, min(slabs, (P + 15) / 16));
     xd_launch(gn_apply_kernel, dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream, 
         (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
-        inner, xd_groupnorm_slabs(nsamples, P, C), (bf16*)out, ldo);
+        inner, xd_groupnorm_slabs(nsamples, P, C), split, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

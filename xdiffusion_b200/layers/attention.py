@@ -157,20 +157,28 @@ class TemporalSelfAttention(ContextBlock, Packed):
         heads, d = self._num_heads, self._dim_head
         if d != 64:
             raise NotImplementedError("attention head dim != 64")
-        wq, wp = self.packed("w", (self._qkv.weight, self._proj_out.weight),
-                             lambda: (bf16_weight(self._qkv.weight), bf16_weight(self._proj_out.weight)))
+        # The logits q.k are NOT scaled by 1/sqrt(d) in the reference (attention.py:647): with |logit| ~ 10 the
+        # softmax amplifies bf16 operand rounding (2^-9) into percent-level output error.  The qkv projection of
+        # this block therefore runs in split precision on the same tensor-core kernel: activations and weights
+        # as bf16 hi + lo pairs, x.W ~ x_hi.W_hi + x_lo.W_hi + x_hi.W_lo (K = 3C, error ~2^-16), fp32 q/k/v.
+        def split_weights():
+            w = self._qkv.weight.detach().reshape(3 * C, C).float()
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            return torch.cat([hi, hi, lo], 1).contiguous(), bf16_weight(self._proj_out.weight)
+        wq3, wp = self.packed("w", (self._qkv.weight, self._proj_out.weight), split_weights)
         relk = self.packed("relk", (self._attention._k_embeddings_table,),
                            lambda: self._attention._k_embeddings_table.detach().float().contiguous())
         if relk.shape[1] != 2 * F - 1:
             raise NotImplementedError("temporal_sequence_length != max_relative_position")
         # GroupNorm over (C/32 x F) for every pixel of every clip: samples (b, hw), rows = frames
         rows = x.as_strided((nimg * HW, C), (x.stride(2), 1))
-        n = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
+        n = torch.empty((nimg * HW, 2 * C), device=x.device, dtype=torch.bfloat16)        # [hi | lo]
         stats = torch.empty(B * HW * 64 * _lib.lib().xd_groupnorm_slabs(B * HW, F, C), device=x.device,
                             dtype=torch.float32)
         torch.ops.xdb200.groupnorm(rows, self._norm.weight, self._norm.bias, None, 1, self._norm.eps, 0, HW, B * HW,
-                                   stats, n)
-        qkv = ops.linear(n, wq, self._qkv.bias)                              # rows (b, f, hw) x 3C
+                                   1, stats, n)
+        qkv = ops.linear(n, wq3, self._qkv.bias, out_dtype=torch.float32, a2=n[:, :C])    # rows (b, f, hw) x 3C
         a = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
         q5 = qkv.view(B, F, HW, heads, 3, d)
         a4 = a.view(B, F, HW, heads, d)

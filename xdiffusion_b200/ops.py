@@ -136,18 +136,18 @@ def _attention(q, k, v, o, scale, relk, scramble, o_cs):
     B, H, Tq, D = q.shape
     Tk = k.shape[2]
     for t in (q, k, v):
-        assert t.dtype == torch.bfloat16 and t.stride(3) == 1
+        assert t.dtype == q.dtype and t.dtype in (torch.bfloat16, torch.float32) and t.stride(3) == 1
     _lib.check(_lib.lib().xd_attention_bf16(
         _p(q), q.stride(0), q.stride(1), q.stride(2), _p(k), k.stride(0), k.stride(1), k.stride(2),
         _p(v), v.stride(0), v.stride(1), v.stride(2), _p(o), o.stride(0), o.stride(1), o.stride(2),
-        B, H, Tq, Tk, D, scale, _p(relk), scramble, o_cs, _stream()), "xd_attention_bf16")
+        B, H, Tq, Tk, D, scale, _p(relk), scramble, o_cs, _dt(q), _stream()), "xd_attention_bf16")
     _count()
 
 
 # ------------------------------------------------------------------------------------ norms
 @_op("groupnorm(Tensor x, Tensor gamma, Tensor beta, Tensor? scale_shift, int ss_div, float eps, int silu, "
-     "int inner, int nsamples, Tensor(a!) stats, Tensor(b!) out) -> ()")
-def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, stats, out):
+     "int inner, int nsamples, int split, Tensor(a!) stats, Tensor(b!) out) -> ()")
+def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, split, stats, out):
     """x [rows, C] bf16 view (channel stride 1) holding nsamples samples of P = rows / nsamples rows
     each; row(s, p) = (s / inner)*P*inner + s % inner + p*inner; 32 groups; stats fp32 [nsamples*64]."""
     _cuda(x, gamma, beta, scale_shift, stats, out)
@@ -156,7 +156,7 @@ def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, 
     assert x.stride(1) == 1 and out.stride(1) == 1 and ns * P == rows and stats.dtype == torch.float32
     assert stats.numel() >= ns * 64 * _lib.lib().xd_groupnorm_slabs(ns, P, C) and stats.is_contiguous()
     l = _lib.lib()
-    if inner == 1 and GROUPNORM_FUSED:
+    if inner == 1 and not split and GROUPNORM_FUSED:
         rc = l.xd_groupnorm_fused(_p(x), x.stride(0), ns, P, C, 32, _p(gamma), _p(beta), _p(scale_shift),
                                   0 if scale_shift is None else scale_shift.stride(0), ss_div, eps, silu, _p(out),
                                   out.stride(0), _stream())
@@ -168,7 +168,7 @@ def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, 
                "xd_groupnorm_stats")
     _lib.check(l.xd_groupnorm_apply(_p(x), x.stride(0), ns, P, C, 32, _p(stats), _p(gamma), _p(beta),
                                     _p(scale_shift), 0 if scale_shift is None else scale_shift.stride(0), ss_div,
-                                    eps, silu, inner, _p(out), out.stride(0), _stream()), "xd_groupnorm_apply")
+                                    eps, silu, inner, split, _p(out), out.stride(0), _stream()), "xd_groupnorm_apply")
     _count(3)
 
 
@@ -365,7 +365,7 @@ def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, 
     x2 = x.as_strided((ns * P, C), (x.stride(1), 1))
     o2 = out.as_strided((ns * P, C), (out.stride(1), 1))
     stats = torch.empty(ns * 64 * _lib.lib().xd_groupnorm_slabs(ns, P, C), device=x.device, dtype=torch.float32)
-    _ops.groupnorm(x2, gamma, beta, scale_shift, ss_div, eps, int(silu), inner, ns, stats, o2)
+    _ops.groupnorm(x2, gamma, beta, scale_shift, ss_div, eps, int(silu), inner, ns, 0, stats, o2)
     return out
 
 
