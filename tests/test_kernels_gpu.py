@@ -85,6 +85,30 @@ def test_gemm_tile_widths_and_epilogues(ops, bn):
     assert rel_l2(out, _gemm_ref(a, w[:, :K], None, 0, None, 1, resb)) < 3e-3
 
 
+# A-stationary tiles (2xxx = 1-CTA, 3xxx = CTA pair): the 128 x K panel of A stays in shared memory while the CTA
+# walks its n-tiles.  Shapes cover one item per CTA, several items per CTA with a ragged last m-tile (panel reuse
+# barriers), and n-groups (few m-tiles).
+@pytest.mark.parametrize("bn", [2192, 3192, 3256])
+@pytest.mark.parametrize("M,N,K,K2", [(2048, 1152, 384, 0), (40000 - 24, 768, 256, 128), (300, 1536, 384, 0),
+                                       (640, 384, 128, 0)])
+def test_gemm_a_stationary(ops, bn, M, N, K, K2):
+    g = torch.Generator().manual_seed(bn + M)
+    rows = 4
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    a2 = bf(torch.randn(M, K2, generator=g)).to(DEV) if K2 else None
+    w = bf(torch.randn(N, K + K2, generator=g) / math.sqrt(K + K2)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    full = a if a2 is None else torch.cat([a, a2], 1)
+    out = ops.linear(a, w, bias, act=ops.ACT_GELU, out_dtype=torch.bfloat16, a2=a2, force_bn=bn)
+    assert rel_l2(out, _gemm_ref(full, w, bias, 2, None, 1, None)) < 3e-3
+    gate = torch.randn(M // rows, N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = _gemm_ref(full, w, bias, 0, gate, rows, res)
+    out = ops.linear(a, w, bias, gate=gate, gate_rows=rows, residual=res, out=res, a2=a2, force_bn=bn)
+    assert out.data_ptr() == res.data_ptr()
+    assert rel_l2(out, ref) < 1e-5
+
+
 def _pack_conv(w, wskip=None):
     """[Cout,C,3,3] -> [Cout, 9*C (+Cs)] tap-major (same packing as the product's weight repack)."""
     co, c = w.shape[:2]

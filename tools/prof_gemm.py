@@ -12,12 +12,16 @@ from xdiffusion_b200 import ops  # noqa: E402
 def main():
     dev = "cuda"
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    bn = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    bn0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    only = sys.argv[3].split(',') if len(sys.argv) > 3 else None
     torch.manual_seed(0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     for (n, k, name, kw) in [(1152, 384, "qkv", {}), (384, 384, "proj", {"res": True}),
                              (1536, 384, "fc1", {"act": ops.ACT_GELU}), (384, 1536, "fc2", {"res": True}),
                              (1536, 384, "fc1_noact", {})]:
+        if only and name not in only:
+            continue
+        bn = bn0 if not (bn0 >= 2000 and k > 384) else 0       # A-stationary tiles need K <= 384
         a = torch.randn(M, k, device=dev).bfloat16()
         w = torch.randn(n, k, device=dev).bfloat16()
         bias = torch.randn(n, device=dev)

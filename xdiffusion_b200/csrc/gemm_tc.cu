@@ -26,6 +26,7 @@
 #include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -45,20 +46,36 @@ struct TcParams {
     int vec_ok;         // unused by the kernel (all accesses are 16-byte; checked on the host)
     int direct_ok;      // bf16 out rows are 16-byte aligned: registers can be stored without the transpose
     int debug;          // experiments only (XDB200_DEBUG): 1 = skip global stores, 2 = skip the MMAs
+    int tma_epi;        // 1: TMA epilogue (bulk tensor load of the residual, bulk tensor store of the output)
+    long long* prof;    // XDB200_PROF=1: per-CTA cycle counters (16 slots per CTA), nullptr otherwise
+    int ng, tpg;        // work items: every m-tile is split into ng groups of tpg consecutive n-tiles
     Epilogue epi;
 };
 
-template <int BN, int CG = 1> struct Cfg {
+// AS ("A-stationary"): the 128 x K panel of A (K <= A_SLOTS * 64) stays in shared memory while the CTA walks the
+// n-tiles of its work item; only B is streamed through the ring.  Operand traffic L2 -> SM per 128 x BN tile
+// drops from (128 + BN) * K to BN * K (BN/2 * K for a CTA pair), which is what bounds the K = 384 DiT
+// contractions (profiles/README.md).
+template <int BN, int CG = 1, bool AS = false> struct Cfg {
     static constexpr int B_ROWS = BN / CG;                       // B rows staged by one CTA
-    static constexpr int STAGES = (B_ROWS <= 64) ? 6 : (B_ROWS <= 128 ? 5 : (B_ROWS <= 192 ? 4 : 3));
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = B_ROWS * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + XPOSE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int A_SLOTS = AS ? 6 : 0;
+    static constexpr int PANEL_BYTES = A_SLOTS * A_BYTES;
+    static constexpr int STAGE_BYTES = AS ? B_BYTES : A_BYTES + B_BYTES;
+    // per epilogue warp: 8 KB of staging (two 32 x 32 output boxes for the TMA epilogue; the legacy path uses the
+    // first 4.5 KB as its padded transpose buffer) + 512 B for the warp's slice of the bias vector
+    static constexpr int EPI_WARP_BYTES = 8192;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int BIAS_BYTES = EPI_WARPS * 512;
+    static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int FIT = (232448 - FIXED_BYTES - PANEL_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > (AS ? 8 : 6) ? (AS ? 8 : 6) : FIT;
+    static constexpr int SMEM = PANEL_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // power of two
     static constexpr int CHUNKS = BN / 32;
     static constexpr int CHUNKS_PER_GROUP = CHUNKS / 2;
+    static_assert(STAGES >= 2 && STAGES <= 8, "ring depth");
 };
 
 // fast activations for the hot epilogue (ex2.approx + rcp.approx; error << bf16 resolution)
@@ -76,37 +93,85 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
     return x;
 }
 
+// Experiments (XDB200_DEBUG knobs) and the in-kernel cycle accounting (XDB200_PROF) are compiled only with
+// -DXDB200_INSTRUMENT (NVCC_EXTRA=-DXDB200_INSTRUMENT csrc/build.sh): they cost code size in the hot loops.
+#ifdef XDB200_INSTRUMENT
+constexpr bool kInst = true;
+#else
+constexpr bool kInst = false;
+#endif
+enum { EPI_LEGACY = 0, EPI_TMA_F32 = 1, EPI_TMA_BF16 = 2 };
+
+// mbarrier wait that (optionally) accounts the waiting time; profiling builds of the wait are only taken when
+// XDB200_PROF is set, the branch is warp-uniform.
+__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t parity, bool prof, long long& acc) {
+    if (prof) {
+        const long long t = clock64();
+        ptx::mbar_wait(bar, parity);
+        acc += clock64() - t;
+    } else {
+        ptx::mbar_wait(bar, parity);
+    }
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
 // 256 x BN tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one
 // M = 256 MMA that reads both CTAs' shared memory and writes both CTAs' TMEM -- half the shared-memory
 // and L2 operand traffic per FLOP, which is what bounds the 1-CTA kernel (see profiles/README.md).
-template <int BN, int ACT, int CG>
+template <int BN, int ACT, int CG, bool AS, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    using C = Cfg<BN, CG>;
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
+               const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
+    using C = Cfg<BN, CG, AS>;
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::XPOSE_BYTES);
-    uint64_t* empty_bar = full_bar + C::STAGES;
-    uint64_t* tmem_full_bar = empty_bar + C::STAGES;     // [2]
+    uint8_t* panel = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = panel + C::PANEL_BYTES;              // the ring
+    uint8_t* epi = smem + C::STAGES * C::STAGE_BYTES;    // 1024-aligned (all stage sizes are multiples of 1024)
+    uint8_t* bias_sm = epi + C::EPI_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_sm + C::BIAS_BYTES);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tmem_full_bar = empty_bar + 8;             // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* a_full_bar = tmem_empty_bar + 2;           // [6]  (AS only)
+    uint64_t* a_empty_bar = a_full_bar + 6;              // [6]
+    uint64_t* res_bar = a_empty_bar + 6;                 // [EPI_WARPS][2]  (TMA epilogue: residual box landed)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool prof = kInst && p.prof != nullptr;
+    const int dbg = kInst ? p.debug : 0;
+    long long* pslot = prof ? p.prof + 16 * blockIdx.x : nullptr;
+    if (prof && threadIdx.x == 0) pslot[8] = (long long)globaltimer_ns();
     const int nk = p.nk0 + p.nk1;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = n_tiles * ((p.M + BM * CG - 1) / (BM * CG));
+    const int total_items = p.ng * ((p.M + BM * CG - 1) / (BM * CG));
     const int rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;     // 0 = leader (issues the MMAs)
-    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
+    const int first_item = blockIdx.x / CG, item_step = gridDim.x / CG;
+// work item w = (m-tile, group of tpg consecutive n-tiles); without AS every item is one tile (n fastest)
+#define XD_ITEM_LOOP for (int w_ = first_item; w_ < total_items; w_ += item_step, ++item)
+#define XD_ITEM_DECODE                                  \
+    const int mt = w_ / p.ng;                           \
+    const int nt0 = (w_ - mt * p.ng) * p.tpg;           \
+    const int nt1 = min(n_tiles, nt0 + p.tpg);
+#define XD_TILE_LOOP for (int nt = nt0; nt < nt1; ++nt, ++it)
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmB);
         if (p.nk1) ptx::prefetch_tmap(&tmA1);
+        if (EPI != EPI_LEGACY) {
+            ptx::prefetch_tmap(&tmOut);
+            if (p.epi.residual) ptx::prefetch_tmap(&tmRes);
+        }
+        for (int k = 0; k < 2 * EPI_WARPS; ++k) ptx::mbar_init(&res_bar[k], 1);
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], CG);                // one arrive.expect_tx per CTA of the group
             ptx::mbar_init(&empty_bar[s], 1);
@@ -114,6 +179,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&tmem_full_bar[b], 1);
             ptx::mbar_init(&tmem_empty_bar[b], EPI_WARPS * CG);
+        }
+        for (int k = 0; k < C::A_SLOTS; ++k) {
+            ptx::mbar_init(&a_full_bar[k], CG);
+            ptx::mbar_init(&a_empty_bar[k], 1);
         }
         ptx::fence_barrier_init();
     }
@@ -139,10 +208,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0;                                          // ring position, continuous across tiles
-            uint32_t ph = 0;
-            for (int tile = first_tile; tile < total_tiles && p.debug != 7; tile += tile_step) {
-                const int m0 = (tile / n_tiles) * (BM * CG) + rank * BM;     // this CTA's 128 rows of A
-                const int n0 = (tile % n_tiles) * BN + rank * C::B_ROWS;     // this CTA's share of the B tile
+            uint32_t ph = 0, it = 0, item = 0;
+            long long w_empty = 0;
+            const long long t_begin = prof ? clock64() : 0;
+            if (dbg != 7 && dbg != 9) XD_ITEM_LOOP { XD_ITEM_DECODE XD_TILE_LOOP {
+                const int m0 = mt * (BM * CG) + rank * BM;                   // this CTA's 128 rows of A
+                const int n0 = nt * BN + rank * C::B_ROWS;                   // this CTA's share of the B tile
                 int img = 0, h0 = 0;
                 if (p.conv) {
                     const int hw = p.H * p.W;
@@ -150,9 +221,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     h0 = (m0 - img * hw) / p.W;
                 }
                 for (int kb = 0; kb < nk; ++kb) {
-                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sA = smem + s * C::STAGE_BYTES;
-                    uint8_t* sB = sA + C::A_BYTES;
+                    const bool load_a = !AS || nt == nt0;
+                    uint64_t* bar_a = AS ? &a_full_bar[kb] : &full_bar[s];
+                    uint8_t* sA = AS ? panel + kb * C::A_BYTES : smem + s * C::STAGE_BYTES;
+                    uint8_t* sB = AS ? smem + s * C::STAGE_BYTES : sA + C::A_BYTES;
+                    if (AS && load_a) ptx::mbar_wait(&a_empty_bar[kb], (item & 1) ^ 1);
+                    wait_acc(&empty_bar[s], ph ^ 1, prof, w_empty);
                     const CUtensorMap* tm = &tmA0;
                     int c0, c1, c2, c3;
                     if (kb < p.nk0) {
@@ -169,21 +243,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         if (!p.conv) { c0 = k1 * BK; c1 = m0; c2 = 0; c3 = 0; }
                         else { c0 = k1 * BK; c1 = 0; c2 = h0; c3 = img; }
                     }
-                    if (p.debug >= 5) {                          // experiment: no operand traffic at all
-                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&full_bar[s]);
-                        else ptx::mbar_arrive(&full_bar[s]);
+                    if (dbg >= 5) {                          // experiment: no operand traffic at all
+                        if constexpr (CG == 2) {
+                            if (AS && load_a) ptx::mbar_arrive_leader(bar_a);
+                            ptx::mbar_arrive_leader(&full_bar[s]);
+                        } else {
+                            if (AS && load_a) ptx::mbar_arrive(bar_a);
+                            ptx::mbar_arrive(&full_bar[s]);
+                        }
                     } else if constexpr (CG == 2) {
-                        ptx::mbar_arrive_expect_tx_leader(&full_bar[s], C::STAGE_BYTES);
-                        ptx::tma_load_4d_2sm(sA, tm, &full_bar[s], c0, c1, c2, c3);
+                        if constexpr (AS) {
+                            if (load_a) {
+                                ptx::mbar_arrive_expect_tx_leader(bar_a, C::A_BYTES);
+                                ptx::tma_load_4d_2sm(sA, tm, bar_a, c0, c1, c2, c3);
+                            }
+                            ptx::mbar_arrive_expect_tx_leader(&full_bar[s], C::B_BYTES);
+                        } else {
+                            ptx::mbar_arrive_expect_tx_leader(&full_bar[s], C::STAGE_BYTES);
+                            ptx::tma_load_4d_2sm(sA, tm, bar_a, c0, c1, c2, c3);
+                        }
                         ptx::tma_load_2d_2sm(sB, &tmB, &full_bar[s], kb * BK, n0);
                     } else {
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-                        ptx::tma_load_4d(sA, tm, &full_bar[s], c0, c1, c2, c3);
+                        if constexpr (AS) {
+                            if (load_a) {
+                                ptx::mbar_arrive_expect_tx(bar_a, C::A_BYTES);
+                                ptx::tma_load_4d(sA, tm, bar_a, c0, c1, c2, c3);
+                            }
+                            ptx::mbar_arrive_expect_tx(&full_bar[s], C::B_BYTES);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                            ptx::tma_load_4d(sA, tm, bar_a, c0, c1, c2, c3);
+                        }
                         ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
                     }
                     if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
-            }
+            }}
+            if (prof) { pslot[3] = clock64() - t_begin; pslot[4] = w_empty; }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
@@ -192,24 +288,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (rank == 0) {
             constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM * CG, BN);
             const uint64_t desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem));
-            uint32_t it = 0;
+            const uint64_t desc_panel = ptx::smem_desc_sw128(ptx::smem_u32(panel));
+            uint32_t it = 0, item = 0;
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+            long long w_tmem = 0, w_full = 0;
+            const long long t_begin = prof ? clock64() : 0;
+            XD_ITEM_LOOP { XD_ITEM_DECODE XD_TILE_LOOP {
                 const uint32_t buf = it & 1;
-                ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                wait_acc(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1, prof, w_tmem);  // epilogue drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * BN;
                 for (int kb = 0; kb < nk; ++kb) {
-                    if (p.debug != 7) {
-                        ptx::mbar_wait(&full_bar[s], ph);
+                    if (dbg != 7 && dbg != 9) {
+                        if (AS && nt == nt0) ptx::mbar_wait(&a_full_bar[kb], item & 1);
+                        wait_acc(&full_bar[s], ph, prof, w_full);
                         ptx::tc_fence_after();
                     }
                     // descriptors differ between stages only in the start-address field (16-byte units)
-                    const uint64_t da = desc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
-                    const uint64_t db = da + (C::A_BYTES >> 4);
+                    const uint64_t dring = desc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
+                    const uint64_t da = AS ? desc_panel + (uint64_t)((kb * C::A_BYTES) >> 4) : dring;
+                    const uint64_t db = AS ? dring : dring + (C::A_BYTES >> 4);
                     if (ptx::elect_one()) {
-                        if (p.debug != 2 && p.debug != 4) {
+                        if (dbg != 2 && dbg != 4) {
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k) {
                                 // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
@@ -218,35 +319,196 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             }
                         }
                         if constexpr (CG == 2) {
-                            if (p.debug != 7) ptx::umma_commit_2sm(&empty_bar[s]);
+                            if (dbg != 7) ptx::umma_commit_2sm(&empty_bar[s]);
+                            if (AS && nt == nt1 - 1) ptx::umma_commit_2sm(&a_empty_bar[kb]);   // panel slot free
                             if (kb == nk - 1) ptx::umma_commit_2sm(&tmem_full_bar[buf]);
                         } else {
-                            if (p.debug != 7) ptx::umma_commit(&empty_bar[s]);
+                            if (dbg != 7) ptx::umma_commit(&empty_bar[s]);
+                            if (AS && nt == nt1 - 1) ptx::umma_commit(&a_empty_bar[kb]);
                             if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[buf]);
                         }
                     }
                     __syncwarp();
                     if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
-            }
+            }}
+            if (prof && lane == 0) { pslot[0] = clock64() - t_begin; pslot[1] = w_tmem; pslot[2] = w_full; pslot[10] = it; }
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         const int e_warp = warp - 2;
         const int grp = e_warp >> 2;                    // which half of the tile's columns
         const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-        float* st = xpose + e_warp * 32 * STAGE_LD;     // private 32 x 32 (+pad) transpose buffer
+        float* st = reinterpret_cast<float*>(epi + e_warp * C::EPI_WARP_BYTES);   // private 32 x 32 (+pad) transpose buffer
         const Epilogue& e = p.epi;
         const int sub_row = lane >> 3;                  // coalesced pass: 4 rows x 8 lanes x 4 columns
         const int sub_col = (lane & 7) * 4;
         const bool res_f32 = e.res_dtype == XD_F32, out_f32 = e.out_dtype == XD_F32;
         const bool direct_bf16 = C::CHUNKS_PER_GROUP >= 2 && !out_f32 && !e.gate && !e.residual && (p.N % 8 == 0) && p.direct_ok;
         const int res_ld = (int)e.res_ld, out_ld = (int)e.out_ld;     // per-tile row offsets fit 32 bits
-        uint32_t it = 0;
-        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
-            const int m0 = (tile / n_tiles) * (BM * CG) + rank * BM + q * 32;   // first row of this warp's 32-row band
-            const int n0 = (tile % n_tiles) * BN;
+        uint32_t it = 0, item = 0;
+        long long w_acc = 0, w_res = 0, seg[4] = {0, 0, 0, 0};
+        const long long t_begin = prof ? clock64() : 0;
+        uint32_t cc = 0;                                 // TMA epilogue: chunks processed by this warp (box / phase)
+        const uint32_t wbuf_a = ptx::smem_u32(epi + e_warp * C::EPI_WARP_BYTES);
+        const uint32_t bias_a = ptx::smem_u32(bias_sm + e_warp * 512);
+        uint64_t* rbar = res_bar + 2 * e_warp;
+        XD_ITEM_LOOP { XD_ITEM_DECODE XD_TILE_LOOP {
+            const int m0 = mt * (BM * CG) + rank * BM + q * 32;   // first row of this warp's 32-row band
+            const int n0 = nt * BN;
             const uint32_t buf = it & 1;
+            if constexpr (EPI != EPI_LEGACY) {
+                constexpr bool out_f32 = EPI == EPI_TMA_F32;
+                // ---- TMA epilogue.  Each warp owns 32 rows x CPG 32-column chunks and works in the TMEM-native
+                // layout (lane = row): the residual chunk arrives by a bulk tensor load into the warp's private
+                // swizzled 32 x 32 box (prefetched one chunk ahead), is combined in place with the accumulator
+                // (bias from the warp's smem slice, gate through L1) and leaves by a bulk tensor store.  No
+                // transpose, no per-element predicates (TMA clips / zero-fills at the M and N edges).
+                constexpr int CPG = C::CHUNKS_PER_GROUP > 0 ? C::CHUNKS_PER_GROUP : 1;
+                const int ncol0 = n0 + grp * CPG * 32;
+                const bool has_res = e.residual != nullptr && !(kInst && dbg >= 3 && dbg != 6);
+                const uint32_t box_bytes = out_f32 ? 4096u : 2048u;
+#pragma unroll
+                for (int k = 0; k < CPG; ++k) {
+                    const int col = ncol0 + k * 32 + lane;
+                    ptx::sts32(bias_a + (k * 32 + lane) * 4, (e.bias && col < p.N) ? __float_as_uint(__ldg(e.bias + col)) : 0u);
+                }
+                if (has_res && lane == 0) {
+                    ptx::bulk_wait_read<1>();                    // the store that last read this buffer (chunk cc - 2)
+                    const uint32_t b = cc & 1;
+                    ptx::mbar_arrive_expect_tx(&rbar[b], box_bytes);
+                    ptx::tma_load_2d_u32(wbuf_a + b * 4096, &tmRes, ptx::smem_u32(&rbar[b]), ncol0, m0);
+                }
+                __syncwarp();
+                const float* gp = nullptr;                       // this lane's (= row's) gate row
+                if (e.gate) gp = e.gate + (long long)(min(m0 + lane, p.M - 1) / e.gate_rows) * e.gate_ld;
+                wait_acc(&tmem_full_bar[buf], (it >> 1) & 1, prof, w_acc);
+                ptx::tc_fence_after();
+                const uint32_t t_addr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + grp * CPG * 32;
+                if (kInst && dbg >= 3 && dbg != 6) {             // experiment: mainloop only
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
+                        else ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                    }
+                    continue;
+                }
+                // TMEM reads are the scarce resource of the epilogue (~64 B/clk/SM, 96 KB per 128 x 192 tile): the load of
+                // chunk ci + 1 is in flight while chunk ci is processed (two register buffers, loop fully unrolled).
+                uint32_t rr[2][32];
+                ptx::tmem_ld_32x32(t_addr, rr[0]);
+#pragma unroll
+                for (int ci = 0; ci < CPG; ++ci, ++cc) {
+                    const int nc = ncol0 + ci * 32;
+                    const uint32_t b = cc & 1;
+                    const uint32_t wb = wbuf_a + b * 4096;
+                    uint32_t* r = rr[ci & 1];
+                    long long tA = prof ? clock64() : 0;
+                    if (lane == 0) {
+                        if (has_res) {
+                            if (ci + 1 < CPG) {                  // prefetch the next residual chunk into the other box
+                                ptx::bulk_wait_read<0>();
+                                ptx::mbar_arrive_expect_tx(&rbar[b ^ 1], box_bytes);
+                                ptx::tma_load_2d_u32(wbuf_a + (b ^ 1) * 4096, &tmRes, ptx::smem_u32(&rbar[b ^ 1]), nc + 32, m0);
+                            }
+                        } else {
+                            ptx::bulk_wait_read<1>();            // box b was last read by the store of chunk cc - 2
+                        }
+                    }
+                    if (prof) { const long long t = clock64(); seg[0] += t - tA; tA = t; }     // bulk_wait_read (+ prefetch issue)
+                    ptx::tmem_ld_wait();
+                    if (ci + 1 < CPG) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, rr[(ci + 1) & 1]);
+                    if (prof) { const long long t = clock64(); seg[1] += t - tA; tA = t; }     // TMEM load
+                    if (ci == CPG - 1) ptx::tc_fence_before();
+                    __syncwarp();
+                    if (ci == CPG - 1 && lane == 0) {            // last TMEM read of this tile by this warp
+                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
+                        else ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                    }
+                    if (has_res) wait_acc(&rbar[b], (cc >> 1) & 1, prof, w_res);
+                    // The shared-memory accesses are volatile asm (program order), so loads are issued in batches
+                    // ahead of the arithmetic: a load -> use -> store chain per 16 bytes costs one LDS latency each.
+                    if constexpr (out_f32) {
+                        const uint32_t rowa = wb + lane * 128;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {            // 16 columns per half
+                            uint4 bq[4], rs[4];
+                            float4 g[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * h + jj;
+                                g[jj] = make_float4(1.f, 1.f, 1.f, 1.f);
+                                if (gp && nc + 4 * j < p.N) g[jj] = __ldg(reinterpret_cast<const float4*>(gp + nc) + j);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) bq[jj] = ptx::lds128(bias_a + (ci * 32 + 16 * h + 4 * jj) * 4);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                rs[jj] = make_uint4(0u, 0u, 0u, 0u);
+                                if (has_res) rs[jj] = ptx::lds128(rowa + (((4 * h + jj) ^ (lane & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int c = 16 * h + 4 * jj;
+                                rs[jj].x = __float_as_uint(fmaf(act_fast<ACT>(__uint_as_float(r[c]) + __uint_as_float(bq[jj].x)), g[jj].x, __uint_as_float(rs[jj].x)));
+                                rs[jj].y = __float_as_uint(fmaf(act_fast<ACT>(__uint_as_float(r[c + 1]) + __uint_as_float(bq[jj].y)), g[jj].y, __uint_as_float(rs[jj].y)));
+                                rs[jj].z = __float_as_uint(fmaf(act_fast<ACT>(__uint_as_float(r[c + 2]) + __uint_as_float(bq[jj].z)), g[jj].z, __uint_as_float(rs[jj].z)));
+                                rs[jj].w = __float_as_uint(fmaf(act_fast<ACT>(__uint_as_float(r[c + 3]) + __uint_as_float(bq[jj].w)), g[jj].w, __uint_as_float(rs[jj].w)));
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) ptx::sts128(rowa + (((4 * h + jj) ^ (lane & 7)) << 4), rs[jj]);
+                        }
+                    } else {
+                        const uint32_t rowa = wb + lane * 64;
+                        uint4 bq[8], rs[4];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bq[j] = ptx::lds128(bias_a + (ci * 32 + 4 * j) * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            rs[j] = make_uint4(0u, 0u, 0u, 0u);
+                            if (has_res) rs[j] = ptx::lds128(rowa + ((j ^ ((lane >> 1) & 3)) << 4));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+                            v[0] = act_fast<ACT>(__uint_as_float(r[8 * j]) + __uint_as_float(bq[2 * j].x));
+                            v[1] = act_fast<ACT>(__uint_as_float(r[8 * j + 1]) + __uint_as_float(bq[2 * j].y));
+                            v[2] = act_fast<ACT>(__uint_as_float(r[8 * j + 2]) + __uint_as_float(bq[2 * j].z));
+                            v[3] = act_fast<ACT>(__uint_as_float(r[8 * j + 3]) + __uint_as_float(bq[2 * j].w));
+                            v[4] = act_fast<ACT>(__uint_as_float(r[8 * j + 4]) + __uint_as_float(bq[2 * j + 1].x));
+                            v[5] = act_fast<ACT>(__uint_as_float(r[8 * j + 5]) + __uint_as_float(bq[2 * j + 1].y));
+                            v[6] = act_fast<ACT>(__uint_as_float(r[8 * j + 6]) + __uint_as_float(bq[2 * j + 1].z));
+                            v[7] = act_fast<ACT>(__uint_as_float(r[8 * j + 7]) + __uint_as_float(bq[2 * j + 1].w));
+                            if (gp) {
+                                float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+                                if (nc + 8 * j < p.N) g0 = __ldg(reinterpret_cast<const float4*>(gp + nc) + 2 * j);
+                                if (nc + 8 * j + 4 < p.N) g1 = __ldg(reinterpret_cast<const float4*>(gp + nc) + 2 * j + 1);
+                                v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+                                v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+                            }
+                            if (has_res) {
+                                float2 t;
+                                t = bf2_to_f2(rs[j].x); v[0] += t.x; v[1] += t.y;
+                                t = bf2_to_f2(rs[j].y); v[2] += t.x; v[3] += t.y;
+                                t = bf2_to_f2(rs[j].z); v[4] += t.x; v[5] += t.y;
+                                t = bf2_to_f2(rs[j].w); v[6] += t.x; v[7] += t.y;
+                            }
+                            rs[j] = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]), f2_to_bf2(v[6], v[7]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ptx::sts128(rowa + ((j ^ ((lane >> 1) & 3)) << 4), rs[j]);
+                    }
+                    if (prof) { const long long t = clock64(); seg[2] += t - tA; tA = t; }     // residual wait + math + STS
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (dbg != 1) ptx::tma_store_2d(&tmOut, wb, nc, m0);
+                        ptx::bulk_commit();
+                    }
+                    if (prof) { const long long t = clock64(); seg[3] += t - tA; tA = t; }     // proxy fence + store issue
+                }
+            } else {
             // per-tile row bookkeeping, hoisted out of the chunk loop (all 32-bit)
             const int rows_left = p.M - m0;                             // rows rr < rows_left are valid
             unsigned gate_row[8];
@@ -259,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-            if (p.debug >= 3 && p.debug != 6) {         // experiment: mainloop only
+            if (dbg >= 3 && dbg != 6) {         // experiment: mainloop only (9 = 7 + per-stage commits)
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -320,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         for (int i = 0; i < 8; ++i) {
                             const int rr = i * 4 + sub_row;
                             const uint4 u = *reinterpret_cast<const uint4*>(sb + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-                            if (rr < rows_left && lane_ok && p.debug != 1)
+                            if (rr < rows_left && lane_ok && dbg != 1)
                                 *reinterpret_cast<uint4*>(out_band + (unsigned)(rr * out_ld + col) * 2u) = u;
                         }
                         __syncwarp();
@@ -376,8 +638,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 __syncwarp();                           // transpose buffer is reused by the next chunk
             }
+            }   // EPI_LEGACY
+        }}
+        if (prof && warp == 2 && lane == 0) {
+            pslot[5] = clock64() - t_begin; pslot[6] = w_acc; pslot[7] = w_res;
+            pslot[12] = seg[0]; pslot[13] = seg[1]; pslot[14] = seg[2]; pslot[15] = seg[3];
         }
+        if (EPI != EPI_LEGACY && lane == 0) ptx::bulk_wait<0>();    // all bulk stores of this warp have completed
+        if (prof && warp == 2 && lane == 0) pslot[11] = clock64() - t_begin;
     }
+#undef XD_ITEM_LOOP
+#undef XD_ITEM_DECODE
+#undef XD_TILE_LOOP
     ptx::tc_fence_before();
     if constexpr (CG == 2) ptx::cluster_sync();             // no remote arrive / peer smem read after a CTA exits
     else __syncthreads();
@@ -386,6 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if constexpr (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
         else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+    if (prof && threadIdx.x == 0) pslot[9] = (long long)globaltimer_ns();
 }
 
 // ------------------------------------------------------------------ host side
@@ -408,13 +681,14 @@ EncodeTiledFn get_encode() {
 
 // bf16 tensor map, inner box = 64 elements (128 B), 128-byte swizzle, zero OOB fill.
 int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box) {
+              const cuuint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+              CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { xd_set_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled entry point not found"); return XD_ERR_TMAP; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
-                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         static char msg[160];
         snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
@@ -451,6 +725,16 @@ int tmap_nhwc(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, l
     return make_tmap(tm, ptr, 4, dims, str, box);
 }
 
+// Epilogue boxes: 32 rows x 32 columns of the [M, N] output / residual (fp32: 128-byte rows, 128-byte swizzle;
+// bf16: 64-byte rows, 64-byte swizzle).
+int tmap_epi(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, bool f32) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {32, 32};
+    return make_tmap(tm, ptr, 2, dims, str, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // The kernel's epilogue uses 16-byte (fp32) / 8-byte (bf16) accesses on 4-column groups.
@@ -459,6 +743,27 @@ int epilogue_vec_ok(const Epilogue& e, int N) {
     ok = ok && (N % 4 == 0) && (e.out_ld % 4 == 0) && (e.res_ld % 4 == 0) && (e.gate_ld % 4 == 0);
     ok = ok && e.out_ld < (1 << 22) && e.res_ld < (1 << 22);      // 32-bit byte offsets inside a 128-row tile
     return ok ? 1 : 0;
+}
+
+// The TMA epilogue needs 16-byte aligned rows (global strides are multiples of 16 bytes) and a residual of the
+// output's dtype; everything else takes the legacy register / transpose epilogue.
+int setup_epilogue(TcParams* p, CUtensorMap* tres, CUtensorMap* tout) {
+    static const int mode = getenv("XDB200_EPI") ? atoi(getenv("XDB200_EPI")) : 1;
+    const Epilogue& e = p->epi;
+    const bool f32 = e.out_dtype == XD_F32;
+    const int esz = f32 ? 4 : 2;
+    bool ok = mode != 0 && (e.out_ld * esz) % 16 == 0;
+    if (e.residual) ok = ok && e.res_dtype == e.out_dtype && (e.res_ld * esz) % 16 == 0;
+    p->tma_epi = 0;
+    memset(tres, 0, sizeof *tres);
+    memset(tout, 0, sizeof *tout);
+    if (!ok) return XD_OK;
+    int rc;
+    if ((rc = tmap_epi(tout, e.out, p->M, p->N, e.out_ld, f32))) return rc;
+    *tres = *tout;
+    if (e.residual && (rc = tmap_epi(tres, e.residual, p->M, p->N, e.res_ld, f32))) return rc;
+    p->tma_epi = 1;
+    return XD_OK;
 }
 
 int sm_count() {
@@ -471,24 +776,25 @@ int sm_count() {
     return n;
 }
 
-template <int BN, int ACT, int CG>
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
+template <int BN, int ACT, int CG, bool AS, int EPI>
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& tr,
+           const CUtensorMap& to, const TcParams& p, cudaStream_t st) {
     static bool configured = false;
-    auto kernel = gemm_tc_kernel<BN, ACT, CG>;
+    auto kernel = gemm_tc_kernel<BN, ACT, CG, AS, EPI>;
     if (!configured) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, AS>::SMEM) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
             return XD_ERR_CUDA;
         }
         configured = true;
     }
-    const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM * CG - 1) / (BM * CG));
+    const long long items = (long long)p.ng * ((p.M + BM * CG - 1) / (BM * CG));
     // persistent: <= one CTA (pair) per SM (pair)
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count() / CG) * CG;
+    const unsigned grid = (unsigned)std::min<long long>(items, sm_count() / CG) * CG;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM;
+    cfg.dynamicSmemBytes = Cfg<BN, CG, AS>::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -499,52 +805,119 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = xd_pdl_enabled() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, kernel, a0, a1, b, p) != cudaSuccess) {
+    static const bool want_prof = kInst && getenv("XDB200_PROF") != nullptr;
+    TcParams pp = p;
+    static long long* prof_dev = nullptr;
+    if (want_prof) {                                            // debugging aid: synchronous, never in a captured graph
+        if (!prof_dev) cudaMalloc(&prof_dev, 16 * 256 * sizeof(long long));
+        cudaMemsetAsync(prof_dev, 0, 16 * 256 * sizeof(long long), st);
+        pp.prof = prof_dev;
+    }
+    if (cudaLaunchKernelEx(&cfg, kernel, a0, a1, b, tr, to, pp) != cudaSuccess) {
         xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
         return XD_ERR_CUDA;
+    }
+    if (want_prof) {
+        static long long h[16 * 256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
+        static const char* names[16] = {"mma total", "mma wait tmem_empty", "mma wait full", "prod total", "prod wait empty",
+                                        "epi total", "epi wait tmem_full", "epi wait residual", "", "", "tiles", "epi total+drain",
+                                        "epi seg wait_read", "epi seg tmem_ld", "epi seg math+sts", "epi seg fence+store"};
+        long long t0 = h[8], t1 = h[9];
+        for (unsigned c = 0; c < grid; ++c) { t0 = std::min(t0, h[16 * c + 8]); t1 = std::max(t1, h[16 * c + 9]); }
+        fprintf(stderr, "[xdb200 prof] BN=%d CG=%d AS=%d M=%d N=%d nk=%d grid=%u span=%.2f us\n", BN, CG, (int)AS, p.M, p.N,
+                p.nk0 + p.nk1, grid, (t1 - t0) * 1e-3);
+        for (int k = 0; k < 16; ++k) {
+            if (!names[k][0]) continue;
+            double sum = 0; long long mx = 0;
+            for (unsigned c = 0; c < grid; ++c) { sum += h[16 * c + k]; mx = std::max(mx, h[16 * c + k]); }
+            fprintf(stderr, "[xdb200 prof]   %-22s mean %9.0f  max %9lld (cycles)\n", names[k], sum / grid, mx);
+        }
+        double first = 1e30, last = 0;
+        for (unsigned c = 0; c < grid; ++c) { first = std::min(first, (double)(h[16 * c + 8] - t0)); last = std::max(last, (double)(h[16 * c + 8] - t0)); }
+        fprintf(stderr, "[xdb200 prof]   CTA start skew %.2f us\n", last * 1e-3);
     }
     return XD_OK;
 }
 
-// Tile shape: (bn, cg).  force: 0 = auto; 64/128/256 = 1-CTA tiles; 1128/1256 = CTA-pair 256 x 128 / 256 x 256.
-void pick_tile(int N, int M, int force, int* bn, int* cg) {
-    if (force >= 1000) { *cg = 2; *bn = force - 1000; return; }
-    if (force) { *cg = 1; *bn = force; return; }
+struct TileChoice {
+    int bn, cg, as;
+};
+
+// force: 0 = auto; 64/128/192/256 = 1-CTA tiles; 1128/1256 = CTA-pair 256 x 128 / 256 x 256;
+// 2192 = A-stationary 1-CTA 128 x 192; 3192 / 3256 = A-stationary CTA pair 256 x 192 / 256 x 256.
+TileChoice pick_tile(int N, int M, int nk, int conv, int force) {
+    if (force >= 3000) return {force - 3000, 2, 1};
+    if (force >= 2000) return {force - 2000, 1, 1};
+    if (force >= 1000) return {force - 1000, 2, 0};
+    if (force) return {force, 1, 0};
     // tcgen05.mma 128 x N x 16 from shared memory runs at ~half rate for N = 128 (operand reads
     // saturate the shared-memory port) and at ~75% of peak for N >= 192 (measured, profiles/README.md),
-    // so take the widest tile that divides N; a CTA pair for the N = 128 leftovers.
+    // so take the widest tile that divides N.
     static const int mode = getenv("XDB200_CG") ? atoi(getenv("XDB200_CG")) : 1;
-    *cg = 1;
-    if (N <= 64) { *bn = 64; return; }
+    static const int as_mode = getenv("XDB200_AS") ? atoi(getenv("XDB200_AS")) : 0;
+    if (N <= 64) return {64, 1, 0};
     const long long m_tiles = (M + BM - 1) / BM;
-    auto fills = [&](int w) { return m_tiles * ((N + w - 1) / w) >= sm_count(); };   // at least one full wave
-    if (N % 192 == 0 && fills(192)) *bn = 192;          // measured: 192 beats 256 when both divide N
-    else if (N % 256 == 0 && fills(256)) *bn = 256;
-    else if (N > 1024 && fills(256)) *bn = 256;
-    else {
-        *bn = 128;
-        if (mode == 2 && M > BM) *cg = 2;
+    if (as_mode && !conv && nk <= Cfg<192, 1, true>::A_SLOTS && N % 192 == 0 && N > 192 && m_tiles * 4 >= 3 * sm_count()) {
+        if (as_mode >= 2 && N % 256 == 0 && as_mode == 3) return {256, 2, 1};
+        if (as_mode >= 2) return {192, 2, 1};
+        return {192, 1, 1};
     }
+    auto fills = [&](int w) { return m_tiles * ((N + w - 1) / w) >= sm_count(); };   // at least one full wave
+    if (N % 192 == 0 && fills(192)) return {192, 1, 0};         // measured: 192 beats 256 when both divide N
+    if (N % 256 == 0 && fills(256)) return {256, 1, 0};
+    if (N > 1024 && fills(256)) return {256, 1, 0};
+    return {128, (mode == 2 && M > BM) ? 2 : 1, 0};
 }
 
-int dispatch(int bn, int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p,
+// Work items for the A-stationary kernels: groups of consecutive n-tiles, as few groups as keep >= 3/4 of the
+// CTAs (pairs) busy.  Without AS every tile is its own item.
+void set_items(TcParams* p, const TileChoice& t) {
+    const int n_tiles = (p->N + t.bn - 1) / t.bn;
+    if (!t.as) { p->ng = n_tiles; p->tpg = 1; return; }
+    const long long m_tiles = (p->M + BM * t.cg - 1) / (BM * t.cg);
+    const long long units = sm_count() / t.cg;
+    int ng = 1;
+    while (m_tiles * ng * 4 < units * 3 && ng < n_tiles) ++ng;
+    p->tpg = (n_tiles + ng - 1) / ng;
+    p->ng = (n_tiles + p->tpg - 1) / p->tpg;
+}
+
+int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
              cudaStream_t st) {
-#define XD_TC_CASE(BN_, CG_)                                                                    \
-    if (bn == BN_ && cg == CG_) {                                                               \
-        switch (p.epi.act) {                                                                    \
-            case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE, CG_>(a0, a1, b, p, st);           \
-            case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU, CG_>(a0, a1, b, p, st);           \
-            case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH, CG_>(a0, a1, b, p, st); \
-        }                                                                                       \
+    CUtensorMap tr, to;
+    if (int rc = setup_epilogue(&p, &tr, &to)) return rc;
+    if (t.as && p.nk0 + p.nk1 > Cfg<192, 1, true>::A_SLOTS) {
+        xd_set_error(__FILE__, __LINE__, "A-stationary tile needs K <= 384");
+        return XD_ERR_ARG;
     }
-    XD_TC_CASE(64, 1)
-    XD_TC_CASE(128, 1)
-    XD_TC_CASE(192, 1)
-    XD_TC_CASE(256, 1)
-    XD_TC_CASE(128, 2)
-    XD_TC_CASE(256, 2)
+    set_items(&p, t);
+    const int epi = p.tma_epi ? (p.epi.out_dtype == XD_F32 ? EPI_TMA_F32 : EPI_TMA_BF16) : EPI_LEGACY;
+#define XD_TC_ACT(BN_, CG_, AS_, EPI_)                                                                     \
+    switch (p.epi.act) {                                                                                   \
+        case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st);       \
+        case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st);       \
+        case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st); \
+    }
+#define XD_TC_CASE(BN_, CG_, AS_)                                                  \
+    if (t.bn == BN_ && t.cg == CG_ && (t.as != 0) == AS_) {                        \
+        if (epi == EPI_TMA_F32) { XD_TC_ACT(BN_, CG_, AS_, EPI_TMA_F32) }          \
+        else if (epi == EPI_TMA_BF16) { XD_TC_ACT(BN_, CG_, AS_, EPI_TMA_BF16) }   \
+        else if (!AS_) { XD_TC_ACT(BN_, CG_, false, EPI_LEGACY) }                  \
+    }
+    XD_TC_CASE(64, 1, false)
+    XD_TC_CASE(128, 1, false)
+    XD_TC_CASE(192, 1, false)
+    XD_TC_CASE(256, 1, false)
+    XD_TC_CASE(128, 2, false)
+    XD_TC_CASE(256, 2, false)
+    XD_TC_CASE(192, 1, true)
+    XD_TC_CASE(192, 2, true)
+    XD_TC_CASE(256, 2, true)
+#undef XD_TC_ACT
 #undef XD_TC_CASE
-    xd_set_error(__FILE__, __LINE__, "unsupported tile shape");
+    xd_set_error(__FILE__, __LINE__, "unsupported tile shape (A-stationary tiles need the TMA epilogue)");
     return XD_ERR_ARG;
 }
 
@@ -569,15 +942,14 @@ extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, lon
     XD_CHECK_ARG(p.vec_ok);
     p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
     p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
-    int bn, cg;
-    pick_tile(N, M, force_bn, &bn, &cg);
+    const TileChoice t = pick_tile(N, M, p.nk0 + p.nk1, 0, force_bn);
     CUtensorMap ta0, ta1, tb;
     int rc;
     if ((rc = tmap_rows(&ta0, A, M, K, lda, BM))) return rc;
     ta1 = ta0;
     if (A2 && (rc = tmap_rows(&ta1, A2, M, K2, lda2, BM))) return rc;
-    if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, bn / cg))) return rc;
-    return dispatch(bn, cg, ta0, ta1, tb, p, (cudaStream_t)stream);
+    if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, t.bn / t.cg))) return rc;
+    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream);
 }
 
 extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
@@ -597,14 +969,13 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     XD_CHECK_ARG(p.vec_ok);
     p.direct_ok = (out_ld % 8 == 0) && getenv("XDB200_NO_DIRECT") == nullptr;
     p.debug = getenv("XDB200_DEBUG") ? atoi(getenv("XDB200_DEBUG")) : 0;
-    int bn, cg;
-    pick_tile(Cout, p.M, force_bn, &bn, &cg);
+    const TileChoice t = pick_tile(Cout, p.M, p.nk0 + p.nk1, 1, force_bn);
     CUtensorMap ta0, ta1, tb;
     int rc;
     if ((rc = tmap_nhwc(&ta0, X, nimg, H, W, C, ldx))) return rc;
     ta1 = ta0;
     if (Xs && (rc = tmap_nhwc(&ta1, Xs, nimg, H, W, Cs, lds))) return rc;
     const long long ktot = 9LL * C + Cs;
-    if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, bn / cg))) return rc;
-    return dispatch(bn, cg, ta0, ta1, tb, p, (cudaStream_t)stream);
+    if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, t.bn / t.cg))) return rc;
+    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream);
 }
