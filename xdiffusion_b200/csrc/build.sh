@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 OUT=../libxdb200.so
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${NVCC_EXTRA:-}"
 mkdir -p ../../build/obj
 pids=()
 for f in abi gemm_tc simt norm attention attention_tc elementwise step; do

@@ -855,7 +855,7 @@ TileChoice pick_tile(int N, int M, int nk, int conv, int force) {
     // tcgen05.mma 128 x N x 16 from shared memory runs at ~half rate for N = 128 (operand reads
     // saturate the shared-memory port) and at ~75% of peak for N >= 192 (measured, profiles/README.md),
     // so take the widest tile that divides N.
-    static const int mode = getenv("XDB200_CG") ? atoi(getenv("XDB200_CG")) : 1;
+    static const int mode = getenv("XDB200_CG") ? atoi(getenv("XDB200_CG")) : 2;     // 1 = never pair CTAs
     static const int as_mode = getenv("XDB200_AS") ? atoi(getenv("XDB200_AS")) : 0;
     if (N <= 64) return {64, 1, 0};
     const long long m_tiles = (M + BM - 1) / BM;
@@ -864,11 +864,16 @@ TileChoice pick_tile(int N, int M, int nk, int conv, int force) {
         if (as_mode >= 2) return {192, 2, 1};
         return {192, 1, 1};
     }
-    auto fills = [&](int w) { return m_tiles * ((N + w - 1) / w) >= sm_count(); };   // at least one full wave
-    if (N % 192 == 0 && fills(192)) return {192, 1, 0};         // measured: 192 beats 256 when both divide N
-    if (N % 256 == 0 && fills(256)) return {256, 1, 0};
-    if (N > 1024 && fills(256)) return {256, 1, 0};
-    return {128, (mode == 2 && M > BM) ? 2 : 1, 0};
+    // CTA pairs (cta_group::2, 256 x BN tiles) halve the B bytes each SM stages per MMA cycle, so the same ring
+    // covers ~1.4x more time: measured 15 % faster on the K = 1536 contraction, 10 % on K = 384 (profiles/README.md).
+    const int cg = (mode != 1 && M >= 2 * BM) ? 2 : 1;
+    const long long units = sm_count() / cg;
+    const long long mt = (M + BM * cg - 1) / (BM * cg);
+    auto fills = [&](int w) { return mt * ((N + w - 1) / w) >= units; };   // at least one full wave
+    if (N % 192 == 0 && fills(192)) return {192, cg, 0};         // measured: 192 beats 256 when both divide N
+    if (N % 256 == 0 && fills(256)) return {256, cg, 0};
+    if (N > 1024 && fills(256)) return {256, cg, 0};
+    return {128, cg, 0};
 }
 
 // Work items for the A-stationary kernels: groups of consecutive n-tiles, as few groups as keep >= 3/4 of the
@@ -911,6 +916,7 @@ int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, 
     XD_TC_CASE(192, 1, false)
     XD_TC_CASE(256, 1, false)
     XD_TC_CASE(128, 2, false)
+    XD_TC_CASE(192, 2, false)
     XD_TC_CASE(256, 2, false)
     XD_TC_CASE(192, 1, true)
     XD_TC_CASE(192, 2, true)
