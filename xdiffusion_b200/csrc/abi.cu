@@ -15,8 +15,11 @@ void xd_set_error(const char* file, int line, const char* msg) {
 extern "C" const char* xd_last_error(void) { return g_err; }
 extern "C" int xd_abi_version(void) { return 1; }
 
-bool xd_pdl_enabled() {
-    // measured neutral under CUDA-graph replay (483 vs 482 img/s, DiT): off unless XDB200_PDL=1
-    static const bool on = getenv("XDB200_PDL") && atoi(getenv("XDB200_PDL")) == 1;
-    return on;
+// Programmatic dependent launch: XDB200_PDL=0 off, 1 every kernel, 2 (default) only the tcgen05 GEMM / conv launches.
+// Measured (profiles/README.md): GEMM-only gains ~2 % on the DiT step; on every kernel it costs the UNet 6 %.
+static int pdl_mode() {
+    static const int m = getenv("XDB200_PDL") ? atoi(getenv("XDB200_PDL")) : 2;
+    return m;
 }
+bool xd_pdl_enabled() { return pdl_mode() == 1; }
+bool xd_pdl_enabled_gemm() { return pdl_mode() >= 1; }

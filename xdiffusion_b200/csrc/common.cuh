@@ -24,7 +24,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
 
-bool xd_pdl_enabled();      // XDB200_PDL=0 disables (abi.cu)
+bool xd_pdl_enabled();       // XDB200_PDL=1: every kernel (abi.cu)
+bool xd_pdl_enabled_gemm();  // XDB200_PDL=1 or 2 (default): the tcgen05 GEMM / conv launches
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t xd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -804,7 +804,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = xd_pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = xd_pdl_enabled_gemm() ? 2 : 1;
     static const bool want_prof = kInst && getenv("XDB200_PROF") != nullptr;
     TcParams pp = p;
     static long long* prof_dev = nullptr;
