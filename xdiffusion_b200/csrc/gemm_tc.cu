@@ -93,6 +93,37 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
     return x;
 }
 
+// (x + b) -> act, two columns at a time.  GELU uses the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2): half the issue
+// slots of the scalar form, same rounding (every step is the same rn operation), one MUFU.TANH per element.
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+template <int ACT> __device__ __forceinline__ void bias_act2(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, float& y0,
+                                                             float& y1) {
+    if constexpr (ACT == XD_ACT_GELU_TANH) {
+        uint64_t x, x2, in, u, h, y;
+        const uint64_t acc = pack_f32x2(__uint_as_float(a0), __uint_as_float(a1));
+        const uint64_t bias = pack_f32x2(__uint_as_float(b0), __uint_as_float(b1));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(acc), "l"(bias));
+        asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(x2) : "l"(x));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(in) : "l"(x2), "l"(pack_f32x2(0.035677408136300125f, 0.035677408136300125f)),
+            "l"(pack_f32x2(0.7978845608028654f, 0.7978845608028654f)));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(x), "l"(in));
+        float u0, u1, t0, t1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(u));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(h) : "l"(x), "l"(pack_f32x2(0.5f, 0.5f)));
+        asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(y) : "l"(h), "l"(pack_f32x2(t0, t1)));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(y));
+    } else {
+        y0 = act_fast<ACT>(__uint_as_float(a0) + __uint_as_float(b0));
+        y1 = act_fast<ACT>(__uint_as_float(a1) + __uint_as_float(b1));
+    }
+}
+
 // Experiments (XDB200_DEBUG knobs) and the in-kernel cycle accounting (XDB200_PROF) are compiled only with
 // -DXDB200_INSTRUMENT (NVCC_EXTRA=-DXDB200_INSTRUMENT csrc/build.sh): they cost code size in the hot loops.
 #ifdef XDB200_INSTRUMENT
@@ -472,14 +503,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float v[8];
-                            v[0] = act_fast<ACT>(__uint_as_float(r[8 * j]) + __uint_as_float(bq[2 * j].x));
-                            v[1] = act_fast<ACT>(__uint_as_float(r[8 * j + 1]) + __uint_as_float(bq[2 * j].y));
-                            v[2] = act_fast<ACT>(__uint_as_float(r[8 * j + 2]) + __uint_as_float(bq[2 * j].z));
-                            v[3] = act_fast<ACT>(__uint_as_float(r[8 * j + 3]) + __uint_as_float(bq[2 * j].w));
-                            v[4] = act_fast<ACT>(__uint_as_float(r[8 * j + 4]) + __uint_as_float(bq[2 * j + 1].x));
-                            v[5] = act_fast<ACT>(__uint_as_float(r[8 * j + 5]) + __uint_as_float(bq[2 * j + 1].y));
-                            v[6] = act_fast<ACT>(__uint_as_float(r[8 * j + 6]) + __uint_as_float(bq[2 * j + 1].z));
-                            v[7] = act_fast<ACT>(__uint_as_float(r[8 * j + 7]) + __uint_as_float(bq[2 * j + 1].w));
+                            bias_act2<ACT>(r[8 * j], r[8 * j + 1], bq[2 * j].x, bq[2 * j].y, v[0], v[1]);
+                            bias_act2<ACT>(r[8 * j + 2], r[8 * j + 3], bq[2 * j].z, bq[2 * j].w, v[2], v[3]);
+                            bias_act2<ACT>(r[8 * j + 4], r[8 * j + 5], bq[2 * j + 1].x, bq[2 * j + 1].y, v[4], v[5]);
+                            bias_act2<ACT>(r[8 * j + 6], r[8 * j + 7], bq[2 * j + 1].z, bq[2 * j + 1].w, v[6], v[7]);
                             if (gp) {
                                 float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
                                 if (nc + 8 * j < p.N) g0 = __ldg(reinterpret_cast<const float4*>(gp + nc) + 2 * j);

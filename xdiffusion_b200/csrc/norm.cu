@@ -4,6 +4,8 @@
 //   LayerNorm(no affine, eps) * (1+scale) + shift over fp32 token rows -> bf16 (score_networks/dit.py:16-17,46-51)
 // Statistics in fp32; 16-byte vector accesses; warp-shuffle / shared-memory reductions.
 #include "common.cuh"
+#include <stdio.h>
+#include "ptx.cuh"
 
 #include <cooperative_groups.h>
 
@@ -22,21 +24,40 @@ __device__ __forceinline__ void block_group_sums(const float (&s)[8], const floa
 #pragma unroll
     for (int k = 0; k < 8; ++k) { mine[k] = active ? s[k] : 0.f; mine[8 + k] = active ? q[k] : 0.f; }
     __syncthreads();
+    // stage 1: one thread per channel folds the ppb pixel slots (in place, into slot 0: a thread only touches its
+    // own channel's column); stage 2: one thread per group folds its cpg channels.  Serial depth ppb + cpg instead
+    // of ppb * cpg (measured 4-11 us of a 20 us kernel with the single-stage loop), same fixed order for every batch.
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float* t = scratch + (c >> 3) * 16 + (c & 7);
+        float cs = t[0], cq = t[8];
+        for (int po = 1; po < ppb; ++po) {
+            cs += t[po * V * 16];
+            cq += t[po * V * 16 + 8];
+        }
+        t[0] = cs;
+        t[8] = cq;
+    }
+    __syncthreads();
     const int cpg = C / G;
     if (threadIdx.x < G) {
         float gs = 0.f, gq = 0.f;
         for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-            const int j = c >> 3, k = c & 7;
-            for (int po = 0; po < ppb; ++po) {
-                const float* t = scratch + (po * V + j) * 16;
-                gs += t[k];
-                gq += t[8 + k];
-            }
+            const float* t = scratch + (c >> 3) * 16 + (c & 7);
+            gs += t[0];
+            gq += t[8];
         }
         part[2 * threadIdx.x] = gs;
         part[2 * threadIdx.x + 1] = gq;
     }
     __syncthreads();
+}
+// SiLU with one MUFU op: y * sigmoid(y) = 0.5 y (1 + tanh(0.5 y)).  The exp + rcp form needs two and made the apply
+// pass MUFU-bound (16 MUFU/clk/SM: 3.7 us for a 64 x 32 x 32 x 128 tensor).
+__device__ __forceinline__ float silu_fast(float y) {
+    const float h = 0.5f * y;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
 }
 // stats[sample][group] = (sum, sum of squares) accumulated with atomics from pixel slabs.
 // "sample" = P consecutive pixels (rows of C channels, stride ld).
@@ -116,7 +137,7 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float y = fmaf(f[k], coef[j * 8 + k], coef[C + j * 8 + k]);
-            f[k] = silu ? silu_f(y) : y;
+            f[k] = silu ? silu_fast(y) : y;
         }
         const bf16x8 hi = pack8(f);
         *reinterpret_cast<bf16x8*>(out + p * ldo + j * 8) = hi;
@@ -136,69 +157,90 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 // statistics are reduced across the cluster through distributed shared memory, and the slab is
 // normalised straight from shared memory -- one HBM/L2 read and one write per element, one launch
 // (the two-kernel path reads x twice and needs a memset + two launches).
-__global__ void __launch_bounds__(256)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ ss, long long ss_ld, int ss_div, float eps,
                 int silu, bf16* __restrict__ out, long long ldo, int slab_px) {
     pdl_prologue();
     extern __shared__ __align__(16) uint8_t smem_gn[];
+#ifdef XDB200_INSTRUMENT
+    long long tph[8]; int nph = 0;
+#define GN_MARK() do { tph[nph++] = clock64(); } while (0)
+#else
+#define GN_MARK() do { } while (0)
+#endif
+    GN_MARK();
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int sample = blockIdx.y;
-    __shared__ float scratch[256 * 16];
+    __shared__ float scratch[NT * 16];
     float* part = reinterpret_cast<float*>(smem_gn);            // [64][2] partial (sum, sumsq) of this CTA
     float* coef = part + 128;                                   // [2][C]
     uint4* slab = reinterpret_cast<uint4*>(coef + 2 * C);       // [slab_px][C/8]
     const int V = C >> 3;
     const int p0 = rank * slab_px, p1 = min(P, p0 + slab_px);
     const int nvec = max(0, p1 - p0) * V;
-    // pass 1: global -> smem, per-thread channel sums.  A thread always sees the same 8 channels when
-    // blockDim is a multiple of V; otherwise it accumulates per vector slot j below.
+    // pass 1: global -> smem with bulk async copies (one per pixel row, or 32 KB pieces when the rows are dense):
+    // the whole slab is in flight at once, which a register-staged loop of 256 threads cannot do (measured 1.5 TB/s
+    // on 32 x 32 x 128 samples, 0.9 TB/s on 32 x 32 x 384).  Then per-thread channel sums from shared memory; a
+    // thread always sees the same 8 channels (blockDim is a multiple of V for every supported C, or po >= ppb idles).
     const bf16* base = x + ((long long)sample * P + p0) * ld;
     const int cpg = C / G;
+    const int npx = max(0, p1 - p0);
+    __shared__ __align__(8) uint64_t slab_bar;
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&slab_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t bar = ptx::smem_u32(&slab_bar), dst = ptx::smem_u32(slab);
+        if (threadIdx.x == 0) ptx::mbar_arrive_expect_tx(&slab_bar, (uint32_t)npx * C * 2);
+        __syncwarp();
+        if (ld == C) {
+            const uint32_t bytes = (uint32_t)npx * C * 2, piece = 32768;
+            for (uint32_t off = threadIdx.x * piece; off < bytes; off += 32 * piece)
+                ptx::bulk_load(dst + off, reinterpret_cast<const char*>(base) + off, min(piece, bytes - off), bar);
+        } else {
+            for (int px = threadIdx.x; px < npx; px += 32)
+                ptx::bulk_load(dst + px * C * 2, base + (long long)px * ld, C * 2, bar);
+        }
+    }
+    ptx::mbar_wait(&slab_bar, 0);
+    GN_MARK();
     float s[8] = {}, q[8] = {};
-    const int ppb = 256 / V;                                    // pixels per block iteration
+    const int ppb = NT / V;                                     // pixels per block iteration
     const int j = threadIdx.x % V, po = threadIdx.x / V;
     if (po < ppb) {
-        const int npx = p1 - p0;
-        int px = po;
-        for (; px + 3 * ppb < npx; px += 4 * ppb) {                // four independent 16-byte loads in flight
-            uint4 u[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const uint4*>(base + (long long)(px + r * ppb) * ld + j * 8);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                slab[(px + r * ppb) * V + j] = u[r];
-                bf16x8 t; t.u = u[r];
-                float f[8];
-                unpack8(t, f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
-            }
-        }
-        for (; px < npx; px += ppb) {
-            const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)px * ld + j * 8);
-            slab[px * V + j] = u;
-            bf16x8 t; t.u = u;
+#pragma unroll 4
+        for (int px = po; px < npx; px += ppb) {
+            bf16x8 t; t.u = slab[px * V + j];
             float f[8];
             unpack8(t, f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
         }
     }
+    GN_MARK();
     block_group_sums(s, q, po < ppb, V, ppb, C, G, scratch, part);
+    GN_MARK();
     cluster.sync();                                             // all partials written (also a CTA barrier)
+    GN_MARK();
     // per-channel affine coefficients from the cluster-wide statistics (DSMEM reads)
     const float inv_cnt = 1.0f / ((float)P * (float)cpg);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        float sum = 0.f, sq = 0.f;
-        for (int r = 0; r < CS; ++r) {
-            const float* rp = cluster.map_shared_rank(part, r);
-            sum += rp[2 * g];
-            sq += rp[2 * g + 1];
+        float2 pr[8];                                           // all remote reads in flight, then a fixed-order sum
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            pr[r] = make_float2(0.f, 0.f);
+            if (r < CS) pr[r] = *reinterpret_cast<const float2*>(cluster.map_shared_rank(part, r) + 2 * g);
         }
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { sum += pr[r].x; sq += pr[r].y; }
         const float mean = sum * inv_cnt;
         const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -210,21 +252,38 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
         }
         coef[c] = a; coef[C + c] = b;
     }
+    GN_MARK();
     cluster.sync();                                             // coefs visible; nobody exits while peers read `part`
-    // pass 2: smem -> normalise -> global
+    GN_MARK();
+    // pass 2: smem -> normalise -> global.  Same (pixel slot, vector) decomposition as pass 1: the thread's 16
+    // coefficients live in registers and the loop has no integer division (the flat-index form spent ~800 cycles
+    // per 16-byte vector: i / V, i % V and 16 scalar coefficient loads).
     bf16* obase = out + ((long long)sample * P + p0) * ldo;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int jj = i % V, px = i / V;
-        bf16x8 t; t.u = slab[i];
-        float f[8];
-        unpack8(t, f);
+    if (po < ppb) {
+        float ca[8], cb[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float y = fmaf(f[k], coef[jj * 8 + k], coef[C + jj * 8 + k]);
-            f[k] = silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
+        for (int k = 0; k < 8; ++k) { ca[k] = coef[j * 8 + k]; cb[k] = coef[C + j * 8 + k]; }
+#pragma unroll 2
+        for (int px = po; px < npx; px += ppb) {
+            bf16x8 t; t.u = slab[px * V + j];
+            float f[8];
+            unpack8(t, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float y = fmaf(f[k], ca[k], cb[k]);
+                f[k] = silu ? silu_fast(y) : y;
+            }
+            *reinterpret_cast<bf16x8*>(obase + (long long)px * ldo + j * 8) = pack8(f);
         }
-        *reinterpret_cast<bf16x8*>(obase + (long long)px * ldo + jj * 8) = pack8(f);
     }
+#ifdef XDB200_INSTRUMENT
+    GN_MARK();
+    if (threadIdx.x == 0 && blockIdx.x == 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1))
+        printf("[gn prof] sample %d P=%d C=%d cs=%d: load %lld  sums %lld  blocksum %lld  csync %lld  coef %lld  csync %lld  apply %lld\n",
+               sample, P, C, CS, tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4],
+               tph[6] - tph[5], tph[7] - tph[6]);
+#endif
+#undef GN_MARK
 }
 
 // ----------------------------------------------------------------------------- LayerNorm + modulate
@@ -338,14 +397,21 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
     XD_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && nsamples > 0 && P > 0);
     const size_t fixed = (128 + 2 * (size_t)C) * sizeof(float);
     const size_t budget = 110 * 1024;                           // (+ 16 KB static scratch) covers 32x32x384 with 8 CTAs
+    // CTAs per sample: enough that a slab is ~16 KB (parallelism: the kernel is latency-bound, 13-17 us at one or two
+    // CTAs per sample), at least what fits the budget.  A function of (P, C) only, never of the batch size, so a
+    // sample's statistics are summed in the same order whatever batch it is part of.
     int cs = 1;
+    while (cs < 8 && (size_t)P * C * 2 > (size_t)cs * 16 * 1024 && P / (2 * cs) >= 4) cs *= 2;
     while (cs <= 8 && (size_t)((P + cs - 1) / cs) * C * 2 + fixed > budget) cs *= 2;
     if (cs > 8) return -1;
     const int slab_px = (P + cs - 1) / cs;
     const size_t smem = fixed + (size_t)slab_px * C * 2;
+    // big slabs (one CTA per SM) get 512 threads: twice the issue slots and loads in flight for the same smem
+    const bool wide = smem > 40 * 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gn_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
+            cudaFuncSetAttribute(gn_fused_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed (gn_fused)");
             return XD_ERR_CUDA;
         }
@@ -353,7 +419,7 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs, nsamples);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(wide ? 512 : 256);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[2];
@@ -365,8 +431,9 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = xd_pdl_enabled() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x, ld, P, C, groups, gamma, beta, scale_shift, ss_ld,
-                           ss_div > 0 ? ss_div : 1, eps, silu, (bf16*)out, ldo, slab_px) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, wide ? gn_fused_kernel<512> : gn_fused_kernel<256>, (const bf16*)x, ld, P, C, groups, gamma,
+                           beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu, (bf16*)out, ldo,
+                           slab_px) != cudaSuccess) {
         xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
         return XD_ERR_CUDA;
     }

@@ -80,6 +80,12 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst_smem, const CUtenso
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_smem), "r"(c0), "r"(c1)
         : "memory");
 }
+// plain (1-D) bulk copy global -> shared, completion counted on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_smem) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar_smem)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
