@@ -40,6 +40,16 @@ int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, long long lda2
                     int gate_rows, long long gate_ld, const void* residual, int res_dtype, long long res_ld,
                     void* out, int out_dtype, long long out_ld, int force_bn, void* stream);
 
+/* LayerNorm (no affine) + adaLN modulate fused into the A operand of the contraction:
+ *   out[m,n] = act( sum_k a[m,k] Wt[n,k] + bias[n] ),  a[m,:] = bf16( LN(x[m,:]) * (1 + scale[m / rows_per_mod]) + shift[m / rows_per_mod] )
+ * x fp32 [M, K] with K = 128, 256 or 384 (one row = one shared-memory A panel), N a multiple of 192, out bf16,
+ * act none or GELU-tanh.  Same numerics as xd_layernorm_modulate followed by xd_gemm_bf16_tc (bit-identical A operand).
+ * Replaces `modulate(norm1(x), shift_msa, scale_msa)` -> `attn.qkv` and `modulate(norm2(x), shift_mlp, scale_mlp)` ->
+ * `mlp.fc1` (+ GELU) of a DiT block (score_networks/dit.py:37-59). */
+int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* shift, const float* scale, long long mod_ld,
+                       int rows_per_mod, float eps, const void* Wt, long long ldw, int M, int N, int K,
+                       const float* bias, int act, void* out, long long out_ld, void* stream);
+
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC bf16 (pixel stride ldx), packed weights
  * Wp[Cout][9*C + Cs] (tap-major, then channel; then the optional 1x1 skip weights over Xs).
  * Replaces Conv2d 3x3 (layers/resnet.py:129,155-157; score_networks/unet.py:107-114) and Conv3d

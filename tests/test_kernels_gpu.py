@@ -109,6 +109,28 @@ def test_gemm_a_stationary(ops, bn, M, N, K, K2):
     assert rel_l2(out, ref) < 1e-5
 
 
+# LayerNorm + modulate fused into the A operand (xd_ln_gemm_bf16_tc) against the two-kernel path and fp32 torch.
+@pytest.mark.parametrize("M,N,D,rows,act", [(2048, 1152, 384, 16, 0), (300, 1536, 384, 4, 2), (40, 192, 256, 8, 0),
+                                             (20000, 384, 384, 16, 2), (4096, 576, 128, 256, 0)])
+def test_ln_gemm_fused(ops, M, N, D, rows, act, monkeypatch):
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).to(DEV)
+    nb = (M + rows - 1) // rows
+    mod = (torch.randn(nb, 3 * D, generator=g) * 0.3).to(DEV)
+    shift, scale = mod[:, :D], mod[:, 2 * D:]                     # strided views, like the adaLN chunks
+    w = bf(torch.randn(N, D, generator=g) / math.sqrt(D)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    monkeypatch.setattr(ops, "LN_GEMM_FUSED", True)
+    fused = ops.ln_linear(x, shift, scale, rows, w, bias, act=act)
+    monkeypatch.setattr(ops, "LN_GEMM_FUSED", False)
+    split = ops.ln_linear(x, shift, scale, rows, w, bias, act=act)
+    assert rel_l2(fused, split) < 1e-6                            # same operand bits, same K order
+    ln = F.layer_norm(x, (D,), eps=1e-6)
+    a = ln * (1 + scale.repeat_interleave(rows, 0)[:M]) + shift.repeat_interleave(rows, 0)[:M]
+    ref = _gemm_ref(bf(a), w, bias, act, None, 1, None)
+    assert rel_l2(fused, ref) < 4e-3
+
+
 def _pack_conv(w, wskip=None):
     """[Cout,C,3,3] -> [Cout, 9*C (+Cs)] tap-major (same packing as the product's weight repack)."""
     co, c = w.shape[:2]

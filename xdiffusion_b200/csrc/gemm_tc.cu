@@ -47,6 +47,13 @@ struct TcParams {
     int direct_ok;      // bf16 out rows are 16-byte aligned: registers can be stored without the transpose
     int debug;          // experiments only (XDB200_DEBUG): 1 = skip global stores, 2 = skip the MMAs
     int tma_epi;        // 1: TMA epilogue (bulk tensor load of the residual, bulk tensor store of the output)
+    // LNA kernels: the A operand is LayerNorm(x) * (1 + scale) + shift computed in the kernel from fp32 rows
+    const float* ln_x;
+    const float* ln_shift;
+    const float* ln_scale;
+    long long ln_ld, ln_mod_ld;
+    int ln_rows_per_mod;
+    float ln_eps;
     long long* prof;    // XDB200_PROF=1: per-CTA cycle counters (16 slots per CTA), nullptr otherwise
     int ng, tpg;        // work items: every m-tile is split into ng groups of tpg consecutive n-tiles
     Epilogue epi;
@@ -154,7 +161,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // 256 x BN tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one
 // M = 256 MMA that reads both CTAs' shared memory and writes both CTAs' TMEM -- half the shared-memory
 // and L2 operand traffic per FLOP, which is what bounds the 1-CTA kernel (see profiles/README.md).
-template <int BN, int ACT, int CG, bool AS, int EPI>
+template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
@@ -212,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_init(&tmem_empty_bar[b], EPI_WARPS * CG);
         }
         for (int k = 0; k < C::A_SLOTS; ++k) {
-            ptx::mbar_init(&a_full_bar[k], CG);
+            ptx::mbar_init(&a_full_bar[k], LNA ? EPI_WARPS * CG : CG);   // LNA: one arrive per transforming warp
             ptx::mbar_init(&a_empty_bar[k], 1);
         }
         ptx::fence_barrier_init();
@@ -252,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     h0 = (m0 - img * hw) / p.W;
                 }
                 for (int kb = 0; kb < nk; ++kb) {
-                    const bool load_a = !AS || nt == nt0;
+                    const bool load_a = !LNA && (!AS || nt == nt0);
                     uint64_t* bar_a = AS ? &a_full_bar[kb] : &full_bar[s];
                     uint8_t* sA = AS ? panel + kb * C::A_BYTES : smem + s * C::STAGE_BYTES;
                     uint8_t* sB = AS ? smem + s * C::STAGE_BYTES : sA + C::A_BYTES;
@@ -384,7 +391,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t wbuf_a = ptx::smem_u32(epi + e_warp * C::EPI_WARP_BYTES);
         const uint32_t bias_a = ptx::smem_u32(bias_sm + e_warp * 512);
         uint64_t* rbar = res_bar + 2 * e_warp;
-        XD_ITEM_LOOP { XD_ITEM_DECODE XD_TILE_LOOP {
+        XD_ITEM_LOOP { XD_ITEM_DECODE
+            if constexpr (LNA) {
+                // ---- fused LayerNorm + modulate: build this CTA's 128 x K panel of A in shared memory.
+                // MEASURED NOT PROFITABLE (profiles/README.md): the 8 epilogue warps need ~10 us for the 128 rows
+                // (~3600 instructions per warp at ~5 clk each, two warps per scheduler) while the stand-alone
+                // LayerNorm kernel takes 7.6 us on the whole machine; kept as an opt-in (XDB200_LN_FUSED=1) and tested.
+                // Each epilogue warp owns 16 rows; one row per warp at a time, lane <-> columns (i * 32 + lane) * 4
+                // (the decomposition and arithmetic of ln_modulate_kernel, norm.cu: bit-identical operand).
+                // The panel is free once the MMAs of the previous item have completed (a_empty, multicast commit).
+                const long long t_ln0 = prof ? clock64() : 0;
+                for (int kb = 0; kb < nk; ++kb) ptx::mbar_wait(&a_empty_bar[kb], (item & 1) ^ 1);
+                const int nv = nk >> 1;                                  // 128-column groups
+                const float Df = (float)(nk * BK);
+                const uint32_t panel_a = ptx::smem_u32(panel);
+                const int row0 = e_warp * 16;
+                // Eight rows per pass: all 24 row loads of the pass are issued before the first reduction, the eight
+                // reductions run as independent shuffle chains (one row at a time is latency-bound: 2500 clk per row).
+                // shift / scale are reloaded only when the modulation row changes (DiT: once per warp).
+                // All index arithmetic is 32-bit and hoisted per pass: the eight epilogue warps are latency-bound
+                // (two warps per scheduler), so the instruction count of this block is its cost.
+                float4 sc[3], sh[3];
+                int cur_mod = -1;
+                const int ldx = (int)p.ln_ld;
+                const unsigned rpm = (unsigned)p.ln_rows_per_mod;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int rbase = row0 + pass * 8;
+                    const int mb = mt * (BM * CG) + rank * BM + rbase;            // first global row of the pass
+                    const int valid = p.M - mb;                                   // rows rr < valid exist
+                    const float* xb = p.ln_x + (long long)mb * p.ln_ld + lane * 4;
+                    float4 v[8][3];
+                    float red[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            v[rr][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (i < nv && rr < valid) v[rr][i] = *reinterpret_cast<const float4*>(xb + rr * ldx + i * 128);
+                        }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) acc += v[rr][i].x + v[rr][i].y + v[rr][i].z + v[rr][i].w;
+                        red[rr] = acc;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) red[rr] += __shfl_xor_sync(0xffffffffu, red[rr], o);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const float mean = red[rr] / Df;
+                        float qacc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            if (i < nv) {
+                                v[rr][i].x -= mean; v[rr][i].y -= mean; v[rr][i].z -= mean; v[rr][i].w -= mean;
+                                qacc += v[rr][i].x * v[rr][i].x + v[rr][i].y * v[rr][i].y + v[rr][i].z * v[rr][i].z +
+                                        v[rr][i].w * v[rr][i].w;
+                            }
+                        }
+                        red[rr] = qacc;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) red[rr] += __shfl_xor_sync(0xffffffffu, red[rr], o);
+                    }
+                    const int m_last = p.M - 1;
+                    const int mod_first = (int)((unsigned)min(mb, m_last) / rpm);
+                    const bool mod_uniform = mod_first == (int)((unsigned)min(mb + 7, m_last) / rpm);
+                    // this lane's byte offset inside a 128-byte swizzled row, without the row XOR
+                    const uint32_t a_lane = panel_a + (lane >> 4) * C::A_BYTES + ((lane & 1) << 3);
+                    const uint32_t chunk = (lane & 15) >> 1;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = rbase + rr;                        // row inside the CTA's 128
+                        const float rstd = rsqrtf(red[rr] / Df + p.ln_eps);
+                        const int mod_row = mod_uniform ? mod_first : (int)((unsigned)min(mb + rr, m_last) / rpm);
+                        if (mod_row != cur_mod) {                        // warp-uniform; DiT: once per warp and item
+                            cur_mod = mod_row;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                sh[i] = sc[i];
+                                if (i < nv) {
+                                    const long long off = (long long)mod_row * p.ln_mod_ld + (i * 32 + lane) * 4;
+                                    if (p.ln_scale) sc[i] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + off));
+                                    if (p.ln_shift) sh[i] = __ldg(reinterpret_cast<const float4*>(p.ln_shift + off));
+                                }
+                            }
+                        }
+                        const bool live = rr < valid;
+                        const uint32_t a_row = a_lane + r * 128 + ((chunk ^ (r & 7)) << 4);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            if (i < nv) {
+                                const float y0 = fmaf(v[rr][i].x * rstd, 1.0f + sc[i].x, sh[i].x), y1 = fmaf(v[rr][i].y * rstd, 1.0f + sc[i].y, sh[i].y);
+                                const float y2 = fmaf(v[rr][i].z * rstd, 1.0f + sc[i].z, sh[i].z), y3 = fmaf(v[rr][i].w * rstd, 1.0f + sc[i].w, sh[i].w);
+                                // k-block 2 i + (lane >> 4)
+                                ptx::sts64(a_row + 2 * i * C::A_BYTES, live ? f2_to_bf2(y0, y1) : 0u, live ? f2_to_bf2(y2, y3) : 0u);
+                            }
+                        }
+                    }
+                }
+                ptx::fence_proxy_async();                                // generic-proxy writes -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) {
+                    for (int kb = 0; kb < nk; ++kb) {
+                        if constexpr (CG == 2) ptx::mbar_arrive_leader(&a_full_bar[kb]);
+                        else ptx::mbar_arrive(&a_full_bar[kb]);
+                    }
+                }
+                if (prof) w_res += clock64() - t_ln0;                    // reported in the "epi wait residual" slot
+            }
+            XD_TILE_LOOP {
             const int m0 = mt * (BM * CG) + rank * BM + q * 32;   // first row of this warp's 32-row band
             const int n0 = nt * BN;
             const uint32_t buf = it & 1;
@@ -803,11 +928,11 @@ int sm_count() {
     return n;
 }
 
-template <int BN, int ACT, int CG, bool AS, int EPI>
+template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& tr,
            const CUtensorMap& to, const TcParams& p, cudaStream_t st) {
     static bool configured = false;
-    auto kernel = gemm_tc_kernel<BN, ACT, CG, AS, EPI>;
+    auto kernel = gemm_tc_kernel<BN, ACT, CG, AS, EPI, LNA>;
     if (!configured) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, AS>::SMEM) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
@@ -1011,4 +1136,38 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     const long long ktot = 9LL * C + Cs;
     if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, t.bn / t.cg))) return rc;
     return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream);
+}
+
+// LayerNorm(no affine) + modulate fused into the A operand of the GEMM:
+//   out[m, n] = act( sum_k LNmod(x)[m, k] * Wt[n, k] + bias[n] ),  LNmod(x)[m, :] = LN(x[m, :]) * (1 + scale[m / rows]) + shift[m / rows]
+// x fp32 [M, K] (K = 128, 256 or 384: the whole row is one A panel), out bf16.  Replaces xd_layernorm_modulate followed by
+// xd_gemm_bf16_tc (reference: `modulate(norm(x), shift, scale)` then `nn.Linear`, score_networks/dit.py:37-59).
+extern "C" int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* shift, const float* scale, long long mod_ld,
+                                  int rows_per_mod, float eps, const void* Wt, long long ldw, int M, int N, int K,
+                                  const float* bias, int act, void* out, long long out_ld, void* stream) {
+    XD_CHECK_ARG(X && Wt && out && M > 0 && N > 0 && rows_per_mod > 0);
+    constexpr int kMaxKb = Cfg<192, 2, true>::A_SLOTS;
+    XD_CHECK_ARG(K % 128 == 0 && K / BK <= kMaxKb && N % 192 == 0);
+    XD_CHECK_ARG(ldx % 4 == 0 && mod_ld % 4 == 0 && ldw % 8 == 0 && out_ld % 8 == 0);
+    XD_CHECK_ARG(aligned16(X) && aligned16(shift) && aligned16(scale) && aligned16(Wt) && aligned16(out) && aligned16(bias));
+    TcParams p{};
+    p.M = M; p.N = N; p.nk0 = K / BK; p.nk1 = 0; p.conv = 0;
+    p.epi = Epilogue{bias, nullptr, nullptr, out, 0, 0, out_ld, act, 1, XD_BF16, XD_BF16};
+    p.vec_ok = 1; p.direct_ok = 1;
+    p.ln_x = X; p.ln_ld = ldx; p.ln_shift = shift; p.ln_scale = scale; p.ln_mod_ld = mod_ld;
+    p.ln_rows_per_mod = rows_per_mod; p.ln_eps = eps;
+    const TileChoice t{192, 2, 1};
+    set_items(&p, t);
+    CUtensorMap tb, tr, to;
+    int rc;
+    if ((rc = tmap_weights(&tb, Wt, N, K, ldw, 96))) return rc;
+    if ((rc = setup_epilogue(&p, &tr, &to))) return rc;
+    XD_CHECK_ARG(p.tma_epi);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (act) {
+        case XD_ACT_NONE: return launch<192, XD_ACT_NONE, 2, true, EPI_TMA_BF16, true>(tb, tb, tb, tr, to, p, st);
+        case XD_ACT_GELU_TANH: return launch<192, XD_ACT_GELU_TANH, 2, true, EPI_TMA_BF16, true>(tb, tb, tb, tr, to, p, st);
+    }
+    XD_CHECK_ARG(false && "xd_ln_gemm_bf16_tc: activation must be none or gelu_tanh");
+    return XD_ERR_ARG;
 }

@@ -21,13 +21,18 @@ class MultiHeadSelfAttention(torch.nn.Module, Packed):
         self.qkv = torch.nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = torch.nn.Linear(dim, dim)
 
-    def forward(self, x_bf16, tokens: int, **epilogue):
-        """x bf16 [B*T, D]; ``epilogue`` (gate / residual / out) is fused into the proj GEMM."""
+    def forward(self, x_bf16, tokens: int, ln=None, **epilogue):
+        """x bf16 [B*T, D]; ``epilogue`` (gate / residual / out) is fused into the proj GEMM.
+        ``ln=(shift, scale, rows_per_mod)``: x is the fp32 residual stream, LayerNorm + modulate is fused into qkv."""
         wq, wp = self.packed("w", (self.qkv.weight, self.proj.weight),
                              lambda: (bf16_weight(self.qkv.weight), bf16_weight(self.proj.weight)))
         M, D = x_bf16.shape
         B, H, d = M // tokens, self.num_heads, self.head_dim
-        qkv = ops.linear(x_bf16, wq, self.qkv.bias).view(B, tokens, 3, H, d)
+        if ln is not None:
+            qkv = ops.ln_linear(x_bf16, ln[0], ln[1], ln[2], wq, self.qkv.bias)
+        else:
+            qkv = ops.linear(x_bf16, wq, self.qkv.bias)
+        qkv = qkv.view(B, tokens, 3, H, d)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
         a = ops.attention(q, k, v, self.scale)                       # [B,H,T,d] view of [B,T,H*d]
         a2 = a.permute(0, 2, 1, 3).reshape(M, D)

@@ -67,6 +67,21 @@ def _op(schema):
 
 
 # ------------------------------------------------------------------------------------ contractions
+@_op("ln_gemm(Tensor x, Tensor? shift, Tensor? scale, int rows_per_mod, float eps, Tensor w, Tensor? bias, int act, "
+     "Tensor(a!) out) -> ()")
+def _ln_gemm(x, shift, scale, rows_per_mod, eps, w, bias, act, out):
+    _cuda(x, shift, scale, w, bias, out)
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.float32 and w.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and w.shape[1] == K
+    assert x.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1 and out.shape == (M, N)
+    mod = shift if shift is not None else scale
+    assert mod is None or (mod.stride(1) == 1 and (shift is None or scale is None or shift.stride(0) == scale.stride(0)))
+    _lib.check(_lib.lib().xd_ln_gemm_bf16_tc(_p(x), x.stride(0), _p(shift), _p(scale), 0 if mod is None else mod.stride(0),
+                                             rows_per_mod, eps, _p(w), w.stride(0), M, N, K, _p(bias), act, _p(out),
+                                             out.stride(0), _stream()), "xd_ln_gemm_bf16_tc")
+
+
 @_op("gemm(Tensor a, Tensor? a2, Tensor w, Tensor? bias, int act, Tensor? gate, int gate_rows, "
      "Tensor? residual, Tensor(a!) out, int force_bn) -> ()")
 def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):
@@ -345,6 +360,26 @@ def linear(a, w, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16, gate=None, g
         out = torch.empty((a.shape[0], w.shape[0]), device=a.device, dtype=out_dtype)
     _ops.gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn)
     return out
+
+
+# Off by default: measured slower than layernorm_modulate + linear (30.1 vs 24.0 us on the qkv shape, see
+# profiles/README.md); the kernel is kept as a tested opt-in.
+LN_GEMM_FUSED = os.environ.get("XDB200_LN_FUSED", "0") == "1"
+
+
+def ln_linear(x, shift, scale, rows_per_mod, w, bias=None, act=ACT_NONE, eps=1e-6, out=None):
+    """act(LNmod(x) @ w.T + bias) -> bf16: x fp32 [M, D], shift/scale fp32 [M / rows_per_mod, D].  One kernel when the
+    row fits a shared-memory A panel (D = 128/256/384, N % 192 == 0), else layernorm_modulate + linear."""
+    M, D = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    if (LN_GEMM_FUSED and MATMUL_BACKEND == "tc" and D in (128, 256, 384) and N % 192 == 0
+            and act in (ACT_NONE, ACT_GELU) and x.stride(0) % 4 == 0):
+        _ops.ln_gemm(x, shift, scale, rows_per_mod, eps, w, bias, act, out)
+        return out
+    a = layernorm_modulate(x, shift, scale, rows_per_mod, eps)
+    return linear(a, w, bias, act=act, out=out)
 
 
 def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, force_bn=0):

@@ -111,10 +111,9 @@ class DiT(torch.nn.Module, Packed):
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
-            a = ops.layernorm_modulate(h, s1, sc1, T)
-            blk.attn(a, T, gate=g1, gate_rows=T, residual=h, out=h)               # h += g1 * attn(...)
-            a = ops.layernorm_modulate(h, s2, sc2, T)
-            blk.mlp(a, gate=g2, gate_rows=T, residual=h, out=h)                   # h += g2 * mlp(...)
+            # LayerNorm + modulate is fused into the A operand of qkv / fc1 (xd_ln_gemm_bf16_tc)
+            blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))
+            blk.mlp(h, ln=(s2, sc2, T), gate=g2, gate_rows=T, residual=h, out=h)        # h += g2 * mlp(modulate(norm(h)))
         base = len(self.blocks) * 6 * D
         a = ops.layernorm_modulate(h, mod[:, base:base + D], mod[:, base + D:base + 2 * D], T)
         w_lin = self.packed("final", (self.final_layer.linear.weight,),
