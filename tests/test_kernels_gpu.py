@@ -251,6 +251,20 @@ def test_attention_layouts(ops):
     assert rel_l2(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("Tk", [8, 24, 77, 100, 128])
+def test_cross_attention_short_context(ops, Tk):
+    """16 queries x Tk keys on the warp-level mma.sync kernel (key blocks of 16, keys >= Tk masked), odd (batch, head) count."""
+    g = torch.Generator().manual_seed(Tk)
+    B, H = 3, 5
+    qq = bf(torch.randn(B, 16, H, 64, generator=g))
+    kv = bf(torch.randn(B, Tk, 2, H, 64, generator=g))
+    ref = ((qq.float().permute(0, 2, 1, 3) @ kv[:, :, 0].float().permute(0, 2, 3, 1)) * 0.125).softmax(-1) \
+        @ kv[:, :, 1].float().permute(0, 2, 1, 3)
+    kd = kv.to(DEV)
+    out = ops.attention(qq.to(DEV).permute(0, 2, 1, 3), kd[:, :, 0].permute(0, 2, 1, 3), kd[:, :, 1].permute(0, 2, 1, 3), 0.125)
+    assert rel_l2(out, ref) < 4e-3
+
+
 def test_attention_relative_position_scrambled(ops):
     """TemporalSelfAttention core incl. the reference's raw reshape (oracle.nets.relpos_attention)."""
     g = torch.Generator().manual_seed(21)

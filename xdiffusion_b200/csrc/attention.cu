@@ -384,6 +384,156 @@ attention_kernel(const AttnParams p) {
     if (active) store_row(p, b, h, row, o, 1.0f / l);
 }
 
+
+// ---- Tq == 16, Tk <= 16 * KT (cross-attention over a short context, e.g. PixArt: 16 latent tokens x 77 text tokens):
+// one warp per (batch, head), same mma.sync structure as above with KT key blocks; keys >= Tk are masked to -inf.
+// Replaces the generic SIMT kernel, which took 131 us per launch on the PixArt workload (46 % of its step).
+template <int KT>
+__global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(const AttnParams p) {
+    pdl_prologue();
+    constexpr int W = KT > 5 ? 1 : 2;                      // warps per CTA (48 KB of static shared memory)
+    __shared__ __align__(128) uint8_t sm[W][(1 + 2 * KT) * 2048];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bh = (long long)blockIdx.x * W + warp;
+    if (bh >= (long long)p.B * p.H) return;
+    const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+    uint8_t* sQ = sm[warp];
+    uint8_t* sK = sQ + 2048;
+    uint8_t* sV = sK + KT * 2048;
+    const bf16* qp = p.q + b * p.q_bs + h * p.q_hs;
+    const bf16* kp = p.k + b * p.k_bs + h * p.k_hs;
+    const bf16* vp = p.v + b * p.v_bs + h * p.v_hs;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    {   // Q and K: 4 + 4 KT chunks of 16 B per lane, all in flight; rows >= Tk are zero
+        uint4 rq[4], rk[4 * KT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            rq[i] = *reinterpret_cast<const uint4*>(qp + (long long)row * p.q_rs + c * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * KT; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            rk[i] = row < p.Tk ? *reinterpret_cast<const uint4*>(kp + (long long)row * p.k_rs + c * 8) : zero;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            *reinterpret_cast<uint4*>(sQ + row * 128 + ((c ^ (row & 7)) << 4)) = rq[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * KT; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            *reinterpret_cast<uint4*>(sK + row * 128 + ((c ^ (row & 7)) << 4)) = rk[i];
+        }
+    }
+    {
+        uint4 rv[4 * KT];
+#pragma unroll
+        for (int i = 0; i < 4 * KT; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            rv[i] = row < p.Tk ? *reinterpret_cast<const uint4*>(vp + (long long)row * p.v_rs + c * 8) : zero;
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * KT; ++i) {
+            const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
+            *reinterpret_cast<uint4*>(sV + row * 128 + ((c ^ (row & 7)) << 4)) = rv[i];
+        }
+    }
+    __syncwarp();
+    const uint32_t aQ = (uint32_t)__cvta_generic_to_shared(sQ), aK = (uint32_t)__cvta_generic_to_shared(sK),
+                   aV = (uint32_t)__cvta_generic_to_shared(sV);
+    // S = Q K^T: per key block two 8-key n-tiles, four 16-wide k-steps over d
+    float s[KT][2][4];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[kt][t][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        {
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8, c = 2 * ks + (lane >> 4);
+            ldsm_x4(aQ + row * 128 + ((c ^ (row & 7)) << 4), a0, a1, a2, a3);
+        }
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            uint32_t b0, b1, b2, b3;
+            const int row = kt * 16 + (lane & 7) + (lane >> 4) * 8, c = 2 * ks + ((lane >> 3) & 1);
+            ldsm_x4(aK + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
+            mma_bf16_16816(s[kt][0], a0, a1, a2, a3, b0, b1);
+            mma_bf16_16816(s[kt][1], a0, a1, a2, a3, b2, b3);
+        }
+    }
+    // mask keys >= Tk, softmax over rows r = lane/4 (elements 0, 1) and r + 8 (elements 2, 3); a row lives in one quad
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = kt * 16 + t * 8 + (lane & 3) * 2 + (j & 1);
+                if (key >= p.Tk) s[kt][t][j] = -INFINITY;
+                if (j < 2) m_lo = fmaxf(m_lo, s[kt][t][j]); else m_hi = fmaxf(m_hi, s[kt][t][j]);
+            }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    const float c = p.scale * 1.4426950408889634f;
+    float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            s[kt][t][0] = exp2f((s[kt][t][0] - m_lo) * c); s[kt][t][1] = exp2f((s[kt][t][1] - m_lo) * c);
+            s[kt][t][2] = exp2f((s[kt][t][2] - m_hi) * c); s[kt][t][3] = exp2f((s[kt][t][3] - m_hi) * c);
+            l_lo += s[kt][t][0] + s[kt][t][1];
+            l_hi += s[kt][t][2] + s[kt][t][3];
+        }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    // O = P V: KT k-steps of 16 keys, eight 8-wide n-tiles over d; V^T fragments via ldmatrix.trans
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const uint32_t pa0 = f2_to_bf2(s[kt][0][0], s[kt][0][1]), pa1 = f2_to_bf2(s[kt][0][2], s[kt][0][3]);
+        const uint32_t pa2 = f2_to_bf2(s[kt][1][0], s[kt][1][1]), pa3 = f2_to_bf2(s[kt][1][2], s[kt][1][3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt += 2) {
+            uint32_t b0, b1, b2, b3;
+            const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, cc = nt + (lane >> 4);
+            ldsm_x4_trans(aV + row * 128 + ((cc ^ (row & 7)) << 4), b0, b1, b2, b3);
+            mma_bf16_16816(o[nt], pa0, pa1, pa2, pa3, b0, b1);
+            mma_bf16_16816(o[nt + 1], pa0, pa1, pa2, pa3, b2, b3);
+        }
+    }
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+    __syncwarp();                                         // everyone is done reading sQ: reuse it for O
+    {
+        const int r = lane >> 2, q4 = (lane & 3) * 4;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(sQ + r * 128 + ((nt ^ (r & 7)) << 4) + q4) = f2_to_bf2(o[nt][0] * i_lo, o[nt][1] * i_lo);
+            *reinterpret_cast<uint32_t*>(sQ + (r + 8) * 128 + ((nt ^ ((r + 8) & 7)) << 4) + q4) =
+                f2_to_bf2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+        }
+    }
+    __syncwarp();
+    bf16* op = p.o + b * p.o_bs + h * p.o_hs;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i, row = idx >> 3, cch = idx & 7;
+        *reinterpret_cast<uint4*>(op + (long long)row * p.o_rs + cch * 8) =
+            *reinterpret_cast<const uint4*>(sQ + row * 128 + ((cch ^ (row & 7)) << 4));
+    }
+}
+
 }  // namespace
 
 int xd_attention_tc256_try(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
@@ -414,6 +564,18 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
     if (Tq == T16 && Tk == T16 && !relk && !scramble && !in_f32) { // warp-level tensor-core path
         const long long nb = ((long long)B * H + W16 - 1) / W16;
         if (xd_launch(attention16_mma_kernel, (unsigned)nb, 32 * W16, 0, (cudaStream_t)stream, p) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+            return XD_ERR_CUDA;
+        }
+        return XD_OK;
+    }
+    if (Tq == T16 && Tk <= 128 && !relk && !scramble && !in_f32) {  // short-context cross-attention (PixArt 16 x 77)
+        const long long nbh = (long long)B * H;
+        cudaError_t e;
+        if (Tk <= 32) e = xd_launch(attention16xn_mma_kernel<2>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);
+        else if (Tk <= 80) e = xd_launch(attention16xn_mma_kernel<5>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);
+        else e = xd_launch(attention16xn_mma_kernel<8>, (unsigned)nbh, 32, 0, (cudaStream_t)stream, p);
+        if (e != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
             return XD_ERR_CUDA;
         }

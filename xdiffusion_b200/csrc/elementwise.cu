@@ -47,6 +47,16 @@ __global__ void act_cast_kernel(const void* in, int in_dtype, void* out, int out
     else ((bf16*)out)[i] = __float2bfloat16_rn(v);
 }
 
+// fp32 -> bf16, 8 elements per thread (two 16-byte loads, one 16-byte store); n % 8 == 0, 16-byte aligned pointers
+__global__ void act_cast_f32_bf16_v8_kernel(const float4* __restrict__ in, uint4* __restrict__ out, int act, long long n8) {
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = in[2 * i], b = in[2 * i + 1];
+    out[i] = make_uint4(f2_to_bf2(apply_act(a.x, act), apply_act(a.y, act)), f2_to_bf2(apply_act(a.z, act), apply_act(a.w, act)),
+                        f2_to_bf2(apply_act(b.x, act), apply_act(b.y, act)), f2_to_bf2(apply_act(b.z, act), apply_act(b.w, act)));
+}
+
 // c = table[label] + temb ; optionally also silu(c) as bf16 (input of every adaLN GEMM)
 __global__ void class_combine_kernel(const float* __restrict__ table, const long long* __restrict__ labels,
                                      const float* __restrict__ temb, int B, int Dm, float* c_out, bf16* silu_out) {
@@ -99,6 +109,16 @@ __global__ void add_rows_periodic_kernel(const float* a, const float* b, long lo
     const int c = (int)(i % cols);
     out[i] = a[i] + b[(r % period) * cols + c];
 }
+// 16-byte version (cols % 4 == 0, 16-byte aligned pointers, < 2^32 vectors): 32-bit index arithmetic
+__global__ void add_rows_periodic_v4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, unsigned nvec,
+                                            unsigned cols4, unsigned period, float4* __restrict__ out) {
+    pdl_prologue();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const unsigned r = i / cols4, c = i - r * cols4;
+    const float4 x = a[i], y = __ldg(&b[(r % period) * cols4 + c]);
+    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
 
 // out[g, r, c] = a[r, c] + tab[g, c]    (PixArt adaLN-single: table(6*D) + t0, for all blocks at once)
 __global__ void add_table_kernel(const float* a, const float* tab, int G, int R, int Ccols, float* out) {
@@ -110,6 +130,18 @@ __global__ void add_table_kernel(const float* a, const float* tab, int G, int R,
     const int r = (int)((i / Ccols) % R);
     const int g = (int)(i / ((long long)Ccols * R));
     out[i] = a[(long long)r * Ccols + c] + tab[(long long)g * Ccols + c];
+}
+
+// 16-byte version of add_table (Ccols % 4 == 0, aligned pointers, < 2^32 vectors)
+__global__ void add_table_v4_kernel(const float4* __restrict__ a, const float4* __restrict__ tab, unsigned G, unsigned R,
+                                    unsigned C4, float4* __restrict__ out) {
+    pdl_prologue();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * R * C4) return;
+    const unsigned row = i / C4, c = i - row * C4;          // row = g * R + r
+    const unsigned g = row / R, r = row - g * R;
+    const float4 x = __ldg(&a[r * C4 + c]), t = __ldg(&tab[g * C4 + c]);
+    out[i] = make_float4(x.x + t.x, x.y + t.y, x.z + t.z, x.w + t.w);
 }
 
 // 2x2 average pool / nearest 2x upsample over NHWC bf16 (8 channels per thread)
@@ -198,7 +230,11 @@ extern "C" int xd_timestep_embed(const void* t, int t_is_i64, int B, const float
 extern "C" int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtype, int act, long long n,
                            void* stream) {
     XD_CHECK_ARG(in && out && n > 0);
-    xd_launch(act_cast_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, in, in_dtype, out, out_dtype, act, n);
+    if (in_dtype == XD_F32 && out_dtype == XD_BF16 && n % 8 == 0 &&
+        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+        xd_launch(act_cast_f32_bf16_v8_kernel, blocks_for(n / 8), 256, 0, (cudaStream_t)stream, (const float4*)in, (uint4*)out, act, n / 8);
+    else
+        xd_launch(act_cast_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, in, in_dtype, out, out_dtype, act, n);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
@@ -232,14 +268,27 @@ extern "C" int xd_unpatchify(const float* y, long long ldy, int B, int C, int H,
 extern "C" int xd_add_rows_periodic(const float* a, const float* b, long long rows, int cols, int period, float* out,
                                     void* stream) {
     XD_CHECK_ARG(a && b && out && period > 0);
-    xd_launch(add_rows_periodic_kernel, blocks_for(rows * cols), 256, 0, (cudaStream_t)stream, a, b, rows, cols, period, out);
+    const long long nvec = rows * cols / 4;
+    const bool v4 = cols % 4 == 0 && nvec < (1LL << 32) &&
+                    ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (v4)
+        xd_launch(add_rows_periodic_v4_kernel, blocks_for(nvec), 256, 0, (cudaStream_t)stream, (const float4*)a,
+                  (const float4*)b, (unsigned)nvec, (unsigned)(cols / 4), (unsigned)period, (float4*)out);
+    else
+        xd_launch(add_rows_periodic_kernel, blocks_for(rows * cols), 256, 0, (cudaStream_t)stream, a, b, rows, cols, period, out);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
 
 extern "C" int xd_add_table(const float* a, const float* tab, int G, int R, int C, float* out, void* stream) {
     XD_CHECK_ARG(a && tab && out);
-    xd_launch(add_table_kernel, blocks_for((long long)G * R * C), 256, 0, (cudaStream_t)stream, a, tab, G, R, C, out);
+    const long long nvec = (long long)G * R * C / 4;
+    if (C % 4 == 0 && nvec < (1LL << 32) &&
+        ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(tab) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+        xd_launch(add_table_v4_kernel, blocks_for(nvec), 256, 0, (cudaStream_t)stream, (const float4*)a, (const float4*)tab,
+                  (unsigned)G, (unsigned)R, (unsigned)(C / 4), (float4*)out);
+    else
+        xd_launch(add_table_kernel, blocks_for((long long)G * R * C), 256, 0, (cudaStream_t)stream, a, tab, G, R, C, out);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }
