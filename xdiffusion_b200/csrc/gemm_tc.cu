@@ -1021,11 +1021,23 @@ TileChoice pick_tile(int N, int M, int nk, int conv, int force) {
     const int cg = (mode != 1 && M >= 2 * BM) ? 2 : 1;
     const long long units = sm_count() / cg;
     const long long mt = (M + BM * cg - 1) / (BM * cg);
-    auto fills = [&](int w) { return mt * ((N + w - 1) / w) >= units; };   // at least one full wave
-    if (N % 192 == 0 && fills(192)) return {192, cg, 0};         // measured: 192 beats 256 when both divide N
-    if (N % 256 == 0 && fills(256)) return {256, cg, 0};
-    if (N > 1024 && fills(256)) return {256, cg, 0};
-    return {128, cg, 0};
+    // Widest tile is not always best and "fills one wave" is the wrong test (a 64 x 16 x 16 x 256 conv, M = 16384,
+    // N = 256: one wave of 64 pair tiles of 256 x 256 takes 19 us, two waves of 256 x 128 tiles 31 us).  Estimated
+    // cost = waves x tile width x rate penalty (128-wide MMAs run at ~2/3 of the 192/256 rate, 64-wide at ~1/2);
+    // ragged N is charged through the tile count.
+    int best = 128;
+    long long best_cost = -1, best_pad = 0;
+    const int widths[4] = {192, 256, 128, 64};
+    for (int i = 0; i < 4; ++i) {
+        const int w = widths[i];
+        const long long tiles = mt * ((N + w - 1) / w);
+        const long long waves = (tiles + units - 1) / units;
+        const long long cost = waves * w * (w == 128 ? 3 : (w == 64 ? 4 : 2));       // x2 to keep integers
+        const long long pad = (long long)((N + w - 1) / w) * w;                       // tie-break: fewer padded columns
+        if (cg == 2 && w == 64) continue;                                             // no 64-wide pair kernel
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && pad < best_pad)) { best = w; best_cost = cost; best_pad = pad; }
+    }
+    return {best, cg, 0};
 }
 
 // Work items for the A-stationary kernels: groups of consecutive n-tiles, as few groups as keep >= 3/4 of the
