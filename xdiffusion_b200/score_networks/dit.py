@@ -90,6 +90,13 @@ class DiT(torch.nn.Module, Packed):
         run_custom_initializers(self)
 
     # ------------------------------------------------------------------ kernels
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            object.__setattr__(self, "_side", st)
+        return st
+
     def _adaln(self):
         """All adaLN linears stacked: one [sum(6D..)+2D, D] GEMM per step instead of depth+1."""
         lins = [b.adaLN_modulation[1] for b in self.blocks] + [self.final_layer.adaLN_modulation[1]]
@@ -99,19 +106,28 @@ class DiT(torch.nn.Module, Packed):
 
     def forward(self, x, context: Dict):
         context = context.copy()
-        for ct in self._context_transformers:
-            context = ct(context, device=x.device)
-        c = context["timestep_embedding"]                              # fp32 [B, D]
         B, D, T = x.shape[0], self.hidden_size, self.x_embedder.num_patches
-        h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
-        silu_c = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
-        torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
         w_ada, b_ada = self._adaln()
-        mod = ops.linear(silu_c, w_ada, b_ada, out_dtype=torch.float32)           # [B, depth*6D + 2D]
+        # Two independent branches before the first block: (a) conditioning -> adaLN GEMM (~60 us of small kernels),
+        # (b) patch embedding.  (a) runs on a side stream (a fork/join in the captured graph); its outputs are
+        # allocated on the main stream so that the caching allocator never recycles them early.
+        main = torch.cuda.current_stream(x.device)
+        side = self._side_stream(x.device)
+        silu_c = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
+        mod = torch.empty((B, w_ada.shape[0]), device=x.device, dtype=torch.float32)    # [B, depth*6D + 2D]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for ct in self._context_transformers:
+                context = ct(context, device=x.device)
+            c = context["timestep_embedding"]                          # fp32 [B, D]
+            torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
+            ops.linear(silu_c, w_ada, b_ada, out=mod)
+        h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
+        main.wait_stream(side)
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
-            # LayerNorm + modulate is fused into the A operand of qkv / fc1 (xd_ln_gemm_bf16_tc)
+            # ln=: LayerNorm + modulate feeding qkv / fc1 (layernorm_modulate kernel; fused into the GEMM with XDB200_LN_FUSED=1)
             blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))
             blk.mlp(h, ln=(s2, sc2, T), gate=g2, gate_rows=T, residual=h, out=h)        # h += g2 * mlp(modulate(norm(h)))
         base = len(self.blocks) * 6 * D
