@@ -171,13 +171,16 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 #define GN_MARK() do { } while (0)
 #endif
     GN_MARK();
+    // "every CTA of the cluster has started" barrier, split: arrive here, wait just before the first DSMEM store
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int sample = blockIdx.y;
     __shared__ float scratch[NT * 16];
-    float* part = reinterpret_cast<float*>(smem_gn);            // [64][2] partial (sum, sumsq) of this CTA
-    float* coef = part + 128;                                   // [2][C]
+    float* all_part = reinterpret_cast<float*>(smem_gn);        // [8 ranks][64][2] partial (sum, sumsq) of every CTA
+    float* part = all_part + rank * 128;                        // this CTA's row
+    float* coef = all_part + 8 * 128;                           // [2][C]
     uint4* slab = reinterpret_cast<uint4*>(coef + 2 * C);       // [slab_px][C/8]
     const int V = C >> 3;
     const int p0 = rank * slab_px, p1 = min(P, p0 + slab_px);
@@ -226,21 +229,23 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
     GN_MARK();
     block_group_sums(s, q, po < ppb, V, ppb, C, G, scratch, part);
     GN_MARK();
-    cluster.sync();                                             // all partials written (also a CTA barrier)
+    // push this CTA's group partials into every peer's table (DSMEM stores), then ONE cluster barrier: afterwards all
+    // statistics are local, nobody touches a peer's shared memory any more, and a CTA may exit as soon as it is done
+    // (the pull version needed a second cluster barrier before exit).
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 2 * G) {
+        const float vme = part[threadIdx.x];
+        for (int r = 0; r < CS; ++r)
+            if (r != rank) cluster.map_shared_rank(all_part, r)[rank * 128 + threadIdx.x] = vme;
+    }
+    cluster.sync();
     GN_MARK();
-    // per-channel affine coefficients from the cluster-wide statistics (DSMEM reads)
+    // per-channel affine coefficients from the cluster-wide statistics (fixed-order sum over the ranks)
     const float inv_cnt = 1.0f / ((float)P * (float)cpg);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        float2 pr[8];                                           // all remote reads in flight, then a fixed-order sum
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            pr[r] = make_float2(0.f, 0.f);
-            if (r < CS) pr[r] = *reinterpret_cast<const float2*>(cluster.map_shared_rank(part, r) + 2 * g);
-        }
         float sum = 0.f, sq = 0.f;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) { sum += pr[r].x; sq += pr[r].y; }
+        for (int r = 0; r < CS; ++r) { sum += all_part[r * 128 + 2 * g]; sq += all_part[r * 128 + 2 * g + 1]; }
         const float mean = sum * inv_cnt;
         const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -253,7 +258,7 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
         coef[c] = a; coef[C + c] = b;
     }
     GN_MARK();
-    cluster.sync();                                             // coefs visible; nobody exits while peers read `part`
+    __syncthreads();                                            // coefs visible to the whole CTA
     GN_MARK();
     // pass 2: smem -> normalise -> global.  Same (pixel slot, vector) decomposition as pass 1: the thread's 16
     // coefficients live in registers and the loop has no integer division (the flat-index form spent ~800 cycles
@@ -395,7 +400,7 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
                                   int ss_div, float eps, int silu, void* out, long long ldo, void* stream) {
     XD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && groups <= 64 && C % groups == 0);
     XD_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0 && nsamples > 0 && P > 0);
-    const size_t fixed = (128 + 2 * (size_t)C) * sizeof(float);
+    const size_t fixed = (8 * 128 + 2 * (size_t)C) * sizeof(float);
     const size_t budget = 110 * 1024;                           // (+ 16 KB static scratch) covers 32x32x384 with 8 CTAs
     // CTAs per sample: enough that a slab is ~16 KB (parallelism: the kernel is latency-bound, 13-17 us at one or two
     // CTAs per sample), at least what fits the budget.  A function of (P, C) only, never of the batch size, so a
@@ -407,7 +412,7 @@ extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int
     const int slab_px = (P + cs - 1) / cs;
     const size_t smem = fixed + (size_t)slab_px * C * 2;
     // big slabs (one CTA per SM) get 512 threads: twice the issue slots and loads in flight for the same smem
-    const bool wide = smem > 40 * 1024;
+    const bool wide = (size_t)slab_px * C * 2 > 40 * 1024;       // the slab alone (one CTA per SM from ~48 KB)
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gn_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
