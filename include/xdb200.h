@@ -50,6 +50,14 @@ int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* shift, const 
                        int rows_per_mod, float eps, const void* Wt, long long ldw, int M, int N, int K,
                        const float* bias, int act, void* out, long long out_ld, void* stream);
 
+/* Scratch for split-K (fp32 partial tiles of long contractions over few output tiles, e.g. the 8x8 / 4x4 UNet convs).
+ * Device pointer, 16-byte aligned, caller-owned; launches that use it must be ordered on one stream.  Optional: without
+ * it every contraction runs unsplit. */
+int xd_set_workspace(void* ptr, long long bytes);
+/* Split-K makes the summation order (hence the low-order bits of a sample) depend on the batch size; 0 disables it and
+ * restores bit-exact batch independence.  Default: on (environment XDB200_SPLITK=0 turns it off). */
+int xd_set_split_k(int enabled);
+
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC bf16 (pixel stride ldx), packed weights
  * Wp[Cout][9*C + Cs] (tap-major, then channel; then the optional 1x1 skip weights over Xs).
  * Replaces Conv2d 3x3 (layers/resnet.py:129,155-157; score_networks/unet.py:107-114) and Conv3d

@@ -109,6 +109,24 @@ def test_gemm_a_stationary(ops, bn, M, N, K, K2):
     assert rel_l2(out, ref) < 1e-5
 
 
+# Split-K (few output tiles, long K): partial tiles in the workspace + reduce kernel, against the unsplit result.
+@pytest.mark.parametrize("M,N,K", [(256, 256, 4096), (512, 128, 2304), (100, 192, 8192)])
+def test_gemm_split_k(ops, M, N, K, monkeypatch):
+    g = torch.Generator().manual_seed(M + K)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = bf(torch.randn(M, N, generator=g)).to(DEV)
+    out = ops.linear(a, w, bias, act=ops.ACT_SILU, out_dtype=torch.bfloat16, residual=res)
+    ref = _gemm_ref(a, w, bias, 1, None, 1, res)
+    assert rel_l2(out, ref) < 3e-3
+    gate = torch.randn(M // 4, N, generator=g).to(DEV)
+    r32 = torch.randn(M, N, generator=g).to(DEV)
+    ref = _gemm_ref(a, w, bias, 0, gate, 4, r32)
+    out = ops.linear(a, w, bias, gate=gate, gate_rows=4, residual=r32, out=r32)
+    assert rel_l2(out, ref) < 1e-5
+
+
 # LayerNorm + modulate fused into the A operand (xd_ln_gemm_bf16_tc) against the two-kernel path and fp32 torch.
 @pytest.mark.parametrize("M,N,D,rows,act", [(2048, 1152, 384, 16, 0), (300, 1536, 384, 4, 2), (40, 192, 256, 8, 0),
                                              (20000, 384, 384, 16, 2), (4096, 576, 128, 256, 0)])

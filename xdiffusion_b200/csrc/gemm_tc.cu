@@ -55,6 +55,8 @@ struct TcParams {
     int ln_rows_per_mod;
     float ln_eps;
     long long* prof;    // XDB200_PROF=1: per-CTA cycle counters (16 slots per CTA), nullptr otherwise
+    int ksplit, kb_per_split, ws_rows;   // split-K: item = (tile, split); split s covers k-blocks [s * kb_per_split, ...) and
+                                         // stores its fp32 partial tile at rows s * ws_rows + m of the workspace (out)
     int ng, tpg;        // work items: every m-tile is split into ng groups of tpg consecutive n-tiles
     Epilogue epi;
 };
@@ -188,17 +190,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int dbg = kInst ? p.debug : 0;
     long long* pslot = prof ? p.prof + 16 * blockIdx.x : nullptr;
     if (prof && threadIdx.x == 0) pslot[8] = (long long)globaltimer_ns();
-    const int nk = p.nk0 + p.nk1;
+    const int nk_total = p.nk0 + p.nk1;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_items = p.ng * ((p.M + BM * CG - 1) / (BM * CG));
+    const int total_items = p.ng * ((p.M + BM * CG - 1) / (BM * CG)) * p.ksplit;
     const int rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;     // 0 = leader (issues the MMAs)
     const int first_item = blockIdx.x / CG, item_step = gridDim.x / CG;
 // work item w = (m-tile, group of tpg consecutive n-tiles); without AS every item is one tile (n fastest)
 #define XD_ITEM_LOOP for (int w_ = first_item; w_ < total_items; w_ += item_step, ++item)
-#define XD_ITEM_DECODE                                  \
-    const int mt = w_ / p.ng;                           \
-    const int nt0 = (w_ - mt * p.ng) * p.tpg;           \
-    const int nt1 = min(n_tiles, nt0 + p.tpg);
+#define XD_ITEM_DECODE                                                              \
+    const int sp = w_ % p.ksplit;                       /* split fastest: the splits of a tile run side by side */ \
+    const int w2_ = w_ / p.ksplit;                                                  \
+    const int mt = w2_ / p.ng;                                                      \
+    const int nt0 = (w2_ - mt * p.ng) * p.tpg;                                      \
+    const int nt1 = min(n_tiles, nt0 + p.tpg);                                      \
+    const int kb0 = sp * p.kb_per_split;                                            \
+    const int nk = min(p.kb_per_split, nk_total - kb0);
 #define XD_TILE_LOOP for (int nt = nt0; nt < nt1; ++nt, ++it)
 
     if (warp == 0 && lane == 0) {
@@ -267,17 +273,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     wait_acc(&empty_bar[s], ph ^ 1, prof, w_empty);
                     const CUtensorMap* tm = &tmA0;
                     int c0, c1, c2, c3;
-                    if (kb < p.nk0) {
+                    const int kg = kb0 + kb;                     // k-block index in the whole contraction
+                    if (kg < p.nk0) {
                         if (!p.conv) {
-                            c0 = kb * BK; c1 = m0; c2 = 0; c3 = 0;
+                            c0 = kg * BK; c1 = m0; c2 = 0; c3 = 0;
                         } else {
-                            const int tap = kb / p.cpb;
-                            const int cc = kb - tap * p.cpb;
+                            const int tap = kg / p.cpb;
+                            const int cc = kg - tap * p.cpb;
                             c0 = cc * BK; c1 = tap % 3 - 1; c2 = h0 + tap / 3 - 1; c3 = img;
                         }
                     } else {
                         tm = &tmA1;
-                        const int k1 = kb - p.nk0;
+                        const int k1 = kg - p.nk0;
                         if (!p.conv) { c0 = k1 * BK; c1 = m0; c2 = 0; c3 = 0; }
                         else { c0 = k1 * BK; c1 = 0; c2 = h0; c3 = img; }
                     }
@@ -300,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             ptx::mbar_arrive_expect_tx_leader(&full_bar[s], C::STAGE_BYTES);
                             ptx::tma_load_4d_2sm(sA, tm, bar_a, c0, c1, c2, c3);
                         }
-                        ptx::tma_load_2d_2sm(sB, &tmB, &full_bar[s], kb * BK, n0);
+                        ptx::tma_load_2d_2sm(sB, &tmB, &full_bar[s], kg * BK, n0);
                     } else {
                         if constexpr (AS) {
                             if (load_a) {
@@ -312,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
                             ptx::tma_load_4d(sA, tm, bar_a, c0, c1, c2, c3);
                         }
-                        ptx::tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                        ptx::tma_load_2d(sB, &tmB, &full_bar[s], kg * BK, n0);
                     }
                     if (++s == C::STAGES) { s = 0; ph ^= 1; }
                 }
@@ -655,7 +662,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (dbg != 1) ptx::tma_store_2d(&tmOut, wb, nc, m0);
+                        if (dbg != 1) ptx::tma_store_2d(&tmOut, wb, nc, m0 + sp * p.ws_rows);
                         ptx::bulk_commit();
                     }
                     if (prof) { const long long t = clock64(); seg[3] += t - tA; tA = t; }     // proxy fence + store issue
@@ -813,6 +820,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (prof && threadIdx.x == 0) pslot[9] = (long long)globaltimer_ns();
 }
 
+// Split-K second pass: out = epilogue( sum_s partial[s] ) over fp32 partial tiles, summed in split order (deterministic).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int S, long long split_stride, int M, int N, const Epilogue e) {
+    pdl_prologue();
+    const int n4 = N >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)M * n4) return;
+    const int m = (int)(i / n4), c = (int)(i - (long long)m * n4) * 4;
+    const float* src = ws + (long long)m * N + c;
+    float4 v = *reinterpret_cast<const float4*>(src);
+    for (int sidx = 1; sidx < S; ++sidx) {
+        const float4 t = *reinterpret_cast<const float4*>(src + sidx * split_stride);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    if (e.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    v.x = apply_act(v.x, e.act); v.y = apply_act(v.y, e.act); v.z = apply_act(v.z, e.act); v.w = apply_act(v.w, e.act);
+    if (e.gate) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + (long long)(m / e.gate_rows) * e.gate_ld + c));
+        v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    if (e.residual) {
+        if (e.res_dtype == XD_F32) {
+            const float4 r = *reinterpret_cast<const float4*>((const float*)e.residual + (long long)m * e.res_ld + c);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        } else {
+            const uint2 u = *reinterpret_cast<const uint2*>((const bf16*)e.residual + (long long)m * e.res_ld + c);
+            const float2 lo = bf2_to_f2(u.x), hi = bf2_to_f2(u.y);
+            v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+        }
+    }
+    if (e.out_dtype == XD_F32) *reinterpret_cast<float4*>((float*)e.out + (long long)m * e.out_ld + c) = v;
+    else *reinterpret_cast<uint2*>((bf16*)e.out + (long long)m * e.out_ld + c) = make_uint2(f2_to_bf2(v.x, v.y), f2_to_bf2(v.z, v.w));
+}
+
+// scratch for split-K partial tiles, provided by the caller (xd_set_workspace); none -> no split-K
+void* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+int g_split_k = -1;      // -1: XDB200_SPLITK (default on), 0 / 1: set by xd_set_split_k
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -940,7 +989,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         }
         configured = true;
     }
-    const long long items = (long long)p.ng * ((p.M + BM * CG - 1) / (BM * CG));
+    const long long items = (long long)p.ng * ((p.M + BM * CG - 1) / (BM * CG)) * p.ksplit;
     // persistent: <= one CTA (pair) per SM (pair)
     const unsigned grid = (unsigned)std::min<long long>(items, sm_count() / CG) * CG;
     cudaLaunchConfig_t cfg{};
@@ -1043,6 +1092,7 @@ TileChoice pick_tile(int N, int M, int nk, int conv, int force) {
 // Work items for the A-stationary kernels: groups of consecutive n-tiles, as few groups as keep >= 3/4 of the
 // CTAs (pairs) busy.  Without AS every tile is its own item.
 void set_items(TcParams* p, const TileChoice& t) {
+    p->ksplit = 1; p->kb_per_split = p->nk0 + p->nk1; p->ws_rows = 0;
     const int n_tiles = (p->N + t.bn - 1) / t.bn;
     if (!t.as) { p->ng = n_tiles; p->tpg = 1; return; }
     const long long m_tiles = (p->M + BM * t.cg - 1) / (BM * t.cg);
@@ -1055,19 +1105,59 @@ void set_items(TcParams* p, const TileChoice& t) {
 
 int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
              cudaStream_t st) {
+    set_items(&p, t);
+    // Split-K: long contractions over few tiles (the 8x8 / 4x4 UNet convs: 16-32 tiles, K = 2304-9216) are bound by
+    // the per-CTA TMA -> MMA round trip (~370 ns per k-block), not by the tensor pipe: S CTAs share a tile's K range,
+    // write fp32 partial tiles to the workspace and a second small kernel applies the epilogue to their sum.
+    static const int split_env = getenv("XDB200_SPLITK") ? atoi(getenv("XDB200_SPLITK")) : 1;
+    const int split_mode = g_split_k >= 0 ? g_split_k : split_env;
+    const Epilogue e_final = p.epi;
+    int S = 1;
+    const int nk_total = p.nk0 + p.nk1;
+    const long long m_tiles_cg = (p.M + BM * t.cg - 1) / (BM * t.cg);
+    if (split_mode && !t.as && g_ws) {
+        const long long tiles = m_tiles_cg * ((p.N + t.bn - 1) / t.bn), units = sm_count() / t.cg;
+        if (tiles * 2 <= units && nk_total >= 16) {
+            long long want = std::min<long long>(std::min<long long>(units / tiles, nk_total / 8), 8);
+            if (want >= 2) {
+                const int per = (int)((nk_total + want - 1) / want);
+                const int splits = (nk_total + per - 1) / per;
+                const long long mpad = m_tiles_cg * BM * t.cg;
+                if (splits >= 2 && (size_t)splits * mpad * p.N * sizeof(float) <= g_ws_bytes && mpad * splits < (1LL << 31)) {
+                    S = splits;
+                    p.ksplit = splits; p.kb_per_split = per; p.ws_rows = (int)mpad;
+                    p.epi = Epilogue{nullptr, nullptr, nullptr, g_ws, 0, 0, p.N, XD_ACT_NONE, 1, XD_F32, XD_F32};
+                }
+            }
+        }
+    }
     CUtensorMap tr, to;
     if (int rc = setup_epilogue(&p, &tr, &to)) return rc;
+    if (S > 1) {
+        if (!p.tma_epi) { xd_set_error(__FILE__, __LINE__, "split-K needs the TMA epilogue"); return XD_ERR_ARG; }
+        if (int rc = tmap_epi(&to, g_ws, (long long)S * p.ws_rows, p.N, p.N, true)) return rc;
+        tr = to;
+    }
+    auto finish = [&](int rc) -> int {
+        if (rc != XD_OK || S == 1) return rc;
+        const long long n4 = (long long)p.M * (p.N / 4);
+        if (xd_launch(splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, (const float*)g_ws, S,
+                      (long long)p.ws_rows * p.N, p.M, p.N, e_final) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+            return XD_ERR_CUDA;
+        }
+        return XD_OK;
+    };
     if (t.as && p.nk0 + p.nk1 > Cfg<192, 1, true>::A_SLOTS) {
         xd_set_error(__FILE__, __LINE__, "A-stationary tile needs K <= 384");
         return XD_ERR_ARG;
     }
-    set_items(&p, t);
     const int epi = p.tma_epi ? (p.epi.out_dtype == XD_F32 ? EPI_TMA_F32 : EPI_TMA_BF16) : EPI_LEGACY;
 #define XD_TC_ACT(BN_, CG_, AS_, EPI_)                                                                     \
     switch (p.epi.act) {                                                                                   \
-        case XD_ACT_NONE: return launch<BN_, XD_ACT_NONE, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st);       \
-        case XD_ACT_SILU: return launch<BN_, XD_ACT_SILU, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st);       \
-        case XD_ACT_GELU_TANH: return launch<BN_, XD_ACT_GELU_TANH, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st); \
+        case XD_ACT_NONE: return finish(launch<BN_, XD_ACT_NONE, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st));       \
+        case XD_ACT_SILU: return finish(launch<BN_, XD_ACT_SILU, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st));       \
+        case XD_ACT_GELU_TANH: return finish(launch<BN_, XD_ACT_GELU_TANH, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st)); \
     }
 #define XD_TC_CASE(BN_, CG_, AS_)                                                  \
     if (t.bn == BN_ && t.cg == CG_ && (t.as != 0) == AS_) {                        \
@@ -1182,4 +1272,21 @@ extern "C" int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* sh
     }
     XD_CHECK_ARG(false && "xd_ln_gemm_bf16_tc: activation must be none or gelu_tanh");
     return XD_ERR_ARG;
+}
+
+// Scratch memory for split-K partial tiles (device pointer, 16-byte aligned).  Launches that use it must be ordered on
+// one stream.  Without a workspace (or with too small a one) the contraction runs unsplit.
+extern "C" int xd_set_workspace(void* ptr, long long bytes) {
+    XD_CHECK_ARG((ptr == nullptr) == (bytes == 0) && bytes >= 0 && aligned16(ptr));
+    g_ws = ptr;
+    g_ws_bytes = (size_t)bytes;
+    return XD_OK;
+}
+
+// Split-K changes the summation order of a contraction with the number of output tiles, i.e. with the batch size: the
+// low-order bits of a sample then depend on the batch it is computed in.  xd_set_split_k(0) restores bit-exact batch
+// independence (sub-batches / ragged multi-GPU shards reproduce the same rows) at the cost of the split-K speed-up.
+extern "C" int xd_set_split_k(int enabled) {
+    g_split_k = enabled ? 1 : 0;
+    return XD_OK;
 }

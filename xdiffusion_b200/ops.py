@@ -44,6 +44,25 @@ def _cuda(*ts):
             raise _lib.XdError("xdb200 ops take CUDA tensors only (no CPU fallback)")
 
 
+# Split-K scratch (fp32 partial tiles of long contractions over few tiles): one caller-owned buffer per process,
+# registered with the library once per device; all GEMM / conv launches of a model run on one stream.
+WORKSPACE_BYTES = int(os.environ.get("XDB200_WORKSPACE_MB", "64")) << 20
+_workspace = {}
+
+
+def _ensure_workspace(t):
+    dev = t.device
+    if _workspace.get("device") != dev:
+        buf = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=dev) if WORKSPACE_BYTES else None
+        _lib.check(_lib.lib().xd_set_workspace(_p(buf), WORKSPACE_BYTES), "xd_set_workspace")
+        _workspace["device"], _workspace["buf"] = dev, buf
+
+
+def set_split_k(enabled: bool):
+    """Split-K for long contractions over few tiles (default on).  Off = bit-exact batch independence."""
+    _lib.check(_lib.lib().xd_set_split_k(int(bool(enabled))), "xd_set_split_k")
+
+
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n
@@ -86,6 +105,7 @@ def _ln_gemm(x, shift, scale, rows_per_mod, eps, w, bias, act, out):
      "Tensor? residual, Tensor(a!) out, int force_bn) -> ()")
 def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):
     _cuda(a, a2, w, bias, gate, residual, out)
+    _ensure_workspace(a)
     M, K = a.shape
     K2 = 0 if a2 is None else a2.shape[1]
     N = w.shape[0]
@@ -107,6 +127,7 @@ def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):
 def _conv3x3(x, xs, wp, bias, act, residual, out, force_bn):
     """x [nimg,H,W,C] bf16 NHWC view (channel stride 1, dense pixels, pixel stride >= C)."""
     _cuda(x, xs, wp, bias, residual, out)
+    _ensure_workspace(x)
     nimg, H, W, C = x.shape
     Cs = 0 if xs is None else xs.shape[3]
     Cout = wp.shape[0]
