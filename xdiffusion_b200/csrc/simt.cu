@@ -3,6 +3,7 @@
 // take: K % 64 != 0), (b) the UNet's first conv (C_in tiny, fp32 NCHW in) and last conv
 // (C_out tiny, fp32 NCHW out), which are bandwidth-bound and not GEMM-shaped.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -91,16 +92,16 @@ conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin, int H, int W, 
     pdl_prologue();
     extern __shared__ __align__(16) float ws_in[];          // [Cin * 9][Cout] + [Cout]
     float* bs = ws_in + Cin * 9 * Cout;
-    for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
-        const int co = i / (Cin * 9), r = i - co * (Cin * 9);   // w[co][c][tap], r = c * 9 + tap
-        ws_in[r * Cout + co] = w[i];
+    for (int d = threadIdx.x; d < Cout * Cin * 9; d += blockDim.x) {       // d = r * Cout + co: conflict-free smem writes
+        const int r = d / Cout, co = d - r * Cout;                          // w[co][c][tap], r = c * 9 + tap
+        ws_in[d] = __ldg(w + co * (Cin * 9) + r);
     }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const int cg = Cout / 8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)nimg * H * W * cg;
-    if (idx >= total) return;
+    // grid-stride: the weights are staged once per block, not once per 256 outputs
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % cg);
     const long long m = idx / cg;
     const int ww = (int)(m % W), hh = (int)((m / W) % H);
@@ -122,6 +123,7 @@ conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin, int H, int W, 
         }
     }
     *reinterpret_cast<bf16x8*>(out + m * ldo + g * 8) = pack8(acc);
+    }
 }
 
 // Last conv: bf16 NHWC (C % 8 == 0, C / 8 a power of two <= 32) -> fp32 NCHW, Cout tiny.  C / 8 lanes per output
@@ -134,14 +136,15 @@ conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, i
                    float* __restrict__ out) {
     pdl_prologue();
     extern __shared__ __align__(16) float ws_out[];         // [Cout][9][C]
-    for (int i = threadIdx.x; i < Cout * C * 9; i += blockDim.x) {
-        const int co = i / (C * 9), r = i - co * (C * 9), c = r / 9, tap = r - c * 9;
-        ws_out[(co * 9 + tap) * C + c] = w[i];
+    for (int d = threadIdx.x; d < Cout * C * 9; d += blockDim.x) {          // d = (co * 9 + tap) * C + c: conflict-free writes
+        const int c = d % C, t2 = d / C, tap = t2 % 9, co = t2 / 9;
+        ws_out[d] = __ldg(w + ((long long)co * C + c) * 9 + tap);
     }
     __syncthreads();
     const int lpp = C >> 3;                                  // lanes per pixel
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)nimg * H * W;
+    const long long nthreads = (total * lpp + 31) / 32 * 32;                 // whole warps stay in the loop together
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nthreads; idx += (long long)gridDim.x * blockDim.x) {
     const long long pix = idx / lpp;
     const int g = (int)(idx - pix * lpp);
     const bool live = pix < total;
@@ -163,6 +166,7 @@ conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, i
         }
         for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (g == 0 && live) out[((img * Cout + co) * H + hh) * W + ww] = acc + (bias ? bias[co] : 0.f);
+    }
     }
 }
 
@@ -201,7 +205,7 @@ extern "C" int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, 
     const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
     XD_CHECK_ARG(smem <= 48 * 1024);
     const long long total = (long long)nimg * H * W * (Cout / 8);
-    xd_launch(conv3x3_in_kernel, (unsigned)((total + 255) / 256), 256, smem, (cudaStream_t)stream, x, nimg, Cin, H, W, w, bias,
+    xd_launch(conv3x3_in_kernel, (unsigned)std::min<long long>((total + 255) / 256, 148 * 8), 256, smem, (cudaStream_t)stream, x, nimg, Cin, H, W, w, bias,
                                                                                         Cout, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
@@ -215,7 +219,7 @@ extern "C" int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, i
     const size_t smem = (size_t)Cout * 9 * C * sizeof(float);
     XD_CHECK_ARG(smem <= 48 * 1024);
     const long long threads = (long long)nimg * H * W * lpp;
-    xd_launch(conv3x3_out_kernel, (unsigned)((threads + 255) / 256), 256, smem, (cudaStream_t)stream, 
+    xd_launch(conv3x3_out_kernel, (unsigned)std::min<long long>((threads + 255) / 256, 148 * 8), 256, smem, (cudaStream_t)stream, 
         (const bf16*)X, ldx, nimg, H, W, C, w, bias, Cout, out);
     XD_CHECK_LAUNCH();
     return XD_OK;
