@@ -2,23 +2,29 @@
 //
 //   D[m, n] = sum_k A[m, k] * Wt[n, k]            (A bf16 row-major, Wt bf16 [N, K] row-major)
 //
-// Persistent kernel: one CTA per SM loops over 128 x BN output tiles (n fastest, so concurrently
-// running CTAs share A tiles and all of Wt through L2).  Warp roles (320 threads):
-//   warp 0      TMA producer: per 64-wide k-block one A box (128 rows x 128 B) and one B box
-//               (BN rows x 128 B) into a STAGES-deep ring (128-byte swizzle, mbarrier complete_tx);
-//               the ring runs ahead across tile boundaries
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 UMMA K=16 steps per k-block)
-//               into one of TWO TMEM accumulators, so tile i+1 is computed while tile i drains
-//   warps 2..9  epilogue, two warps per TMEM lane quadrant (each takes half of the columns):
-//               tcgen05.ld 32x32b.x32 -> +bias, activation in registers -> per-warp padded smem
-//               transpose -> row-contiguous 16-byte global accesses for gate / residual / output
-// The epilogue never touches local memory and every global access is a full 128-byte (fp32) or
-// 64-byte (bf16) row segment per 8 lanes.
+// Persistent kernel gemm_tc_kernel<BN, ACT, CG, AS, EPI, LNA>: one CTA per SM (CG = 1) or one CTA pair per SM pair
+// (CG = 2, tcgen05 cta_group::2, 256 x BN tiles) loops over output tiles, n fastest (concurrently running CTAs share A
+// tiles and all of Wt through L2).  Warp roles (320 threads):
+//   warp 0      TMA producer: per 64-wide k-block one A box (128 rows x 128 B) and one B box (BN / CG rows x 128 B)
+//               into a STAGES-deep ring (128-byte swizzle, mbarrier complete_tx); the ring runs ahead across tiles
+//   warp 1      TMEM allocator + MMA issuer (warp-uniform loop, one elected lane; 4 UMMA K = 16 steps per k-block)
+//               into one of TWO TMEM accumulators, so tile i + 1 is computed while tile i drains
+//   warps 2..9  epilogue, two warps per TMEM lane quadrant (each takes half of the columns), 32-column chunks with
+//               double-buffered tcgen05.ld.  EPI_TMA_F32 / EPI_TMA_BF16 (default): work in the TMEM-native layout
+//               (lane = row), residual box in by bulk tensor load, result out by bulk tensor store, bias slice staged in
+//               shared memory, no predicates (TMA clips the edges).  EPI_LEGACY: register epilogue with a padded
+//               shared-memory transpose and 16-byte global accesses (unaligned rows, mixed residual dtype).
+// Options: AS = A-stationary work items (the 128 x K panel of A stays in shared memory across the n-tiles of an item),
+// LNA = the epilogue warps build that panel as LayerNorm(x) * (1 + scale) + shift from fp32 rows, split-K (host side:
+// fp32 partial tiles to a workspace + splitk_reduce_kernel), programmatic dependent launch.
 //
 // Implicit conv3x3 (NHWC, pad 1): the A operand of k-block (tap, 64-channel chunk) is a 4-D TMA
 // box (64 ch, W, TH rows, TN images) of the activation tensor shifted by the tap offset; TMA's
 // out-of-bounds zero fill *is* the padding.  An optional second A segment (1x1, no shift) lets a
 // resblock's skip projection accumulate into the same TMEM tile (K = 9*C + Cskip).
+//
+// What bounds it (profiles/README.md): ~5 us fixed per launch; the K-loop is limited by operand delivery (TMA sustains
+// ~64 B/clk/SM, tcgen05.mma operand reads share the 128 B/clk shared-memory port), not by the tensor pipe.
 #include "common.cuh"
 #include "ptx.cuh"
 
