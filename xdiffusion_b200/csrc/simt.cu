@@ -111,11 +111,17 @@ conv3x3_in_kernel(const float* __restrict__ x, int nimg, int Cin, int H, int W, 
     for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
     for (int c = 0; c < Cin; ++c) {
         const float* xp = x + (img * Cin + c) * H * W;
+        float xv[9];                                       // all nine taps in flight (clamped address, masked value)
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
-            if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
-            const float v = __ldg(xp + y * W + xx);
+            const bool ok = y >= 0 && y < H && xx >= 0 && xx < W;
+            const float t = __ldg(xp + min(max(y, 0), H - 1) * W + min(max(xx, 0), W - 1));
+            xv[tap] = ok ? t : 0.f;
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float v = xv[tap];
             const float4 w0 = *reinterpret_cast<const float4*>(ws_in + (c * 9 + tap) * Cout + g * 8);
             const float4 w1 = *reinterpret_cast<const float4*>(ws_in + (c * 9 + tap) * Cout + g * 8 + 4);
             acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
@@ -153,12 +159,18 @@ conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, i
     const long long img = pc / ((long long)W * H);
     for (int co = 0; co < Cout; ++co) {
         float acc = 0.f;
+        bf16x8 xt[9];                                      // all nine taps in flight (clamped address, masked value)
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = min(max(hh + tap / 3 - 1, 0), H - 1), xx = min(max(ww + tap % 3 - 1, 0), W - 1);
+            xt[tap] = *reinterpret_cast<const bf16x8*>(X + ((img * H + y) * W + xx) * ldx + g * 8);
+        }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
             if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(X + ((img * H + y) * W + xx) * ldx + g * 8), f);
+            unpack8(xt[tap], f);
             const float4 w0 = *reinterpret_cast<const float4*>(ws_out + (co * 9 + tap) * C + g * 8);
             const float4 w1 = *reinterpret_cast<const float4*>(ws_out + (co * 9 + tap) * C + g * 8 + 4);
             acc = fmaf(f[0], w0.x, acc); acc = fmaf(f[1], w0.y, acc); acc = fmaf(f[2], w0.z, acc); acc = fmaf(f[3], w0.w, acc);
