@@ -1,21 +1,27 @@
-"""Benchmark of the sampling hot path (BASELINE.json: images/sec over the full sampling loop).
+"""Benchmark of the sampling hot path (BASELINE.json: images/sec over the full sampling loop for the DDPM UNet & DiT).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload dit|unet]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload dit|unet|rf|pixart|video]
 
-A "step" is one full ``sample()`` call: the complete reverse-process loop (1000 timesteps) over one
-batch of synthetic inputs.  Default workload = configs[1] of BASELINE.json: DiT on MNIST
-(configs/image/mnist/dit.yaml), DDPM ancestral sampling with dynamic thresholding, batch 1024 per GPU
-(weak scaling: global batch = 1024 * N), random-init weights with the zero-initialised tensors
-re-randomised, Gaussian initial latents, in-kernel Philox step noise.  Prints ONE JSON line.
+A "step" is one full ``sample()`` call: the complete reverse process (1000 timesteps) over one GLOBAL batch of
+synthetic inputs.  The default run measures what BASELINE.json names:
 
-  value   whole-job images/s, inputs resident in HBM, device-timed (CUDA events, max over ranks)
-  e2e     the same through the public API with HOST inputs: pinned x_T + labels copied H2D and the
-          finished samples copied D2H inside the timed region, every step
-  roofline  the dominant kernel (tcgen05 GEMM; the four contraction shapes of a DiT block), each
-          launch timed alone with CUDA events after an L2 flush; algorithmic FLOPs / time vs the
-          measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle (CPU port of the reference path) on the host cores, bounded sample
-``--impl reference`` times that CPU port instead (the reference itself is Python and does not travel).
+  * main line  = configs[1]: DiT on MNIST, DDPM ancestral + dynamic thresholding, GLOBAL batch 1024 sharded over the
+                 N GPUs (``xdiffusion_b200.dist``: rows [r*B/N, (r+1)*B/N) per rank, one final all-gather) ->
+                 ``"scaling": "strong"`` (128 images per GPU at N = 8);
+  * ``workloads.unet_c1`` = configs[0]: DDPM UNet 32x32, ancestral, global batch 64 (sharded the same way), with its
+                 own value / e2e / conv3x3 roofline;
+  * ``weak_scaling`` (N > 1 only): the DiT number with 1024 images PER GPU, for comparison with round 1.
+
+Per record:
+  value     whole-job images/s, inputs resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e       the same through the public API with HOST inputs: every rank copies its shard of the pinned x_T / labels
+            H2D, rank 0 copies the gathered samples D2H, all inside the timed region, every step
+  roofline  the dominant kernel class, each distinct launch shape timed in-loop (20 launches replayed from a CUDA
+            graph, CUDA events on the replay stream): algorithmic FLOPs / time vs the measured burst bf16 peak
+  cpu_baseline  the oracle (CPU port of the reference path) on the host cores, bounded sample, rank 0 at N = 1
+``--impl reference`` times that CPU port instead (the reference itself is Python + checkpoints that do not travel).
+Weights are synthetic and built HERE (constructor init under seed 0, zero-initialised tensors re-drawn from N(0, 0.02)):
+the product arm imports nothing from ``oracle/``.
 """
 import argparse
 import json
@@ -30,11 +36,18 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# SURVEY.md section 8(d), 2*MAC per sample per network forward (pixart: x2 forwards under CFG; video: per clip)
-FLOP_PER_IMAGE_STEP = {"dit": 0.7081e9, "unet": 10.684e9, "rf": 10.684e9, "pixart": 2 * 1.437e9, "video": 188.22e9}
+# SURVEY.md section 8(d), 2*MAC per sample per network forward EXECUTED.  pixart: two forwards under CFG with the
+# cross-attention K/V and the ContextProjection cached across timesteps (0.824 GFLOP each; the reference recomputes them:
+# 1.437); video: per clip.
+FLOP_PER_SAMPLE_STEP = {"dit": 0.7081e9, "unet": 10.684e9, "rf": 10.684e9, "pixart": 2 * 0.824e9, "video": 188.22e9}
 FIXTURE = {"dit": "c2", "unet": "c1", "rf": "c3", "pixart": "c4", "video": "c5"}
-DEFAULT_BATCH = {"dit": 1024, "unet": 64, "rf": 64, "pixart": 512, "video": 2}
-SAMPLING_STEPS = 1000
+GLOBAL_BATCH = {"dit": 1024, "unet": 64, "rf": 64, "pixart": 512, "video": 8}
+UNIT = {"dit": "images/s", "unet": "images/s", "rf": "images/s", "pixart": "images/s", "video": "clips/s"}
+NAMES = {"dit": "DiT on MNIST (configs/image/mnist/dit.yaml), DDPM ancestral + dynamic thresholding",
+         "unet": "DDPM UNet 32x32 (configs/image/mnist/ddpm_32x32_epsilon_discrete.yaml), ancestral",
+         "rf": "Rectified flow UNet 32x32 (configs/image/mnist/rectified_flow_32x32.yaml), Euler",
+         "pixart": "PixArt-alpha (configs/image/mnist/pixart_alpha.yaml), synthetic 77x768 text embeddings, CFG w=2",
+         "video": "Video UNet-3D 16x32x32 clips (configs/video/moving_mnist/video_diffusion_models.yaml), v-pred"}
 
 
 def measured_peaks():
@@ -45,9 +58,25 @@ def measured_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
-def load_fixture(workload):
-    from tests.conftest import load_golden
-    return load_golden(FIXTURE[workload])
+def load_config(workload):
+    """The reference YAML of the workload as a dict (stored in the golden fixture by tests/golden/make_golden.py)."""
+    return torch.load(os.path.join(ROOT, "tests", "golden", FIXTURE[workload] + ".pt"), weights_only=False)["config"]
+
+
+def build_model(workload, device):
+    """Random-init weights of the reference architecture: constructor init under seed 0, then every zero-initialised
+    tensor (resblock out-convs, attention out-projections, adaLN / final layers -- the DiT output would be identically 0)
+    re-drawn from N(0, 0.02)  (SURVEY.md section 8d)."""
+    from xdiffusion_b200.diffusion import GaussianDiffusion_DDPM
+    from xdiffusion_b200.utils import DotConfig
+    torch.manual_seed(0)
+    m = GaussianDiffusion_DDPM(DotConfig(load_config(workload)))
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.ndim >= 1 and "pos_embed" not in name and float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return m.to(device).eval()
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -88,7 +117,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------ CPU arm
+# ------------------------------------------------------------------------------------ CPU arm (the only user of oracle/)
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core the process may run on."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -96,78 +125,328 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_port_images_per_sec(workload, batch, denoise_steps=2):
-    """The oracle = CPU restatement of the reference path, all host threads, fp32.  Times
-    `denoise_steps` reverse-process steps at the full batch and scales to the 1000-step loop (every
-    step has identical cost)."""
+def cpu_port_rate(workload, batch, denoise_steps=2):
+    """The oracle = CPU restatement of the reference path, all host threads, fp32.  Times `denoise_steps`
+    reverse-process steps at the full batch and scales to the full loop (every step has identical cost).  The port is
+    FASTER than the unmodified reference (SURVEY probe: reference 4.35 s/step at 8 threads for DiT B=1024; the port
+    ~0.7 s at 16), so GPU/CPU ratios built on it are conservative."""
+    from oracle import samplers as os_
+    from tests.conftest import load_golden
     from tests.helpers import oracle_model
     use_all_host_threads()
-    fx = load_fixture(workload)
-    om = oracle_model(fx)
+    om = oracle_model(load_golden(FIXTURE[workload]))
+    total = om.steps
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, 1, 32, 32, generator=g)
     ctx = {"classes": torch.randint(0, 10, (batch,), generator=g)} if workload == "dit" else {}
     z = torch.randn(batch, 1, 32, 32, generator=g)
 
     def one(i, x):
-        t = torch.full((batch,), i, dtype=torch.int64)
-        o = om.score(x, t, ctx)
-        from oracle import samplers as os_
-        return os_.ancestral_discrete(x, o, z, i, om.tables, om.logvar, om.prediction, om.threshold)
+        n = x.shape[0]
+        t = torch.full((n,), i, dtype=torch.int64)
+        o = om.score(x, t, {k: v[:n] for k, v in ctx.items()})
+        return os_.ancestral_discrete(x, o, z[:n], i, om.tables, om.logvar, om.prediction, om.threshold)
 
-    small = max(1, batch // 16)
-    one(999, x[:small].clone()) if workload == "unet" else None       # touch the code path once (warm-up)
+    one(total - 1, x[:max(1, batch // 16)].clone())                  # touch the code path once (warm-up)
     t0 = time.perf_counter()
     for k in range(denoise_steps):
-        x = one(SAMPLING_STEPS - 1 - k, x)
+        x = one(total - 1 - k, x)
     dt = (time.perf_counter() - t0) / denoise_steps
-    return batch / (dt * SAMPLING_STEPS), dt
+    return batch / (dt * total), dt, total
+
+
+def cpu_baseline_record(workload, batch, denoise_steps=2):
+    v, dt, total = cpu_port_rate(workload, batch, denoise_steps)
+    return {"value": v, "unit": UNIT[workload], "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{denoise_steps} of {total} reverse-process steps at batch {batch} ({dt:.2f} s/step), scaled "
+                      f"x{total}; the port is faster than the unmodified PyTorch reference, so the ratio is conservative"}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """CPU arm: rank 0 alone works.  Same config / metric / unit as our arm; one bench step = one reverse-process step of
+    the workload at the full global batch, scaled to the full loop."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = use_all_host_threads()
-    batch = args.batch
-    vals = []
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_port_images_per_sec(args.workload, batch, 1)
+    main = args.workload or "dit"
+    if main not in ("dit", "unet"):
+        print(json.dumps({"impl": "reference", "unavailable": f"CPU port arm covers dit / unet, not {main}"}))
+        return
+    batch = args.batch or GLOBAL_BATCH[main]
+
+    def arm(workload, b):
+        for _ in range(min(args.warmup, 1)):
+            cpu_port_rate(workload, b, 1)
+        vals = [cpu_port_rate(workload, b, 1)[0] for _ in range(args.steps)]
+        return sum(vals) / len(vals)
+
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        v, dt = cpu_port_images_per_sec(args.workload, batch, 1)
-        vals.append(v)
-    wall = time.perf_counter() - t_all
-    value = sum(vals) / len(vals)
-    sample = (f"1 of {SAMPLING_STEPS} reverse-process steps per bench step at batch {batch}, scaled x{SAMPLING_STEPS}")
-    print(json.dumps({
-        "impl": "reference", "metric": "images_per_sec_full_sampling_loop", "value": value, "unit": "images/s",
+    value = arm(main, batch)
+    sample = f"1 of 1000 reverse-process steps per bench step at batch {batch}, scaled x1000"
+    line = {
+        "impl": "reference", "metric": "images_per_sec_full_sampling_loop", "value": value, "unit": UNIT[main],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * batch / value,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": wall}))
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(main, batch, args.gpus, 1000),
+        "cpu_baseline": {"value": value, "unit": UNIT[main], "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT[main], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.workload:
+        v = arm("unet", GLOBAL_BATCH["unet"])
+        line["workloads"] = {"unet_c1": {"value": v, "unit": "images/s", "e2e": {"value": v, "unit": "images/s"},
+                                         "config": workload_config("unet", GLOBAL_BATCH["unet"], args.gpus, 1000)}}
+    line["wall_s"] = time.perf_counter() - t_all
+    print(json.dumps(line))
 
 
-def workload_config(args, n):
-    name = {"dit": "DiT on MNIST (configs/image/mnist/dit.yaml), DDPM ancestral + dynamic thresholding",
-            "unet": "DDPM UNet 32x32 (configs/image/mnist/ddpm_32x32_epsilon_discrete.yaml), ancestral",
-            "rf": "Rectified flow UNet 32x32 (configs/image/mnist/rectified_flow_32x32.yaml), Euler",
-            "pixart": "PixArt-alpha (configs/image/mnist/pixart_alpha.yaml), synthetic 77x768 text embeddings, CFG w=2",
-            "video": "Video UNet-3D 16x32x32 (configs/video/moving_mnist/video_diffusion_models.yaml), v-pred"}[args.workload]
-    return {"workload": name, "sampling_steps": args.sampling_steps or (1024 if args.workload == "video" else 1000),
-            "per_gpu_batch": args.batch,
-            "global_batch": args.batch * n, "parallelism": f"batch-sharded x{n}, one final all-gather",
-            "l2": "activations per timestep exceed L2 (126 MB) at this batch; no flush between loops"}
+def workload_config(workload, global_batch, n, sampling_steps):
+    return {"workload": NAMES[workload], "sampling_steps": sampling_steps, "global_batch": global_batch,
+            "per_gpu_batch": -(-global_batch // n), "parallelism": f"batch sharded over {n} GPU(s), one final all-gather",
+            "l2": "each loop replays 1000 timesteps whose activations + weights (> 126 MB at batch 1024; weights 65 MB) "
+                  "cycle through L2; no explicit flush between loops"}
 
 
-def ncu_dram_bytes_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one GEMM launch (qkv shape) from the committed
-    `ncu --set full` summary under profiles/, or None."""
+# ------------------------------------------------------------------------------------ rooflines of the contractions
+def _time_in_graph(call, reps=20):
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            call()
+    graph.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
+    return sorted(ts)[len(ts) // 2]                       # ms per launch
+
+
+def gemm_roofline(batch, device):
+    """The four contractions of one DiT block at this per-GPU batch WITH their real epilogues (bias; bias + GELU; bias +
+    gate + fp32 residual in place), operands L2-resident as they are between the kernels of a timestep."""
+    from xdiffusion_b200 import ops
+    M = batch * 16
+    shapes = [(1152, 384, "qkv", False, 0), (384, 384, "proj", True, 0), (1536, 384, "fc1", False, ops.ACT_GELU),
+              (384, 1536, "fc2", True, 0)]
+    tot_flop, tot_ms, per = 0.0, 0.0, {}
+    for (n, k, name, rmw, act) in shapes:
+        a = torch.randn(M, k, device=device).bfloat16()
+        w = (torch.randn(n, k, device=device) * k ** -0.5).bfloat16()
+        bias = torch.randn(n, device=device)
+        if rmw:
+            out = torch.randn(M, n, device=device)
+            gate = torch.randn(M // 16, n, device=device) * 0.01
+            call = lambda: ops.linear(a, w, bias, gate=gate, gate_rows=16, residual=out, out=out)
+        else:
+            out = torch.empty(M, n, device=device, dtype=torch.bfloat16)
+            call = lambda: ops.linear(a, w, bias, act=act, out=out)
+        t = _time_in_graph(call)
+        per[name] = {"us": round(t * 1e3, 2), "tflops": round(2.0 * M * n * k / t / 1e9, 1)}
+        tot_flop += 2.0 * M * n * k
+        tot_ms += t
+    return tot_flop / tot_ms / 1e9, per
+
+
+def conv_roofline(model, batch, device):
+    """Every distinct conv3x3 launch of one UNet forward at this per-GPU batch (shape = pixels x C_in (+ fused 1x1 skip
+    segment) -> C_out, recorded from a real forward), each timed in-loop; achieved = sum(count * FLOP) / sum(count * time)."""
+    from xdiffusion_b200 import ops
+    seen, real = {}, ops.conv3x3
+
+    def spy(x, wp, bias=None, act=ops.ACT_NONE, residual=None, xs=None, out=None, force_bn=0):
+        key = (tuple(x.shape), 0 if xs is None else xs.shape[3], wp.shape[0], residual is not None)
+        seen[key] = seen.get(key, 0) + 1
+        return real(x, wp, bias, act=act, residual=residual, xs=xs, out=out, force_bn=force_bn)
+
+    ops.conv3x3 = spy
+    try:
+        x = torch.randn(batch, 1, 32, 32, device=device)
+        model.predict_score(x, context={"timestep": torch.full((batch,), 500, device=device)})
+    finally:
+        ops.conv3x3 = real
+    tot_flop, tot_ms, per = 0.0, 0.0, {}
+    for (shape, cs, cout, has_res), count in sorted(seen.items()):
+        nimg, H, W, C = shape
+        K = 9 * C + cs
+        xin = torch.randn(shape, device=device).bfloat16()
+        xs = torch.randn(nimg, H, W, cs, device=device).bfloat16() if cs else None
+        wp = (torch.randn(cout, K, device=device) * K ** -0.5).bfloat16()
+        bias = torch.randn(cout, device=device)
+        res = torch.randn(nimg, H, W, cout, device=device).bfloat16() if has_res else None
+        out = torch.empty(nimg, H, W, cout, device=device, dtype=torch.bfloat16)
+        t = _time_in_graph(lambda: real(xin, wp, bias, residual=res, xs=xs, out=out))
+        flop = 2.0 * nimg * H * W * cout * K
+        per[f"{H}x{W} {C}{'+' + str(cs) if cs else ''}->{cout}{' +res' if has_res else ''}"] = {
+            "count": count, "us": round(t * 1e3, 2), "tflops": round(flop / t / 1e9, 1)}
+        tot_flop += count * flop
+        tot_ms += count * t
+    return tot_flop / tot_ms / 1e9, per, tot_ms
+
+
+# ------------------------------------------------------------------------------------ our arm
+class Runner:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.args = args
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(self.local) as clk:
+            e0.record()
+            for k in range(self.args.steps):
+                fn(k)
+            e1.record()
+            self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, clk.summary()
+
+    def run_workload(self, workload, global_batch, model=None, with_e2e=True):
+        """value / e2e of one workload with its GLOBAL batch sharded over the ranks."""
+        from xdiffusion_b200 import ops
+        from xdiffusion_b200.dist import gather_rows, shard_bounds
+        args, device, world, rank = self.args, self.device, self.world, self.rank
+        model = model if model is not None else build_model(workload, device)
+        B = global_batch
+        lo, hi = shard_bounds(B, world, rank)
+        nloc = hi - lo
+        g = torch.Generator().manual_seed(1234)                              # same stream on every rank: rows [lo, hi)
+        shape = (B, 1, 16, 32, 32) if workload == "video" else (B, 1, 32, 32)
+        x_host = torch.randn(shape, generator=g)[lo:hi].contiguous().pin_memory()
+        cls_host = torch.randint(0, 10, (B,), generator=g)[lo:hi].contiguous().pin_memory()
+        out_host = torch.empty(shape).pin_memory() if rank == 0 else None
+        x_dev, cls_dev = x_host.to(device), cls_host.to(device)
+        extra, cfg_w = {}, None
+        if workload == "pixart":
+            from xdiffusion_b200.context import UnconditionalEmbeddingAdapter
+            extra["text_embeddings"] = torch.randn(B, 77, 768, generator=g)[lo:hi].to(device)
+            model._unconditional_context = UnconditionalEmbeddingAdapter([77, 768]).to(device)
+            cfg_w = 2.0
+        n_steps = args.sampling_steps if args.sampling_steps else model.noise_scheduler().steps()
+
+        def loop(x0, cls, seed):
+            ctx = dict(extra)
+            if workload in ("dit", "pixart"):
+                ctx["classes"] = cls
+            s, _ = model.sample(context=ctx, num_samples=nloc, initial_noise=x0, num_sampling_steps=n_steps, seed=seed,
+                                classifier_free_guidance=cfg_w, row_offset=lo)
+            return gather_rows(s, B) if world > 1 else s
+
+        loop(x_dev, cls_dev, 0)                       # builds + captures the step graph (untimed)
+        launches_per_timestep = None
+        if model._loops:
+            lp = next(iter(model._loops.values()))
+            ops.LAUNCHES = 0
+            lp._step()                                 # one eager step = the kernels one graph replay launches
+            launches_per_timestep = ops.LAUNCHES
+        for w in range(max(args.warmup - 1, 0)):
+            loop(x_dev, cls_dev, 1 + w)
+        ms, clocks = self.timed(lambda k: loop(x_dev, cls_dev, 100 + k))
+        rec = {"value": B * args.steps / (ms / 1e3), "unit": UNIT[workload], "ms_per_step": ms / args.steps,
+               "ms_per_timestep": ms / args.steps / n_steps, "launches_per_timestep": launches_per_timestep,
+               "gpu_launches": ((launches_per_timestep or 0) * n_steps + 2) * args.steps, "clocks": clocks,
+               "config": workload_config(workload, B, world, n_steps)}
+        rec["step_tensor_frac_of_sustained"] = (rec["value"] / world * FLOP_PER_SAMPLE_STEP[workload] * n_steps
+                                                / (measured_peaks()[1] * 1e12))
+        if with_e2e:
+            def e2e_step(k):
+                xd = x_host.to(device, non_blocking=True)
+                cd = cls_host.to(device, non_blocking=True)
+                full = loop(xd, cd, 200 + k)
+                if rank == 0:
+                    out_host.copy_(full, non_blocking=True)
+
+            e2e_step(0)
+            ms_e2e, _ = self.timed(e2e_step)
+            per_rank_h2d = x_host.numel() * 4 + cls_host.numel() * 8
+            rec["e2e"] = {"value": B * args.steps / (ms_e2e / 1e3), "unit": UNIT[workload],
+                          "h2d_bytes_per_step": per_rank_h2d * world, "d2h_bytes_per_step": B * x_host[0].numel() * 4}
+        return rec, model
+
+    def run(self):
+        args, world, rank = self.args, self.world, self.rank
+        burst, sustained, hbm, src = measured_peaks()
+        main = args.workload or "dit"
+        gb = args.batch or GLOBAL_BATCH[main]
+        rec, model = self.run_workload(main, gb)
+        extra = {}
+        if not args.workload:                                       # the default run also carries configs[0] (UNet C1)
+            urec, umodel = self.run_workload("unet", GLOBAL_BATCH["unet"])
+            if world > 1:
+                wrec, _ = self.run_workload("dit", gb * world, model=model, with_e2e=False)
+                extra["weak_scaling"] = {"value": wrec["value"], "unit": wrec["unit"], "global_batch": gb * world,
+                                         "per_gpu_batch": gb, "ms_per_step": wrec["ms_per_step"]}
+        self.barrier()
+        if rank != 0:
+            if world > 1:
+                self.dist.destroy_process_group()
+            return
+        per_gpu = -(-gb // world)
+        line = {"metric": "images_per_sec_full_sampling_loop", "value": rec["value"], "unit": rec["unit"],
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": rec["config"], "clocks": rec["clocks"], "e2e": rec["e2e"],
+                "gpu_launches": rec["gpu_launches"], "launches_per_timestep": rec["launches_per_timestep"],
+                "ms_per_timestep": rec["ms_per_timestep"],
+                "step_tensor_frac_of_sustained": rec["step_tensor_frac_of_sustained"]}
+        if main in ("dit", "pixart"):
+            tf, per = gemm_roofline(per_gpu, self.device)
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                                "traffic": ncu_dram_bytes("gemm"), "peak_source": src, "per_shape": per,
+                                "kernel": "gemm_tc_kernel (tcgen05, TMA epilogue): qkv + proj + fc1 + fc2 of one DiT block "
+                                          f"at M = {per_gpu * 16} rows with their real epilogues"}
+        elif main in ("unet", "rf"):
+            tf, per, _ = conv_roofline(model, per_gpu, self.device)
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                                "traffic": ncu_dram_bytes("conv"), "peak_source": src, "per_shape": per,
+                                "kernel": "gemm_tc_kernel, implicit-GEMM conv3x3: every distinct launch of one forward"}
+        if not args.workload:
+            ub = -(-GLOBAL_BATCH["unet"] // world)
+            tf, per, conv_ms = conv_roofline(umodel, ub, self.device)
+            urec["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                                "traffic": ncu_dram_bytes("conv"), "peak_source": src, "per_shape": per,
+                                "conv_ms_per_timestep": conv_ms,
+                                "kernel": "gemm_tc_kernel, implicit-GEMM conv3x3: every distinct launch of one UNet forward"}
+            line["gpu_launches"] += urec["gpu_launches"]
+            line["workloads"] = {"unet_c1": urec}
+            line.update(extra)
+        if world == 1 and not args.no_cpu and main in ("dit", "unet"):
+            line["cpu_baseline"] = cpu_baseline_record(main, gb)
+            if not args.workload:
+                line["workloads"]["unet_c1"]["cpu_baseline"] = cpu_baseline_record("unet", GLOBAL_BATCH["unet"], 1)
+        print(json.dumps(line))
+        if world > 1:
+            self.dist.destroy_process_group()
+
+
+def ncu_dram_bytes(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the newest committed `ncu --set full` summary of that
+    kernel class under profiles/ (r*_ncu_<kind>_*_summary.csv), or None."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_gemm_*_summary.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_{kind}_*_summary.csv")))
     if not files:
         return None
     try:
@@ -181,196 +460,22 @@ def ncu_dram_bytes_per_launch():
         return None
 
 
-# ------------------------------------------------------------------------------------ roofline of the GEMM
-def gemm_roofline(batch, device):
-    """The four contractions of one DiT block at this batch WITH their real epilogues (bias; bias + GELU; bias + gate +
-    fp32 residual in place).  `achieved` uses the in-loop condition: 20 launches per shape replayed from a CUDA graph
-    (operands L2-resident as they are between the kernels of a timestep), CUDA events on the replay stream.  The
-    cold number (one launch after an L2 flush, includes launch latency) is reported beside it."""
-    from xdiffusion_b200 import ops
-    M = batch * 16
-    shapes = [(1152, 384, "qkv", False, 0), (384, 384, "proj", True, 0), (1536, 384, "fc1", False, ops.ACT_GELU),
-              (384, 1536, "fc2", True, 0)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    tot_flop, tot_ms, per = 0.0, 0.0, {}
-    for (n, k, name, rmw, act) in shapes:
-        a = torch.randn(M, k, device=device).bfloat16()
-        w = (torch.randn(n, k, device=device) * k ** -0.5).bfloat16()
-        bias = torch.randn(n, device=device)
-        if rmw:
-            out = torch.randn(M, n, device=device)
-            gate = torch.randn(M // 16, n, device=device) * 0.01
-            call = lambda: ops.linear(a, w, bias, gate=gate, gate_rows=16, residual=out, out=out)
-        else:
-            out = torch.empty(M, n, device=device, dtype=torch.bfloat16)
-            call = lambda: ops.linear(a, w, bias, act=act, out=out)
-        for _ in range(3):
-            call()
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for _ in range(20):
-                call()
-        graph.replay()
-        torch.cuda.synchronize()
-        reps = []
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            graph.replay()
-            e1.record()
-            e1.synchronize()
-            reps.append(e0.elapsed_time(e1) / 20)
-        t = sorted(reps)[len(reps) // 2]
-        cold = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            call()
-            e1.record()
-            e1.synchronize()
-            cold.append(e0.elapsed_time(e1))
-        per[name] = {"us": round(t * 1e3, 2), "tflops": round(2.0 * M * n * k / t / 1e9, 1),
-                     "us_cold_single_launch": round(sorted(cold)[2] * 1e3, 2)}
-        tot_flop += 2.0 * M * n * k
-        tot_ms += t
-    return tot_flop / tot_ms / 1e9, per
-
-
-# ------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from tests.helpers import product_model
-    from xdiffusion_b200 import ops
-    from xdiffusion_b200.dist import gather_rows
-
-    fx = load_fixture(args.workload)
-    model = product_model(fx, device)
-    B = args.batch
-    g = torch.Generator().manual_seed(1234 + rank)
-    shape = (B, 1, 16, 32, 32) if args.workload == "video" else (B, 1, 32, 32)
-    x_host = torch.randn(shape, generator=g).pin_memory()
-    cls_host = torch.randint(0, 10, (B,), generator=g).pin_memory()
-    out_host = torch.empty(shape).pin_memory()
-    x_dev, cls_dev = x_host.to(device), cls_host.to(device)
-    extra, cfg_w = {}, None
-    if args.workload == "pixart":
-        from xdiffusion_b200.context import UnconditionalEmbeddingAdapter
-        extra["text_embeddings"] = torch.randn(B, 77, 768, generator=g).to(device)
-        model._unconditional_context = UnconditionalEmbeddingAdapter([77, 768]).to(device)
-        cfg_w = 2.0
-    n_steps = args.sampling_steps if args.sampling_steps else model.noise_scheduler().steps()
-
-    def loop(x0, cls, seed):
-        ctx = dict(extra)
-        if args.workload in ("dit", "pixart"):
-            ctx["classes"] = cls
-        s, _ = model.sample(context=ctx, num_samples=B, initial_noise=x0, num_sampling_steps=n_steps, seed=seed,
-                            classifier_free_guidance=cfg_w)
-        return gather_rows(s, B * world) if world > 1 else s
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    l0 = ops.LAUNCHES
-    loop(x_dev, cls_dev, 0)                       # builds + captures the step graph (untimed)
-    launches_per_timestep = None
-    if model._loops:
-        lp = next(iter(model._loops.values()))
-        ops.LAUNCHES = 0
-        lp._step()                                 # one eager step = the kernels one graph replay launches
-        launches_per_timestep = ops.LAUNCHES
-    for w in range(max(args.warmup - 1, 0)):
-        loop(x_dev, cls_dev, 1 + w)
-
-    def timed(fn):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            e0.record()
-            for k in range(args.steps):
-                fn(k)
-            e1.record()
-            barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, clk.summary()
-
-    ms, clocks = timed(lambda k: loop(x_dev, cls_dev, 100 + k))
-
-    def e2e_step(k):
-        xd = x_host.to(device, non_blocking=True)
-        cd = cls_host.to(device, non_blocking=True)
-        out_host.copy_(loop(xd, cd, 200 + k)[:B], non_blocking=True)
-
-    e2e_step(0)
-    ms_e2e, _ = timed(e2e_step)
-    total_images = B * world * args.steps
-    value = total_images / (ms / 1e3)
-    e2e_value = total_images / (ms_e2e / 1e3)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    burst, sustained, hbm, src = measured_peaks()
-    rl_tflops, per_shape = gemm_roofline(B, device) if args.workload == "dit" else (None, {})
-    flop_img = FLOP_PER_IMAGE_STEP[args.workload] * n_steps
-    line = {
-        "metric": "images_per_sec_full_sampling_loop", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, world), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + cls_host.numel() * 8,
-                "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": ((launches_per_timestep or 0) * n_steps + 2) * args.steps,
-        "launches_per_timestep": launches_per_timestep,
-        "ms_per_timestep": ms / args.steps / n_steps,
-        "step_tensor_frac_of_sustained": value / world * flop_img / (sustained * 1e12),
-    }
-    if rl_tflops is not None:
-        line["roofline"] = {"bound": "tensor", "achieved": rl_tflops, "peak": burst, "unit": "TFLOP/s",
-                            "frac": rl_tflops / burst, "traffic": ncu_dram_bytes_per_launch(), "peak_source": src,
-                            "kernel": "gemm_tc_kernel (tcgen05, CTA-pair 256x192 tiles, TMA epilogue): qkv+proj+fc1+fc2 of one DiT block with their real epilogues, 20 launches per shape replayed from a CUDA graph",
-                            "per_shape": per_shape}
-    if world == 1 and not args.no_cpu:
-        v, dt = cpu_port_images_per_sec(args.workload, B, 2)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"2 of {SAMPLING_STEPS} reverse-process steps at batch {B} "
-                                          f"({dt:.2f} s/step), scaled x{SAMPLING_STEPS}"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dit", choices=list(FIXTURE))
-    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 1024 DiT, 64 UNet)")
+    ap.add_argument("--workload", default=None, choices=list(FIXTURE),
+                    help="measure only this workload (default: DiT C2 main line + UNet C1 record)")
+    ap.add_argument("--batch", type=int, default=None, help="GLOBAL batch (default 1024 DiT, 64 UNet)")
     ap.add_argument("--sampling-steps", type=int, default=0, help="0 = the scheduler's full step count")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.batch is None:
-        args.batch = DEFAULT_BATCH[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        Runner(args).run()
 
 
 if __name__ == "__main__":

@@ -90,13 +90,15 @@ int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, int H, int W
  * q/k/v are bf16 (qkv_dtype 1) or, for the Tq = Tk = 16 relative-position path, fp32 (qkv_dtype 0; strides
  * then count fp32 elements).  logits = scale * q.k (+ q.relk[h, j-i+Tk-1]); relk fp32 [H][2Tk-1][64] or NULL; scramble=1 stores
  * through the reference's raw (B,H,L,D)->(B,H*D,L) reinterpretation with channel stride o_cs.
+ * heads_per_group (0 = H): the head index may carry an outer group g (h = g*heads_per_group + head, e.g. g = pixel of a
+ * clip, so that ALL clips run in one launch); `head` selects the relk table and the scrambled row, g adds g*o_gs to the store.
  * Replaces bmm+softmax+bmm at layers/attention.py:182-188 (UNet), :371-375 (DiT), :219-224 (PixArt
  * cross), :551-676 (temporal, relative positions). */
 int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
                       long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
                       long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs, long long o_rs,
                       int B, int H, int Tq, int Tk, int head_dim, float scale, const float* relk, int scramble,
-                      long long o_cs, int qkv_dtype, void* stream);
+                      long long o_cs, int qkv_dtype, int heads_per_group, long long o_gs, void* stream);
 
 /* ---- bandwidth-bound kernels ------------------------------------------------------------------ */
 
@@ -157,11 +159,13 @@ int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, 
 /* mode 0 ancestral (samplers/ancestral.py:21-72,189-267), 1 DDIM (samplers/ddim.py:43-123), 2 Euler
  * (samplers/rectified_flow.py:46-84).  coefs fp32 [N][8], row = loop index, read from *idx_dev when
  * non-NULL else idx_host.  z NULL -> in-kernel Philox normals keyed by *seed_dev when non-NULL (graph replay), else seed.  threshold=1 -> dynamic thresholding
- * (utils.py:379-396) with floor(rank)=thr_k, frac=thr_w, cap=thr_c.  In place (out == x) allowed. */
+ * (utils.py:379-396) with floor(rank)=thr_k, frac=thr_w, cap=thr_c.  In place (out == x) allowed.
+ * elem_offset (multiple of 4): index of x[0] in the UNSHARDED batch (first global row * n_per_sample); it is added to the
+ * Philox counter so that a batch sharded over ranks draws exactly the noise of the one-GPU run with the same seed. */
 int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float* o, const float* z,
                     long long z_step_stride, float* out, const float* coefs, const int* idx_dev, int idx_host,
                     long long n_total, int n_per_sample, int threshold, int thr_k, float thr_w, float thr_c,
-                    unsigned long long seed, const unsigned long long* seed_dev, void* stream);
+                    unsigned long long seed, const unsigned long long* seed_dev, long long elem_offset, void* stream);
 /* *idx_dev <- set_to (>= 0), *idx_dev - 1 (set_to == -1) or unchanged (-2); then out_*[b] = tab_*[*idx_dev], b < B
  * (the per-step `t = torch.tensor([idx]*B)` / logsnr lookups of diffusion/ddpm.py:928-955). */
 int xd_schedule_advance(int* idx_dev, int set_to, const long long* tab_i64, const float* tab_f32a,

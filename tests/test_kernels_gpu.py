@@ -304,6 +304,21 @@ def test_attention_relative_position_scrambled(ops):
     ops.attention(q, k, v, 1.0, out=out.view(Bp, L, H, 64).permute(0, 2, 1, 3), relk=ek.to(DEV), scramble=True,
                   o_cs=1)
     assert rel_l2(out.permute(0, 2, 1), ref) < 3e-3
+    # grouped heads: all clips in ONE launch (rows ordered (clip, frame, pixel) as in the video UNet) must equal the
+    # per-pixel-batch launch verified above, bit for bit
+    Bc, HW, C = 2, 16, H * 64
+    x = (torch.randn(Bc, L, HW, 3 * C, generator=g) * 0.3).to(DEV)
+    pix = x.permute(0, 2, 1, 3).reshape(Bc * HW, L, H, 3, 64)                          # (clip, pixel) batch
+    q, k, v = (pix[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    want = torch.empty(Bc * HW, L, C, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, 1.0, out=want.view(Bc * HW, L, H, 64).permute(0, 2, 1, 3), relk=ek.to(DEV), scramble=True,
+                  o_cs=1)
+    C3 = 3 * C
+    q, k, v = (x.as_strided((Bc, HW * H, L, 64), (L * HW * C3, 192, HW * C3, 1), i * 64) for i in range(3))
+    got = torch.empty(Bc, L, HW, C, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, 1.0, out=got.as_strided((Bc, HW * H, L, 64), (L * HW * C, 64, HW * C, 1)), relk=ek.to(DEV),
+                  scramble=True, o_cs=1, hpg=H, o_gs=C)
+    assert torch.equal(got.permute(0, 2, 1, 3).reshape(Bc * HW, L, C), want)
 
 
 def test_split_precision_gemm(ops):
@@ -389,13 +404,13 @@ def test_sampler_step_discrete_bit_exact(ops, pred, threshold):
         ranks = torch.tensor(0.99, dtype=torch.float32) * (1024 - 1)
         out = torch.empty_like(x, device=DEV)
         torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out, coefs, None, i,
-                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None)
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None, 0)
         assert torch.equal(out.cpu(), ref), (i, float((out.cpu() - ref).abs().max()))
         # device-resident loop index (the CUDA-graph path)
         idx = torch.tensor([i], dtype=torch.int32, device=DEV)
         out2 = torch.empty_like(out)
         torch.ops.xdb200.sampler_step(0, 0, 0, x.to(DEV), o.to(DEV), z.to(DEV), 0, out2, coefs, idx, -1,
-                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None)
+                                      int(threshold), int(ranks.floor()), float(ranks - ranks.floor()), 1.7, 0, None, 0)
         assert torch.equal(out2, out)
 
 
@@ -406,7 +421,7 @@ def test_sampler_step_euler_and_philox(ops):
     coefs[:, 0] = 1.0 / 1000
     out = torch.empty_like(x, device=DEV)
     torch.ops.xdb200.sampler_step(2, 0, 0, x.to(DEV), o.to(DEV), None, 0, out, coefs.to(DEV), None, 5, 0, 0, 0.0,
-                                  0.0, 0, None)
+                                  0.0, 0, None, 0)
     assert torch.equal(out.cpu(), osamplers.euler_flow(x, o, 1000))
     # in-kernel noise: x0 == 0 => out = sigma * z ~ N(0, sigma^2), different per step and per seed
     n = 1 << 20
@@ -416,12 +431,63 @@ def test_sampler_step_euler_and_philox(ops):
     outs = []
     for step, seed in ((1, 1), (2, 1), (1, 2)):
         o_ = torch.empty_like(zeros)
-        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, o_, c, None, step, 0, 0, 0.0, 0.0, seed, None)
+        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, o_, c, None, step, 0, 0, 0.0, 0.0, seed, None, 0)
         outs.append(o_.cpu())
     for o_ in outs:
         assert abs(float(o_.mean())) < 5e-3 and abs(float(o_.std()) - 1) < 5e-3
         assert abs(float((o_ ** 4).mean()) - 3) < 0.05
     assert abs(float((outs[0] * outs[1]).mean())) < 5e-3 and abs(float((outs[0] * outs[2]).mean())) < 5e-3
+
+
+def test_philox_offset_makes_shards_reproduce_the_unsharded_noise(ops):
+    """The Philox counter is the GLOBAL element index: rows [lo, hi) computed with elem_offset = lo * n_per_sample draw
+    the noise those rows get in the unsharded launch (xdiffusion_b200/dist.py), for both step kernels."""
+    B, n = 8, 1024
+    zeros = torch.zeros(B, 1, 32, 32, device=DEV)
+    c = torch.zeros(4, 8, device=DEV)
+    c[:, 4] = 1.0
+    for threshold in (0, 1):
+        full = torch.empty_like(zeros)
+        torch.ops.xdb200.sampler_step(0, 0, 0, zeros, zeros, None, 0, full, c, None, 2, threshold, 1012, 0.77, 1.7, 5,
+                                      None, 0)
+        assert len(torch.unique(full.view(B, -1)[:, :16], dim=0)) == B          # rows differ
+        for lo, hi in ((0, 3), (3, 8)):
+            part = torch.empty_like(zeros[lo:hi])
+            torch.ops.xdb200.sampler_step(0, 0, 0, zeros[lo:hi], zeros[lo:hi], None, 0, part, c, None, 2, threshold,
+                                          1012, 0.77, 1.7, 5, None, lo * n)
+            assert torch.equal(part, full[lo:hi])
+
+
+@pytest.mark.parametrize("pred", ["v", "epsilon"])
+@pytest.mark.parametrize("sampler", ["ancestral", "ddim"])
+@pytest.mark.parametrize("N", [1024, 1000, 50])
+def test_sampler_step_continuous_bit_exact(ops, pred, sampler, N):
+    """MODE_DDIM, x0 form 1 (continuous epsilon) and the continuous ancestral rows: host-built coefficient rows
+    (xdiffusion_b200/scheduler.py) + the fused kernel against the oracle's restatement of scheduler.py:414-494,524-544
+    and samplers/ddim.py:43-123 -- bit for bit, at the first / middle / last loop indices incl. i = 0."""
+    from xdiffusion_b200.scheduler import ContinuousNoiseScheduler
+    sched = ContinuousNoiseScheduler(1024, "cosine", "l2", -20, 20)
+    gammas = oschedules.cosine_logsnr_table(1024, -20, 20)
+    assert torch.equal(sched.gammas, gammas)
+    coefs, form = sched.step_coefficients(pred, N, sampler)
+    assert form == (0 if pred == "v" else 1)
+    coefs = coefs.to(DEV)
+    g = torch.Generator().manual_seed(23 + N)
+    B = 4
+    mode = 0 if sampler == "ancestral" else 1
+    for i in (N - 1, N // 2, 7, 1, 0):
+        x, o, z = (torch.randn(B, 1, 32, 32, generator=g) for _ in range(3))
+        x = x * torch.linspace(0.3, 2.5, B)[:, None, None, None]
+        idx_s, idx_t = oschedules.continuous_indices(i, N, 1024)
+        lam_s, lam_t = gammas[idx_s], gammas[idx_t]
+        if sampler == "ancestral":
+            ref = osamplers.ancestral_continuous(x, o, z, i, lam_s, lam_t, pred, None)
+        else:
+            ref = osamplers.ddim_continuous(x, o, i, lam_s, lam_t, pred, None)
+        out = torch.empty_like(x, device=DEV)
+        torch.ops.xdb200.sampler_step(mode, form, int(pred == "v"), x.to(DEV), o.to(DEV), z.to(DEV), 0, out, coefs,
+                                      None, i, 0, 0, 0.0, 0.0, 0, None, 0)
+        assert torch.equal(out.cpu(), ref), (sampler, pred, N, i, float((out.cpu() - ref).abs().max()))
 
 
 def test_schedule_advance_and_misc(ops):

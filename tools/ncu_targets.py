@@ -1,0 +1,94 @@
+"""One launch of every hot kernel at its benchmark shape, between cudaProfilerStart/Stop, for
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r2_hot python tools/ncu_targets.py
+
+Shapes: DiT C2 at batch 1024 (M = 16384 token rows), UNet C1 at batch 64, PixArt cross-attention 16 x 77.
+Each target is warmed up outside the profiled range (lazy attribute setup, tensor maps) and then launched once inside.
+"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from xdiffusion_b200 import ops  # noqa: E402
+
+dev = "cuda"
+bf = lambda *s: torch.randn(*s, device=dev).bfloat16()
+targets = []
+
+
+def target(name):
+    def deco(fn):
+        targets.append((name, fn))
+        return fn
+    return deco
+
+
+# ---- DiT block contractions (gemm_tc_kernel) -------------------------------------------------------------------
+M = 16384
+for (n, k, nm, rmw, act) in [(1152, 384, "qkv", False, 0), (384, 384, "proj", True, 0), (1536, 384, "fc1", False, ops.ACT_GELU),
+                             (384, 1536, "fc2", True, 0)]:
+    a, w, bias = bf(M, k), bf(n, k) * k ** -0.5, torch.randn(n, device=dev)
+    if rmw:
+        out, gate = torch.randn(M, n, device=dev), torch.randn(M // 16, n, device=dev) * 0.01
+        targets.append((f"gemm {nm}", lambda a=a, w=w, bias=bias, gate=gate, out=out:
+                        ops.linear(a, w, bias, gate=gate, gate_rows=16, residual=out, out=out)))
+    else:
+        out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
+        targets.append((f"gemm {nm}", lambda a=a, w=w, bias=bias, act=act, out=out: ops.linear(a, w, bias, act=act, out=out)))
+
+# ---- conv3x3, one per UNet resolution (batch 64) -----------------------------------------------------------------
+for (hw, c, cs, co) in [(32, 128, 0, 128), (32, 384, 384, 128), (16, 256, 0, 256), (8, 256, 0, 256), (4, 256, 0, 256)]:
+    x, wp, bias = bf(64, hw, hw, c), bf(co, 9 * c + cs) * (9 * c) ** -0.5, torch.randn(co, device=dev)
+    xs = bf(64, hw, hw, cs) if cs else None
+    res = None if cs else bf(64, hw, hw, co)
+    out = torch.empty(64, hw, hw, co, device=dev, dtype=torch.bfloat16)
+    targets.append((f"conv {hw}x{hw} {c}+{cs}->{co}", lambda x=x, wp=wp, bias=bias, xs=xs, res=res, out=out:
+                    ops.conv3x3(x, wp, bias, residual=res, xs=xs, out=out)))
+
+# ---- GroupNorm + SiLU (gn_fused_kernel) ------------------------------------------------------------------------------
+for (hw, c) in [(32, 128), (32, 256), (16, 256), (16, 512), (8, 256)]:
+    x, gamma, beta = bf(64, hw * hw, c), torch.randn(c, device=dev), torch.randn(c, device=dev)
+    out = torch.empty_like(x)
+    targets.append((f"groupnorm {hw}x{hw}x{c}", lambda x=x, gamma=gamma, beta=beta, out=out:
+                    ops.groupnorm(x, gamma, beta, silu=True, out=out)))
+
+# ---- LayerNorm + modulate ---------------------------------------------------------------------------------------------
+xh, sh, sc = torch.randn(M, 384, device=dev), torch.randn(1024, 384, device=dev), torch.randn(1024, 384, device=dev)
+targets.append(("ln_modulate", lambda: ops.layernorm_modulate(xh, sh, sc, 16)))
+
+# ---- attention ----------------------------------------------------------------------------------------------------------
+qkv = bf(1024 * 16, 3 * 6 * 64).view(1024, 16, 3, 6, 64)
+q16, k16, v16 = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+targets.append(("attention T=16 (DiT)", lambda: ops.attention(q16, k16, v16, 0.125)))
+qkv2 = bf(64, 256, 4, 3, 64)
+q256, k256, v256 = (qkv2[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+targets.append(("attention T=256 (UNet 16x16)", lambda: ops.attention(q256, k256, v256, 0.125)))
+qx = bf(512, 16, 6, 64).permute(0, 2, 1, 3)
+kv = bf(512, 77, 2, 6, 64)
+targets.append(("attention 16x77 (PixArt cross)", lambda: ops.attention(qx, kv[:, :, 0].permute(0, 2, 1, 3),
+                                                                        kv[:, :, 1].permute(0, 2, 1, 3), 0.125)))
+
+# ---- fused sampler step with dynamic thresholding (DiT C2) ------------------------------------------------------------------
+x = torch.randn(1024, 1, 32, 32, device=dev)
+o = torch.randn_like(x)
+coefs = torch.rand(1000, 8, device=dev)
+targets.append(("sampler step (threshold, philox)", lambda: torch.ops.xdb200.sampler_step(
+    0, 0, 0, x, o, None, 0, x, coefs, None, 500, 1, 1012, 0.77, 1.7, 3, None, 0)))
+x64 = torch.randn(64, 1, 32, 32, device=dev)
+o64 = torch.randn_like(x64)
+targets.append(("sampler step (clamp)", lambda: torch.ops.xdb200.sampler_step(
+    0, 0, 0, x64, o64, None, 0, x64, coefs, None, 500, 0, 0, 0.0, 0.0, 3, None, 0)))
+
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+targets = [(n, f) for n, f in targets if only in n]
+for name, fn in targets:
+    fn()
+    fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for name, fn in targets:
+    fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("profiled:", [n for n, _ in targets])

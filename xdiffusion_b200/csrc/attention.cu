@@ -28,6 +28,8 @@ struct AttnParams {
     int scramble;               // temporal quirk: out viewed as (H*64, L) from a (H, L, 64) buffer
     long long o_cs;             // scramble: element stride between "channels" of the (C, L) view
     int in_f32;                 // q/k/v are fp32 (T = 16 relative-position path only)
+    int hpg;                    // heads per group: index h = g * hpg + head; `head` selects the relk table / scramble row,
+    long long o_gs;             // g (e.g. the pixel of a clip) adds g * o_gs to the scrambled store.  hpg == H: no groups
 };
 
 // q . k over 64 dims with four independent accumulators (a single 64-long FMA chain is latency-bound)
@@ -66,10 +68,11 @@ __device__ __forceinline__ void store_row(const AttnParams& p, int b, int h, int
         // a[b, h, row, d] is element (h*L + row)*64 + d of a flat buffer that the reference then
         // views as (C = H*64, L): flat = c*L + l.
         const int L = p.Tq;
-        bf16* ob = p.o + b * p.o_bs;
+        const int g = h / p.hpg, hh = h - g * p.hpg;
+        bf16* ob = p.o + b * p.o_bs + g * p.o_gs;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const int flat = (h * L + row) * D + d;
+            const int flat = (hh * L + row) * D + d;
             const int c = flat / L, lpos = flat % L;
             ob[(long long)lpos * p.o_rs + (long long)c * p.o_cs] = __float2bfloat16_rn(o[d] * inv);
         }
@@ -137,7 +140,7 @@ attention16_kernel(const AttnParams p) {
     for (int j = 0; j < T16; ++j) {
         float acc = dot64(q, reinterpret_cast<const float4*>(sK + j * RS16));
         if (p.relk)
-            acc += dot64_ldg(q, reinterpret_cast<const float4*>(p.relk + ((long long)h * (2 * T16 - 1) + (j - row + T16 - 1)) * D));
+            acc += dot64_ldg(q, reinterpret_cast<const float4*>(p.relk + ((long long)(h % p.hpg) * (2 * T16 - 1) + (j - row + T16 - 1)) * D));
         s[j] = acc;
         mx = fmaxf(mx, acc);
     }
@@ -353,7 +356,7 @@ attention_kernel(const AttnParams p) {
                 acc = dot64(q, reinterpret_cast<const float4*>(sK + kk * D));
                 if (p.relk)
                     acc += dot64_ldg(q, reinterpret_cast<const float4*>(
-                        p.relk + ((long long)h * (2 * p.Tk - 1) + (k0 + kk - row + p.Tk - 1)) * D));
+                        p.relk + ((long long)(h % p.hpg) * (2 * p.Tk - 1) + (k0 + kk - row + p.Tk - 1)) * D));
             } else {
                 acc = -INFINITY;
             }
@@ -545,7 +548,8 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
                                  long long k_bs, long long k_hs, long long k_rs, const void* v, long long v_bs,
                                  long long v_hs, long long v_rs, void* o, long long o_bs, long long o_hs,
                                  long long o_rs, int B, int H, int Tq, int Tk, int head_dim, float scale,
-                                 const float* relk, int scramble, long long o_cs, int qkv_dtype, void* stream) {
+                                 const float* relk, int scramble, long long o_cs, int qkv_dtype, int heads_per_group,
+                                 long long o_gs, void* stream) {
     XD_CHECK_ARG(q && k && v && o && head_dim == D && B > 0 && H > 0 && Tq > 0 && Tk > 0);
     const int in_f32 = qkv_dtype == XD_F32;
     XD_CHECK_ARG(!in_f32 || (Tq == 16 && Tk == 16));            // fp32 q/k/v: SIMT T = 16 kernel only
@@ -554,8 +558,10 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
                  q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0);
     XD_CHECK_ARG(scramble || (o_rs % 8 == 0 && o_hs % 8 == 0 && o_bs % 8 == 0));
     XD_CHECK_ARG(!relk || Tq == Tk);
+    if (heads_per_group <= 0) heads_per_group = H;
+    XD_CHECK_ARG(H % heads_per_group == 0 && (heads_per_group == H || relk || scramble));
     AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, q_bs, q_hs, q_rs, k_bs, k_hs, k_rs,
-                 v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs, in_f32};
+                 v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs, in_f32, heads_per_group, o_gs};
     if (Tq == 256 && Tk == 256 && !relk && !scramble) {           // tcgen05 path (csrc/attention_tc.cu)
         const int rc = xd_attention_tc256_try(q, q_bs, q_hs, q_rs, k, k_bs, k_hs, k_rs, v, v_bs, v_hs, v_rs, o, o_bs,
                                               o_hs, o_rs, B, H, scale, (cudaStream_t)stream);

@@ -34,6 +34,8 @@ struct StepParams {
     float thr_w, thr_c;         // rank - floor(rank), hard cap c
     unsigned long long seed;    // in-kernel Philox noise when z == nullptr
     const unsigned long long* seed_dev;   // if non-null the seed is read from device memory (CUDA-graph replay)
+    unsigned long long vec_offset;        // Philox counter of this shard's first float4: (first global row * n_per_sample) / 4,
+                                          // so that a batch sharded over ranks draws the noise of the unsharded run
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 + Box-Muller
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
             r.z = __fadd_rn(x.z, __fmul_rn(o.z, cf[0])); r.w = __fadd_rn(x.w, __fmul_rn(o.w, cf[0]));
         } else {
             float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (need_noise) zz = z ? reinterpret_cast<const float4*>(z)[v] : philox_normal4(seed, (unsigned long long)v, (uint32_t)i);
+            if (need_noise) zz = z ? reinterpret_cast<const float4*>(z)[v] : philox_normal4(seed, p.vec_offset + (unsigned long long)v, (uint32_t)i);
             const float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, zs[4] = {zz.x, zz.y, zz.z, zz.w};
             float rs[4];
 #pragma unroll
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) step_threshold_kernel(const StepParams p,
         float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
         if (need_noise)
             zz = z ? reinterpret_cast<const float4*>(z + base)[e4]
-                   : philox_normal4(seed, (unsigned long long)(base / 4 + e4), (uint32_t)i);
+                   : philox_normal4(seed, p.vec_offset + (unsigned long long)(base / 4 + e4), (uint32_t)i);
         const float zs[4] = {zz.x, zz.y, zz.z, zz.w};
         float rs[4];
 #pragma unroll
@@ -235,11 +237,12 @@ extern "C" int xd_sampler_step(int mode, int form, int pred_v, const float* x, c
                                long long z_step_stride, float* out, const float* coefs, const int* idx_dev,
                                int idx_host, long long n_total, int n_per_sample, int threshold, int thr_k,
                                float thr_w, float thr_c, unsigned long long seed,
-                               const unsigned long long* seed_dev, void* stream) {
+                               const unsigned long long* seed_dev, long long elem_offset, void* stream) {
     XD_CHECK_ARG(x && o && out && coefs && n_total > 0 && n_per_sample > 0 && n_total % n_per_sample == 0);
+    XD_CHECK_ARG(elem_offset >= 0 && elem_offset % 4 == 0);
     XD_CHECK_ARG(n_per_sample % 4 == 0 && mode >= 0 && mode <= 2 && (idx_dev || idx_host >= 0));
     StepParams p{x, o, z, out, coefs, idx_dev, idx_host, z_step_stride, n_total, n_per_sample, mode, form, pred_v,
-                 threshold, thr_k, thr_w, thr_c, seed, seed_dev};
+                 threshold, thr_k, thr_w, thr_c, seed, seed_dev, (unsigned long long)(elem_offset / 4)};
     cudaStream_t st = (cudaStream_t)stream;
     if (threshold && mode != MODE_EULER) {
         XD_CHECK_ARG(n_per_sample <= 8192 && thr_k >= 0 && thr_k < n_per_sample);

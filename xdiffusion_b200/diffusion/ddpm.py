@@ -107,6 +107,11 @@ class GaussianDiffusion_DDPM(DiffusionModel):
             for k in missing:
                 assert "temporal" in k or "motion_module" in k, k
 
+    def _weights_fingerprint(self):
+        """(storage, version) of every parameter and buffer: changes on load_state_dict / load_checkpoint / in-place
+        updates (EMA swaps) / .to(); used to invalidate captured sampling loops."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     # ------------------------------------------------------------------ schedule glue for the fused kernels
     def step_coefficients(self, sampler_name: str, num_sampling_steps: int):
         """Device copy of the per-loop-index coefficient rows for csrc/step.cu (cached)."""
@@ -160,11 +165,13 @@ class GaussianDiffusion_DDPM(DiffusionModel):
                classifier_free_guidance: Optional[float] = None, num_sampling_steps: Optional[int] = None,
                sampler: Optional[ReverseProcessSampler] = None, initial_noise: Optional[torch.Tensor] = None,
                context_preprocessor: Optional[torch.nn.Module] = None, noise: Optional[torch.Tensor] = None,
-               use_cuda_graph: bool = True, seed: Optional[int] = None,
+               use_cuda_graph: bool = True, seed: Optional[int] = None, row_offset: int = 0,
                ) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
         """Same contract as the reference's ``sample()`` (diffusion/ddpm.py:544-669).  Extras:
         ``noise`` [N, *shape] injects the per-step Gaussian noise (row = loop index) for parity runs,
-        ``seed`` keys the in-kernel Philox noise otherwise, ``use_cuda_graph=False`` runs the loop eagerly."""
+        ``seed`` keys the in-kernel Philox noise (and x_T when ``initial_noise`` is None) otherwise,
+        ``row_offset`` is the index of this call's first sample in a larger sharded batch (it offsets the Philox
+        counter, so shards reproduce the rows of the unsharded run), ``use_cuda_graph=False`` runs the loop eagerly."""
         if guidance_fn is not None:
             raise NotImplementedError("classifier guidance needs autograd through the network (out of scope)")
         shape = self._output_shape(num_samples)
@@ -191,7 +198,8 @@ class GaussianDiffusion_DDPM(DiffusionModel):
         latents, intermediates = self._p_sample_loop(
             shape, context=context, unconditional_context=unconditional_context, guidance_fn=guidance_fn,
             classifier_free_guidance=classifier_free_guidance, num_sampling_steps=steps, sampler=sampler,
-            initial_noise=initial_noise, noise=noise, use_cuda_graph=use_cuda_graph, seed=seed)
+            initial_noise=initial_noise, noise=noise, use_cuda_graph=use_cuda_graph, seed=seed,
+            row_offset=row_offset)
         samples = self._unnormalize(latents)
         self.train()                         # the reference leaves the module in train mode (ddpm.py:668)
         return samples, intermediates
@@ -200,7 +208,7 @@ class GaussianDiffusion_DDPM(DiffusionModel):
                        guidance_fn=None, classifier_free_guidance: Optional[float] = None,
                        sampler: Optional[ReverseProcessSampler] = None, initial_noise: Optional[torch.Tensor] = None,
                        save_intermediate_outputs: bool = False, noise: Optional[torch.Tensor] = None,
-                       use_cuda_graph: bool = True, seed: Optional[int] = None):
+                       use_cuda_graph: bool = True, seed: Optional[int] = None, row_offset: int = 0):
         device = next(self.parameters()).device
         if "video_mask" in context:
             raise NotImplementedError("video_mask blending (autoregressive extension) is a 'next' row")
@@ -210,25 +218,43 @@ class GaussianDiffusion_DDPM(DiffusionModel):
             raise NotImplementedError("initial_timestep != 0")
         sampler = sampler if sampler is not None else self._reverse_process_sampler
         N, B = num_sampling_steps, shape[0]
-        x0 = initial_noise.to(device=device, dtype=torch.float32) if initial_noise is not None \
-            else torch.randn(shape, device=device)
+        if N < 1 or (not self._noise_scheduler.continuous() and N > self._noise_scheduler.steps()):
+            # the discrete tables have steps() rows and loop index i reads row i (the reference raises IndexError)
+            raise ValueError(f"num_sampling_steps={N} outside [1, {self._noise_scheduler.steps()}] of the schedule")
+        if initial_noise is not None:
+            x0 = initial_noise.to(device=device, dtype=torch.float32)
+        elif seed is not None:
+            x0 = seeded_initial_noise(shape, seed, device, row_offset)
+        else:
+            x0 = torch.randn(shape, device=device)
         if noise is not None:
             noise = noise.to(device=device, dtype=torch.float32).contiguous()
             assert noise.shape == (N,) + tuple(shape), "noise must be [num_sampling_steps, *shape]"
         seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
-        key = (tuple(shape), N, id(sampler), classifier_free_guidance, use_cuda_graph,
-               _ctx_signature(context), _ctx_signature(unconditional_context))
+        # A captured loop bakes in the repacked weights (Packed caches are only refreshed by the Python forward,
+        # which a replay skips), the device and the Philox row offset: all three are part of its identity.
+        key = (tuple(shape), N, id(sampler), classifier_free_guidance, use_cuda_graph, int(row_offset), str(device),
+               _ctx_signature(context), _ctx_signature(unconditional_context), self._weights_fingerprint())
         loop = self._loops.get(key) if noise is None else None
         if loop is None:
             loop = _DeviceLoop(self, sampler, tuple(shape), N, context, unconditional_context,
-                               classifier_free_guidance)
+                               classifier_free_guidance, row_offset)
             if noise is None:
                 self._loops = {key: loop}        # keep one captured loop alive (its buffers are static)
         else:
             loop.load_context(context, unconditional_context)
         x = loop.run(x0, noise, seed, use_cuda_graph)
         return x, []
+
+
+def seeded_initial_noise(shape, seed: int, device, row_offset: int = 0):
+    """x_T rows [row_offset, row_offset + shape[0]) of the batch a one-GPU run with this seed would draw: the device
+    generator is advanced past the rows of the lower ranks (Philox: skipping is an offset, values are identical)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    full = torch.randn((row_offset + shape[0],) + tuple(shape[1:]), device=device, generator=g)
+    return full[row_offset:].contiguous()
 
 
 def _ctx_signature(ctx):
@@ -242,8 +268,9 @@ class _DeviceLoop:
     captured once and replayed: x_t, the loop index, the per-step network inputs (refreshed from
     host-built tables by xd_schedule_advance) and static copies of the conditioning tensors."""
 
-    def __init__(self, model, sampler, shape, N, context, uncond_context, cfg):
+    def __init__(self, model, sampler, shape, N, context, uncond_context, cfg, row_offset=0):
         self.model, self.sampler, self.shape, self.N = model, sampler, shape, N
+        self.row_offset = int(row_offset)
         dev = next(model.parameters()).device
         B = shape[0]
         self.cfg = cfg
@@ -259,6 +286,7 @@ class _DeviceLoop:
         self.noise = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # Philox key, read by the step kernel
         self.graph = None
+        self._precompute()
 
     @staticmethod
     def _static(ctx, dev):
@@ -298,6 +326,7 @@ class _DeviceLoop:
     def _ctx(self, base):
         c = dict(base)
         c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep, self.idx, self.N
+        c["row_offset"] = self.row_offset
         if self.logsnr_t is not None:
             c["logsnr_t"], c["logsnr_s"] = self.logsnr_t, self.logsnr_s
         return c

@@ -56,7 +56,10 @@ def sample_sharded(model, context: Optional[Dict] = None, num_samples: int = 16,
     ctx = shard_context(context, num_samples, lo, hi)
     x0 = None if initial_noise is None else initial_noise[lo:hi].contiguous()
     z = None if noise is None else noise[:, lo:hi].contiguous()
-    local, inter = model.sample(context=ctx, num_samples=hi - lo, initial_noise=x0, noise=z, **kwargs)
+    # row_offset: the in-kernel Philox counter (and a seeded x_T) is indexed by the GLOBAL row, so every rank draws
+    # the noise its rows get in the one-GPU run with the same seed: shards differ from each other and
+    # world = 1 / world = N produce the same batch.
+    local, inter = model.sample(context=ctx, num_samples=hi - lo, initial_noise=x0, noise=z, row_offset=lo, **kwargs)
     if gather and world > 1:
         return gather_rows(local, num_samples, group), inter
     return local, inter

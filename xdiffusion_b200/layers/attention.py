@@ -185,11 +185,14 @@ class TemporalSelfAttention(ContextBlock, Packed):
                                    1, stats, n)
         qkv = ops.linear(n, wq3, self._qkv.bias, out_dtype=torch.float32, a2=n[:, :C])    # rows (b, f, hw) x 3C
         a = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
-        q5 = qkv.view(B, F, HW, heads, 3, d)
-        a4 = a.view(B, F, HW, heads, d)
-        for b in range(B):                                                   # batch index of the kernel = pixel
-            q, k, v = (q5[b, :, :, :, i].permute(1, 2, 0, 3) for i in range(3))     # [HW, heads, F, d]
-            ops.attention(q, k, v, 1.0, out=a4[b].permute(1, 2, 0, 3), relk=relk, scramble=True, o_cs=1)
+        # ONE launch for all clips: kernel batch = clip, kernel "head" index = (pixel, head) -- the (pixel, head) pair has a
+        # uniform stride (pixel: 3C = heads * 3d, head: 3d), `hpg = heads` recovers the true head for the rel-pos table
+        # and the scrambled store, `o_gs = C` is the pixel's offset in the output.
+        C3 = 3 * C
+        q, k, v = (qkv.as_strided((B, HW * heads, F, d), (F * HW * C3, 3 * d, HW * C3, 1), qkv.storage_offset() + i * d)
+                   for i in range(3))
+        o = a.as_strided((B, HW * heads, F, d), (F * HW * C, d, HW * C, 1), a.storage_offset())
+        ops.attention(q, k, v, 1.0, out=o, relk=relk, scramble=True, o_cs=1, hpg=heads, o_gs=C)
         if out is None:
             out = torch.empty((nimg, H, W, C), device=x.device, dtype=torch.bfloat16)
         o2 = out.as_strided((nimg * HW, C), (out.stride(2), 1))

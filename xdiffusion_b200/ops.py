@@ -44,14 +44,19 @@ def _cuda(*ts):
             raise _lib.XdError("xdb200 ops take CUDA tensors only (no CPU fallback)")
 
 
-# Split-K scratch (fp32 partial tiles of long contractions over few tiles): one caller-owned buffer per process,
-# registered with the library once per device; all GEMM / conv launches of a model run on one stream.
+# Split-K scratch (fp32 partial tiles of long contractions over few tiles): one caller-owned buffer per process.
+# The library keeps process-global state (this workspace, lazily configured kernel attributes), so a process drives
+# ONE device -- the deployment model is one process per GPU (dist.py); a second device raises instead of silently
+# freeing a buffer that captured graphs still reference.
 WORKSPACE_BYTES = int(os.environ.get("XDB200_WORKSPACE_MB", "64")) << 20
 _workspace = {}
 
 
 def _ensure_workspace(t):
     dev = t.device
+    if _workspace.get("device") not in (None, dev):
+        raise _lib.XdError(f"xdb200 drives one CUDA device per process (first used {_workspace['device']}, now {dev}); "
+                           "launch one process per GPU (xdiffusion_b200.dist)")
     if _workspace.get("device") != dev:
         buf = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=dev) if WORKSPACE_BYTES else None
         _lib.check(_lib.lib().xd_set_workspace(_p(buf), WORKSPACE_BYTES), "xd_set_workspace")
@@ -165,8 +170,9 @@ def _conv3x3_out(x, w, bias, out):
     _count()
 
 
-@_op("attention(Tensor q, Tensor k, Tensor v, Tensor(a!) o, float scale, Tensor? relk, int scramble, int o_cs) -> ()")
-def _attention(q, k, v, o, scale, relk, scramble, o_cs):
+@_op("attention(Tensor q, Tensor k, Tensor v, Tensor(a!) o, float scale, Tensor? relk, int scramble, int o_cs, "
+     "int hpg, int o_gs) -> ()")
+def _attention(q, k, v, o, scale, relk, scramble, o_cs, hpg, o_gs):
     """q [B,H,Tq,64], k/v [B,H,Tk,64], o [B,H,Tq,64]: arbitrary-stride bf16 views (last stride 1)."""
     _cuda(q, k, v, o, relk)
     B, H, Tq, D = q.shape
@@ -176,7 +182,7 @@ def _attention(q, k, v, o, scale, relk, scramble, o_cs):
     _lib.check(_lib.lib().xd_attention_bf16(
         _p(q), q.stride(0), q.stride(1), q.stride(2), _p(k), k.stride(0), k.stride(1), k.stride(2),
         _p(v), v.stride(0), v.stride(1), v.stride(2), _p(o), o.stride(0), o.stride(1), o.stride(2),
-        B, H, Tq, Tk, D, scale, _p(relk), scramble, o_cs, _dt(q), _stream()), "xd_attention_bf16")
+        B, H, Tq, Tk, D, scale, _p(relk), scramble, o_cs, _dt(q), hpg, o_gs, _stream()), "xd_attention_bf16")
     _count()
 
 
@@ -333,18 +339,20 @@ def _cfg_combine(cond, uncond, w, out):
 # ------------------------------------------------------------------------------------ sampler step
 @_op("sampler_step(int mode, int form, int pred_v, Tensor x, Tensor o, Tensor? z, int z_step_stride, "
      "Tensor(a!) out, Tensor coefs, Tensor? idx_dev, int idx_host, int threshold, int thr_k, float thr_w, "
-     "float thr_c, int seed, Tensor? seed_dev) -> ()")
+     "float thr_c, int seed, Tensor? seed_dev, int elem_offset) -> ()")
 def _sampler_step(mode, form, pred_v, x, o, z, z_step_stride, out, coefs, idx_dev, idx_host, threshold, thr_k,
-                  thr_w, thr_c, seed, seed_dev):
+                  thr_w, thr_c, seed, seed_dev, elem_offset):
     _cuda(x, o, z, out, coefs, idx_dev, seed_dev)
     assert seed_dev is None or seed_dev.dtype == torch.int64
     assert x.is_contiguous() and o.is_contiguous() and out.is_contiguous() and coefs.is_contiguous()
     assert x.dtype == torch.float32 and o.dtype == torch.float32 and coefs.dtype == torch.float32
     assert idx_dev is None or idx_dev.dtype == torch.int32
     n = x.numel()
+    if idx_dev is None and not 0 <= idx_host < coefs.shape[0]:
+        raise IndexError(f"timestep_idx {idx_host} outside the {coefs.shape[0]}-row schedule table")
     _lib.check(_lib.lib().xd_sampler_step(mode, form, pred_v, _p(x), _p(o), _p(z), z_step_stride, _p(out),
                                           _p(coefs), _p(idx_dev), idx_host, n, n // x.shape[0], threshold, thr_k,
-                                          thr_w, thr_c, seed, _p(seed_dev), _stream()), "xd_sampler_step")
+                                          thr_w, thr_c, seed, _p(seed_dev), elem_offset, _stream()), "xd_sampler_step")
     _count()
 
 
@@ -431,9 +439,9 @@ def layernorm_modulate(x, shift, scale, rows_per_mod, eps=1e-6):
     return out
 
 
-def attention(q, k, v, scale, out=None, relk=None, scramble=False, o_cs=0):
+def attention(q, k, v, scale, out=None, relk=None, scramble=False, o_cs=0, hpg=0, o_gs=0):
     if out is None:
         B, H, Tq, D = q.shape
         out = torch.empty((B, Tq, H, D), device=q.device, dtype=torch.bfloat16).permute(0, 2, 1, 3)
-    _ops.attention(q, k, v, out, float(scale), relk, int(scramble), o_cs)
+    _ops.attention(q, k, v, out, float(scale), relk, int(scramble), o_cs, hpg, o_gs)
     return out

@@ -55,5 +55,5 @@ class ReverseProcessSampler:
         torch.ops.xdb200.sampler_step(mode, form, pred_v, x, o, z, z_stride, out, coefs, idx_dev, idx_host,
                                       int(thr is not None), thr[0] if thr else 0, thr[1] if thr else 0.0,
                                       thr[2] if thr else 0.0, int(context.get("seed", self.seed)),
-                                      context.get("seed_dev"))
+                                      context.get("seed_dev"), int(context.get("row_offset", 0)) * x[0].numel())
         return out
