@@ -50,6 +50,18 @@ int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* shift, const 
                        int rows_per_mod, float eps, const void* Wt, long long ldw, int M, int N, int K,
                        const float* bias, int act, void* out, long long out_ld, void* stream);
 
+/* Fused second half of a DiT block (hidden size D = 384), one CTA pair per 256 token rows, in place on the fp32 stream h:
+ *   h1 = h + gate1 * (O Wp^T + bp);  a = bf16(LN(h1) * (1 + scale2) + shift2);  u = bf16(gelu_tanh(a W1^T + b1));
+ *   h  = h1 + gate2 * (u W2^T + b2);  stats_out[m] = (mean, rstd) of the new row m (optional; feeds the next LayerNorm).
+ * O bf16 [M, D] (attention output), Wp [D, D], W1 [hidden, D], W2 [D, hidden] bf16 row-major, hidden % 128 == 0; gate / shift /
+ * scale are fp32 rows of D values, row index m / rows_per_mod, mod_ld floats apart.  The [M, hidden] activation never leaves
+ * the SM.  Replaces `x + gate_msa * attn.proj(.)` and `x + gate_mlp * mlp(modulate(norm2(x), shift_mlp, scale_mlp))`
+ * (score_networks/dit.py:46-59, layers/attention.py:376-380, layers/mlp.py:30-45). */
+int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1, const float* b1,
+                            const void* W2, const float* b2, int hidden, float* h, long long ldh, int M, int D,
+                            const float* gate1, const float* shift2, const float* scale2, const float* gate2,
+                            long long mod_ld, int rows_per_mod, float eps, float* stats_out, void* stream);
+
 /* Scratch for split-K (fp32 partial tiles of long contractions over few output tiles, e.g. the 8x8 / 4x4 UNet convs).
  * Device pointer, 16-byte aligned, caller-owned; launches that use it must be ordered on one stream.  Optional: without
  * it every contraction runs unsplit. */

@@ -28,8 +28,9 @@ from tests.golden.make_fulllen import fulllen_inputs  # noqa: E402
 from tests.helpers import fixture_state_dict, oracle_model, product_model, rel_l2  # noqa: E402
 
 DEV = "cuda"
-#: final-sample tolerance after the full 1000-step loop (relative L2 on [0,1] images, bf16 path vs fp32 reference)
-FULL_TOL = {"c1": 5e-2, "c2": 5e-2, "c3": 5e-2}
+#: final-sample tolerance after the full 1000-step loop (relative L2 on [0,1] images, bf16 path vs fp32 reference).
+#: Measured on B200 (round 2, first GPU run): c2 1.4e-3 (worst row 1.8e-3), c1 2.1e-3 (2.3e-3), c3 1.7e-3 (1.8e-3).
+FULL_TOL = {"c1": 1e-2, "c2": 1e-2, "c3": 1e-2}
 BENCH_BATCH = {"c1": 64, "c2": 1024, "c3": 64}
 MEDIUM_TOL = 2e-2
 

@@ -490,6 +490,43 @@ def test_sampler_step_continuous_bit_exact(ops, pred, sampler, N):
         assert torch.equal(out.cpu(), ref), (sampler, pred, N, i, float((out.cpu() - ref).abs().max()))
 
 
+def _ln(x, eps=1e-6):
+    return F.layer_norm(x, (x.shape[-1],), eps=eps)
+
+
+@pytest.mark.parametrize("B", [64, 13, 1024])
+def test_dit_proj_mlp_fused(ops, B):
+    """xd_dit_proj_mlp_bf16_tc (proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual in one
+    kernel) against fp32 torch math on the same bf16-rounded operands (score_networks/dit.py:46-59); B = 13 leaves a
+    ragged last 256-row tile.  The emitted (mean, rstd) row statistics are checked against torch too."""
+    g = torch.Generator().manual_seed(100 + B)
+    T, D, Hd = 16, 384, 1536
+    M = B * T
+    o = bf(torch.randn(M, D, generator=g))
+    h = torch.randn(M, D, generator=g) * 1.5 + 0.3
+    wp = bf(torch.randn(D, D, generator=g) / math.sqrt(D))
+    w1 = bf(torch.randn(Hd, D, generator=g) / math.sqrt(D))
+    w2 = bf(torch.randn(D, Hd, generator=g) / math.sqrt(Hd))
+    bp, b1, b2 = (torch.randn(n, generator=g) * 0.1 for n in (D, Hd, D))
+    mod = torch.randn(B, 6 * D, generator=g) * 0.5
+    g1, s2, sc2, g2 = (mod[:, i * D:(i + 1) * D] for i in (2, 3, 4, 5))
+    rep = lambda t: t.repeat_interleave(T, dim=0)
+    h1 = h + rep(g1) * (o.float() @ wp.float().T + bp)
+    a = bf(_ln(h1) * (1 + rep(sc2)) + rep(s2)).float()
+    u = bf(F.gelu(a @ w1.float().T + b1, approximate="tanh")).float()
+    ref = h1 + rep(g2) * (u @ w2.float().T + b2)
+    hd = h.to(DEV)
+    md = mod.to(DEV)
+    g1d, s2d, sc2d, g2d = (md[:, i * D:(i + 1) * D] for i in (2, 3, 4, 5))
+    stats = torch.zeros(M, 2, device=DEV)
+    torch.ops.xdb200.dit_proj_mlp(o.to(DEV), wp.to(DEV), bp.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), hd,
+                                  g1d, s2d, sc2d, g2d, T, 1e-6, stats)
+    assert rel_l2(hd, ref) < 3e-3, rel_l2(hd, ref)
+    mean, var = ref.mean(1), ref.var(1, unbiased=False)
+    assert float((stats[:, 0].cpu() - mean).abs().max()) < 2e-3
+    assert rel_l2(stats[:, 1], torch.rsqrt(var + 1e-6)) < 2e-3
+
+
 def test_schedule_advance_and_misc(ops):
     idx = torch.zeros(1, dtype=torch.int32, device=DEV)
     tab = torch.arange(1000, dtype=torch.int64, device=DEV) * 3

@@ -7,7 +7,7 @@ NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${NVCC_EXTRA:-}"
 mkdir -p ../../build/obj
 pids=()
-for f in abi gemm_tc simt norm attention attention_tc elementwise step; do
+for f in abi gemm_tc dit_block simt norm attention attention_tc elementwise step; do
   $NVCC $FLAGS -c $f.cu -o ../../build/obj/$f.o &
   pids+=($!)
 done

@@ -1,0 +1,463 @@
+// Fused DiT half-blocks on tcgen05 / TMEM / TMA (sm_100a), hidden size D = 384.
+//
+// A 128-row tile of the token stream (8 images x 16 tokens) never interacts with another tile inside a DiT block
+// (LayerNorm is per token, attention per image, adaLN modulation per image), so a CTA pair can walk a 256-row tile
+// through several operators without a grid-wide dependency and without the intermediates leaving the SM.
+//
+// dit_mlp_kernel  (xd_dit_proj_mlp_bf16_tc):   reference score_networks/dit.py:46-59, layers/mlp.py:30-45
+//     h1 = h + gate1 * (O Wp^T + bp)                         attention output projection, gated residual
+//     a  = bf16( LN(h1) * (1 + scale2) + shift2 )            LayerNorm (no affine) + adaLN modulate
+//     u  = bf16( gelu_tanh(a W1^T + b1) )                    fc1, 128 hidden columns at a time: stays in shared memory
+//     h  = h1 + gate2 * (u W2^T + b2)                        fc2 accumulates over the hidden chunks in TMEM
+//     stats[m] = (mean, rstd) of the new h rows              consumed by the next block's LayerNorm (no second pass)
+//   replaces 4 launches (proj GEMM, LayerNorm-modulate, fc1 GEMM, fc2 GEMM) and the 16384 x 1536 bf16 round trip.
+//
+// One cluster of two CTAs per 256-row tile, tcgen05 cta_group::2 (each CTA owns 128 rows of every A operand and stages
+// HALF of every weight tile; the leader issues M = 256 MMAs).  TMEM (512 columns per CTA): [0, 384) = acc2 (proj result,
+// then h1 parked for the LayerNorm second pass, then the fc2 accumulator), [384, 512) = acc1 (one fc1 chunk).
+// Warp roles (320 threads): warp 0 TMA producer (weight tiles through a 5-slot ring, in the exact order the MMA warp
+// consumes them), warp 1 MMA issuer (leader CTA), warps 2..9 epilogue (TMEM lane quadrant = warp & 3, column half =
+// (warp - 2) / 4), all in the TMEM-native layout lane = row.
+// Steady state of the MMA queue: fc1(c + 1), fc2(c), fc1(c + 2), ... -- the GELU of chunk c runs while fc1(c + 1) is
+// on the tensor pipe, so the single acc1 buffer costs one bubble at the start only.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+using namespace tcx;
+
+constexpr int DM = 384;                     // model width
+constexpr int KB = DM / 64;                 // k-blocks of the panel (6)
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int A_BYTES = 128 * 64 * 2;       // one 128-row x 64-column bf16 operand tile (128-byte swizzled rows)
+constexpr int PANEL_BYTES = KB * A_BYTES;   // 96 KB: O (proj A operand), then a = LN2(h1) (fc1 A operand)
+constexpr int HID_BYTES = 2 * A_BYTES;      // one fc1 chunk: 128 rows x 128 hidden columns
+constexpr int SLOT_BYTES = 96 * 128;        // largest per-CTA weight tile: 96 rows x 64 columns
+constexpr int RING = 5;
+constexpr int MISC_BYTES = 4096;            // barriers, tmem pointer, per-row statistics exchange
+constexpr int SMEM_BYTES = 1024 + PANEL_BYTES + 2 * HID_BYTES + RING * SLOT_BYTES + MISC_BYTES;
+constexpr int ACC1_COL = 384;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+struct MlpParams {
+    int M, hidden, rows_per_mod;
+    long long mod_ld;
+    const float *bp, *b1, *b2;
+    const float *gate1, *shift2, *scale2, *gate2;
+    float2* stats_out;
+    float eps;
+};
+
+// Warp-level pass over this warp's 32 rows x 192 columns of acc2 (six 32-column chunks):
+//   v = res + gate * (acc + bias),  res = the h box (TMA load, prefetched one chunk ahead), v -> h (TMA store),
+// optionally v -> TMEM (parked for a second pass), and the shifted sums  s = sum(v - c0), qq = sum((v - c0)^2).
+template <bool TO_TMEM>
+__device__ __forceinline__ void gated_residual_pass(const CUtensorMap* tmH, uint32_t wbuf_a, uint64_t* rbar, uint32_t& cc,
+                                                    uint32_t t_addr, int m0w, int col_base, const float* bias,
+                                                    const float* gp, int lane, float& c0, float& s, float& qq) {
+    if (lane == 0) {
+        ptx::bulk_wait_read<1>();                        // the store that last read this box (chunk cc - 2)
+        const uint32_t b = cc & 1;
+        ptx::mbar_arrive_expect_tx(&rbar[b], 4096);
+        ptx::tma_load_2d_u32(wbuf_a + b * 4096, tmH, ptx::smem_u32(&rbar[b]), col_base, m0w);
+    }
+    __syncwarp();
+    uint32_t rr[2][32];
+    ptx::tmem_ld_32x32(t_addr, rr[0]);
+    s = 0.f; qq = 0.f; c0 = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 6; ++ci, ++cc) {
+        const int nc = col_base + ci * 32;
+        const uint32_t b = cc & 1;
+        const uint32_t wb = wbuf_a + b * 4096;
+        uint32_t* r = rr[ci & 1];
+        if (lane == 0 && ci + 1 < 6) {                   // prefetch the next h box into the other buffer
+            ptx::bulk_wait_read<0>();
+            ptx::mbar_arrive_expect_tx(&rbar[b ^ 1], 4096);
+            ptx::tma_load_2d_u32(wbuf_a + (b ^ 1) * 4096, tmH, ptx::smem_u32(&rbar[b ^ 1]), nc + 32, m0w);
+        }
+        ptx::tmem_ld_wait();
+        if (ci + 1 < 6) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, rr[(ci + 1) & 1]);
+        ptx::mbar_wait(&rbar[b], (cc >> 1) & 1);
+        const uint32_t rowa = wb + lane * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                    // 16 columns per half
+            uint4 rs[4];
+            float4 g[4], bq[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                g[jj] = __ldg(reinterpret_cast<const float4*>(gp + nc) + 4 * h + jj);
+                bq[jj] = __ldg(reinterpret_cast<const float4*>(bias + nc) + 4 * h + jj);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) rs[jj] = ptx::lds128(rowa + (((4 * h + jj) ^ (lane & 7)) << 4));
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c = 16 * h + 4 * jj;
+                float v0 = fmaf(__uint_as_float(r[c]) + bq[jj].x, g[jj].x, __uint_as_float(rs[jj].x));
+                float v1 = fmaf(__uint_as_float(r[c + 1]) + bq[jj].y, g[jj].y, __uint_as_float(rs[jj].y));
+                float v2 = fmaf(__uint_as_float(r[c + 2]) + bq[jj].z, g[jj].z, __uint_as_float(rs[jj].z));
+                float v3 = fmaf(__uint_as_float(r[c + 3]) + bq[jj].w, g[jj].w, __uint_as_float(rs[jj].w));
+                if (ci == 0 && h == 0 && jj == 0) c0 = v0;
+                const float d0 = v0 - c0, d1 = v1 - c0, d2 = v2 - c0, d3 = v3 - c0;
+                s += (d0 + d1) + (d2 + d3);
+                qq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, qq))));
+                rs[jj] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+                if (TO_TMEM) { r[c] = rs[jj].x; r[c + 1] = rs[jj].y; r[c + 2] = rs[jj].z; r[c + 3] = rs[jj].w; }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) ptx::sts128(rowa + (((4 * h + jj) ^ (lane & 7)) << 4), rs[jj]);
+        }
+        if (TO_TMEM) ptx::tmem_st_32x32(t_addr + ci * 32, r);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tmH, wb, nc, m0w);
+            ptx::bulk_commit();
+        }
+    }
+    if (TO_TMEM) ptx::tmem_st_wait();
+}
+
+// Combine the two column halves' shifted sums of a row (Chan's parallel formula; n = 192 each) -> mean, rstd.
+__device__ __forceinline__ void combine_stats(float2* stat_sm, int grp, int row, int q, float c0, float s, float qq, float eps,
+                                              float& mean, float& rstd) {
+    const float n = 192.0f;
+    const float mh = c0 + s / n;
+    const float m2h = fmaxf(qq - s * s / n, 0.f);
+    stat_sm[grp * 128 + row] = make_float2(mh, m2h);
+    ptx::named_bar_sync(1 + q, 64);
+    const float2 o = stat_sm[(grp ^ 1) * 128 + row];
+    mean = 0.5f * (mh + o.x);
+    const float dm = mh - o.x;
+    const float m2 = m2h + o.y + dm * dm * (n * 0.5f);
+    rstd = rsqrtf(m2 / (2.0f * n) + eps);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWp,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmH, const MlpParams p) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* panel = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* hid = panel + PANEL_BYTES;                 // [2][HID_BYTES]; aliased by the epilogue staging boxes
+    uint8_t* ring = hid + 2 * HID_BYTES;
+    uint8_t* misc = ring + RING * SLOT_BYTES;
+    uint64_t* ring_full = reinterpret_cast<uint64_t*>(misc);     // [RING]
+    uint64_t* ring_empty = ring_full + RING;                     // [RING]
+    uint64_t* panel_full = ring_empty + RING;                    // [KB]
+    uint64_t* acc2_full = panel_full + KB;                       // completes twice: proj done, fc2 done
+    uint64_t* a_full = acc2_full + 1;                            // LN2 panel written (16 warp arrivals at the leader)
+    uint64_t* acc1_full = a_full + 1;
+    uint64_t* acc1_empty = acc1_full + 1;                        // 16 warp arrivals at the leader
+    uint64_t* hid_full = acc1_empty + 1;                         // [2], 16 warp arrivals at the leader
+    uint64_t* hid_empty = hid_full + 2;                          // [2], tcgen05.commit multicast
+    uint64_t* res_bar = hid_empty + 2;                           // [EPI_WARPS][2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+    float2* stat_sm = reinterpret_cast<float2*>(misc + 1024);    // [2][128]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)ptx::cluster_ctarank();
+    const int tile = blockIdx.x >> 1;
+    const int m0 = tile * 256 + rank * 128;                      // this CTA's first row
+    const int nch = p.hidden / 128;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmO);
+        ptx::prefetch_tmap(&tmWp);
+        ptx::prefetch_tmap(&tmW1);
+        ptx::prefetch_tmap(&tmW2);
+        ptx::prefetch_tmap(&tmH);
+        for (int s = 0; s < RING; ++s) {
+            ptx::mbar_init(&ring_full[s], 2);
+            ptx::mbar_init(&ring_empty[s], 1);
+        }
+        for (int k = 0; k < KB; ++k) ptx::mbar_init(&panel_full[k], 2);
+        ptx::mbar_init(acc2_full, 1);
+        ptx::mbar_init(a_full, 2 * EPI_WARPS);
+        ptx::mbar_init(acc1_full, 1);
+        ptx::mbar_init(acc1_empty, 2 * EPI_WARPS);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&hid_full[b], 2 * EPI_WARPS);
+            ptx::mbar_init(&hid_empty[b], 1);
+        }
+        for (int k = 0; k < 2 * EPI_WARPS; ++k) ptx::mbar_init(&res_bar[k], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_2sm(tmem_ptr, 512);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs: own rows / own tile halves)
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                ptx::mbar_arrive_expect_tx_leader(&panel_full[kb], A_BYTES);
+                ptx::tma_load_2d_2sm(panel + kb * A_BYTES, &tmO, &panel_full[kb], kb * 64, m0);
+            }
+            int s = 0;
+            uint32_t ph = 0;
+            auto load_b = [&](const CUtensorMap* tm, uint32_t bytes, int ck, int cn) {
+                ptx::mbar_wait(&ring_empty[s], ph ^ 1);
+                ptx::mbar_arrive_expect_tx_leader(&ring_full[s], bytes);
+                ptx::tma_load_2d_2sm(ring + s * SLOT_BYTES, tm, &ring_full[s], ck, cn);
+                if (++s == RING) { s = 0; ph ^= 1; }
+            };
+            for (int kb = 0; kb < KB; ++kb)
+                for (int nh = 0; nh < 2; ++nh) load_b(&tmWp, 96 * 128, kb * 64, nh * 192 + rank * 96);
+            for (int it = 0; it <= nch; ++it) {
+                if (it < nch)
+                    for (int kb = 0; kb < KB; ++kb) load_b(&tmW1, 64 * 128, kb * 64, it * 128 + rank * 64);
+                if (it >= 1)
+                    for (int kb2 = 0; kb2 < 2; ++kb2)
+                        for (int nh = 0; nh < 2; ++nh) load_b(&tmW2, 96 * 128, (it - 1) * 128 + kb2 * 64, nh * 192 + rank * 96);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop)
+        if (rank == 0) {
+            constexpr uint32_t idesc192 = ptx::idesc_bf16_f32(256, 192);
+            constexpr uint32_t idesc128 = ptx::idesc_bf16_f32(256, 128);
+            const uint64_t d_panel = ptx::smem_desc_sw128(ptx::smem_u32(panel));
+            const uint64_t d_hid = ptx::smem_desc_sw128(ptx::smem_u32(hid));
+            const uint64_t d_ring = ptx::smem_desc_sw128(ptx::smem_u32(ring));
+            int s = 0;
+            uint32_t ph = 0;
+            // four K = 16 steps on one (A tile, B slot); frees the slot when they have completed
+            auto mma_block = [&](uint32_t tmem_d, uint64_t da, uint32_t idesc, bool fresh) {
+                ptx::mbar_wait(&ring_full[s], ph);
+                ptx::tc_fence_after();
+                const uint64_t db = d_ring + (uint64_t)((s * SLOT_BYTES) >> 4);
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
+                    ptx::umma_commit_2sm(&ring_empty[s]);
+                }
+                __syncwarp();
+                if (++s == RING) { s = 0; ph ^= 1; }
+            };
+            // ---- proj: acc2 = O Wp^T
+            for (int kb = 0; kb < KB; ++kb) {
+                ptx::mbar_wait(&panel_full[kb], 0);
+                for (int nh = 0; nh < 2; ++nh)
+                    mma_block(tmem_base + nh * 192, d_panel + (uint64_t)((kb * A_BYTES) >> 4), idesc192, kb == 0);
+            }
+            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full);
+            __syncwarp();
+            // ---- MLP: fc1(it), fc2(it - 1)
+            ptx::mbar_wait(a_full, 0);
+            ptx::tc_fence_after();
+            for (int it = 0; it <= nch; ++it) {
+                if (it < nch) {
+                    if (it >= 1) {
+                        ptx::mbar_wait(acc1_empty, (it - 1) & 1);
+                        ptx::tc_fence_after();
+                    }
+                    for (int kb = 0; kb < KB; ++kb)
+                        mma_block(tmem_base + ACC1_COL, d_panel + (uint64_t)((kb * A_BYTES) >> 4), idesc128, kb == 0);
+                    if (ptx::elect_one()) ptx::umma_commit_2sm(acc1_full);
+                    __syncwarp();
+                }
+                if (it >= 1) {
+                    const int c = it - 1, b = c & 1;
+                    ptx::mbar_wait(&hid_full[b], (c >> 1) & 1);
+                    ptx::tc_fence_after();
+                    for (int kb2 = 0; kb2 < 2; ++kb2)
+                        for (int nh = 0; nh < 2; ++nh)
+                            mma_block(tmem_base + nh * 192, d_hid + (uint64_t)((b * HID_BYTES + kb2 * A_BYTES) >> 4), idesc192,
+                                      c == 0 && kb2 == 0);
+                    if (ptx::elect_one()) ptx::umma_commit_2sm(&hid_empty[b]);
+                    __syncwarp();
+                }
+            }
+            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full);
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        const int e_warp = warp - 2;
+        const int grp = e_warp >> 2;                    // column half
+        const int q = warp & 3;                         // TMEM lane quadrant
+        const int row = q * 32 + lane;                  // row inside this CTA's 128
+        const int m0w = m0 + q * 32;
+        const int gm = min(m0 + row, p.M - 1);
+        const long long mod_off = (long long)(gm / p.rows_per_mod) * p.mod_ld;
+        const uint32_t wbuf_a = ptx::smem_u32(hid + e_warp * 8192);
+        uint64_t* rbar = res_bar + 2 * e_warp;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int col_base = grp * 192;
+        uint32_t cc = 0;
+        float c0, s, qq, mean, rstd;
+
+        // ---- h1 = h + gate1 * (acc2 + bp) -> h (global) and TMEM; LayerNorm statistics
+        ptx::mbar_wait(acc2_full, 0);
+        ptx::tc_fence_after();
+        gated_residual_pass<true>(&tmH, wbuf_a, rbar, cc, t_lane + col_base, m0w, col_base, p.bp, p.gate1 + mod_off, lane, c0, s, qq);
+        combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
+        // ---- second pass over the parked h1: a = LN(h1) * (1 + scale2) + shift2 -> bf16 panel (fc1's A operand)
+        {
+            const float* scp = p.scale2 + mod_off;
+            const float* shp = p.shift2 + mod_off;
+            const uint32_t panel_a = ptx::smem_u32(panel);
+            uint32_t rr[2][32];
+            ptx::tmem_ld_32x32(t_lane + col_base, rr[0]);
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci) {
+                const int col = col_base + ci * 32;
+                uint32_t* r = rr[ci & 1];
+                ptx::tmem_ld_wait();
+                if (ci + 1 < 6) ptx::tmem_ld_32x32(t_lane + col + 32, rr[(ci + 1) & 1]);
+                const uint32_t rowa = panel_a + (col >> 6) * A_BYTES + row * 128;
+                const int j0 = (col & 63) >> 3;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scp + col) + 2 * jj);
+                    const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scp + col) + 2 * jj + 1);
+                    const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shp + col) + 2 * jj);
+                    const float4 sh1 = __ldg(reinterpret_cast<const float4*>(shp + col) + 2 * jj + 1);
+                    const int c = 8 * jj;
+                    const float y0 = fmaf((__uint_as_float(r[c]) - mean) * rstd, 1.0f + sc0.x, sh0.x);
+                    const float y1 = fmaf((__uint_as_float(r[c + 1]) - mean) * rstd, 1.0f + sc0.y, sh0.y);
+                    const float y2 = fmaf((__uint_as_float(r[c + 2]) - mean) * rstd, 1.0f + sc0.z, sh0.z);
+                    const float y3 = fmaf((__uint_as_float(r[c + 3]) - mean) * rstd, 1.0f + sc0.w, sh0.w);
+                    const float y4 = fmaf((__uint_as_float(r[c + 4]) - mean) * rstd, 1.0f + sc1.x, sh1.x);
+                    const float y5 = fmaf((__uint_as_float(r[c + 5]) - mean) * rstd, 1.0f + sc1.y, sh1.y);
+                    const float y6 = fmaf((__uint_as_float(r[c + 6]) - mean) * rstd, 1.0f + sc1.z, sh1.z);
+                    const float y7 = fmaf((__uint_as_float(r[c + 7]) - mean) * rstd, 1.0f + sc1.w, sh1.w);
+                    ptx::sts128(rowa + (((j0 + jj) ^ (row & 7)) << 4),
+                                make_uint4(f2_to_bf2(y0, y1), f2_to_bf2(y2, y3), f2_to_bf2(y4, y5), f2_to_bf2(y6, y7)));
+                }
+            }
+        }
+        ptx::fence_proxy_async();                        // generic-proxy panel writes -> visible to tcgen05.mma
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::bulk_wait_read<0>();         // staging boxes alias the hidden buffers: stores have read them
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(a_full);
+
+        // ---- fc1 chunks: u = gelu(acc1 + b1) -> bf16 hidden buffer (fc2's A operand)
+        const uint32_t hid_a = ptx::smem_u32(hid);
+        for (int c = 0; c < nch; ++c) {
+            const int b = c & 1;
+            ptx::mbar_wait(acc1_full, c & 1);
+            ptx::tc_fence_after();
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64, r0);
+            ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64 + 32, r1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(acc1_empty);
+            ptx::mbar_wait(&hid_empty[b], ((c >> 1) & 1) ^ 1);
+            const uint32_t hb = hid_a + b * HID_BYTES + grp * A_BYTES + row * 128;
+            const float* bptr = p.b1 + c * 128 + grp * 64;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t* r = j < 4 ? r0 + 8 * j : r1 + 8 * (j - 4);
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(bptr) + 2 * j);
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bptr) + 2 * j + 1);
+                float v[8];
+                bias_act2<XD_ACT_GELU_TANH>(r[0], r[1], __float_as_uint(ba.x), __float_as_uint(ba.y), v[0], v[1]);
+                bias_act2<XD_ACT_GELU_TANH>(r[2], r[3], __float_as_uint(ba.z), __float_as_uint(ba.w), v[2], v[3]);
+                bias_act2<XD_ACT_GELU_TANH>(r[4], r[5], __float_as_uint(bb.x), __float_as_uint(bb.y), v[4], v[5]);
+                bias_act2<XD_ACT_GELU_TANH>(r[6], r[7], __float_as_uint(bb.z), __float_as_uint(bb.w), v[6], v[7]);
+                ptx::sts128(hb + ((j ^ (row & 7)) << 4),
+                            make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]), f2_to_bf2(v[6], v[7])));
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&hid_full[b]);
+        }
+
+        // ---- h = h1 + gate2 * (acc2 + b2); statistics of the new rows for the next block's LayerNorm
+        if (lane == 0) ptx::bulk_wait<0>();              // this warp's h1 stores have landed before they are re-read
+        __syncwarp();
+        ptx::mbar_wait(acc2_full, 1);
+        ptx::tc_fence_after();
+        gated_residual_pass<false>(&tmH, wbuf_a, rbar, cc, t_lane + col_base, m0w, col_base, p.b2, p.gate2 + mod_off, lane, c0, s, qq);
+        combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
+        if (p.stats_out && grp == 0 && m0 + row < p.M) p.stats_out[m0 + row] = make_float2(mean, rstd);
+        if (lane == 0) ptx::bulk_wait<0>();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+int tmap_2d_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    return make_tmap(tm, ptr, 2, dims, str, box);
+}
+
+}  // namespace
+
+// h <- h1 + gate2 * (gelu(LNmod(h1) W1^T + b1) W2^T + b2),  h1 = h + gate1 * (O Wp^T + bp)   (in place on h, fp32)
+// LNmod(x)[m, :] = LN(x[m, :]) * (1 + scale2[m / rows_per_mod]) + shift2[m / rows_per_mod]; gate / shift / scale rows are
+// mod_ld floats apart.  stats_out (optional) receives (mean, rstd) of every new h row.  D = 384.
+extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
+                                       const float* b1, const void* W2, const float* b2, int hidden, float* h,
+                                       long long ldh, int M, int D, const float* gate1, const float* shift2,
+                                       const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
+                                       float eps, float* stats_out, void* stream) {
+    XD_CHECK_ARG(O && Wp && bp && W1 && b1 && W2 && b2 && h && gate1 && shift2 && scale2 && gate2 && M > 0);
+    XD_CHECK_ARG(D == DM && hidden % 128 == 0 && hidden >= 128 && rows_per_mod > 0);
+    XD_CHECK_ARG(ldo % 8 == 0 && ldh % 4 == 0 && mod_ld % 4 == 0);
+    XD_CHECK_ARG(aligned16(O) && aligned16(Wp) && aligned16(W1) && aligned16(W2) && aligned16(h) && aligned16(bp) &&
+                 aligned16(b1) && aligned16(b2) && aligned16(gate1) && aligned16(shift2) && aligned16(scale2) &&
+                 aligned16(gate2) && (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0);
+    CUtensorMap tO, tWp, tW1, tW2, tH;
+    int rc;
+    if ((rc = tmap_2d_bf16(&tO, O, M, DM, ldo, 128))) return rc;
+    if ((rc = tmap_2d_bf16(&tWp, Wp, DM, DM, DM, 96))) return rc;
+    if ((rc = tmap_2d_bf16(&tW1, W1, hidden, DM, DM, 64))) return rc;
+    if ((rc = tmap_2d_bf16(&tW2, W2, DM, hidden, hidden, 96))) return rc;
+    if ((rc = tmap_epi(&tH, h, M, DM, ldh, true))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(dit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
+            return XD_ERR_CUDA;
+        }
+        configured = true;
+    }
+    MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
+                reinterpret_cast<float2*>(stats_out), eps};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * ((M + 255) / 256));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = xd_pdl_enabled_gemm() ? 2 : 1;
+    if (cudaLaunchKernelEx(&cfg, dit_mlp_kernel, tO, tWp, tW1, tW2, tH, p) != cudaSuccess) {
+        xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        return XD_ERR_CUDA;
+    }
+    return XD_OK;
+}

@@ -21,11 +21,24 @@ class MultiHeadSelfAttention(torch.nn.Module, Packed):
         self.qkv = torch.nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = torch.nn.Linear(dim, dim)
 
+    def weights(self):
+        return self.packed("w", (self.qkv.weight, self.proj.weight),
+                           lambda: (bf16_weight(self.qkv.weight), bf16_weight(self.proj.weight)))
+
+    def attend(self, x, tokens: int, ln=None):
+        """softmax(q k^T / sqrt(d)) v for every head, WITHOUT the output projection: bf16 [B*T, D]."""
+        wq, _ = self.weights()
+        M, D = x.shape
+        B, H, d = M // tokens, self.num_heads, self.head_dim
+        qkv = ops.ln_linear(x, ln[0], ln[1], ln[2], wq, self.qkv.bias) if ln is not None else ops.linear(x, wq, self.qkv.bias)
+        qkv = qkv.view(B, tokens, 3, H, d)
+        q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        return ops.attention(q, k, v, self.scale).permute(0, 2, 1, 3).reshape(M, D)
+
     def forward(self, x_bf16, tokens: int, ln=None, **epilogue):
         """x bf16 [B*T, D]; ``epilogue`` (gate / residual / out) is fused into the proj GEMM.
         ``ln=(shift, scale, rows_per_mod)``: x is the fp32 residual stream, LayerNorm + modulate is fused into qkv."""
-        wq, wp = self.packed("w", (self.qkv.weight, self.proj.weight),
-                             lambda: (bf16_weight(self.qkv.weight), bf16_weight(self.proj.weight)))
+        wq, wp = self.weights()
         M, D = x_bf16.shape
         B, H, d = M // tokens, self.num_heads, self.head_dim
         if ln is not None:

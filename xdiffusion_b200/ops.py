@@ -106,6 +106,26 @@ def _ln_gemm(x, shift, scale, rows_per_mod, eps, w, bias, act, out):
                                              out.stride(0), _stream()), "xd_ln_gemm_bf16_tc")
 
 
+@_op("dit_proj_mlp(Tensor o, Tensor wp, Tensor bp, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor(a!) h, Tensor gate1, "
+     "Tensor shift2, Tensor scale2, Tensor gate2, int rows_per_mod, float eps, Tensor(b!)? stats) -> ()")
+def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, rows_per_mod, eps, stats):
+    """Fused proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual, in place on h (fp32 [M, 384])."""
+    _cuda(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, stats)
+    M, D = h.shape
+    hidden = w1.shape[0]
+    assert o.dtype == torch.bfloat16 and o.shape == (M, D) and o.stride(1) == 1 and h.dtype == torch.float32 and h.stride(1) == 1
+    assert wp.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and wp.shape == (D, D)
+    assert w1.shape == (hidden, D) and w2.shape == (D, hidden) and all(w.dtype == torch.bfloat16 for w in (wp, w1, w2))
+    mods = (gate1, shift2, scale2, gate2)
+    assert all(t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) == gate1.stride(0) for t in mods)
+    assert stats is None or (stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= 2 * M)
+    _lib.check(_lib.lib().xd_dit_proj_mlp_bf16_tc(_p(o), o.stride(0), _p(wp), _p(bp), _p(w1), _p(b1), _p(w2), _p(b2), hidden,
+                                                  _p(h), h.stride(0), M, D, _p(gate1), _p(shift2), _p(scale2), _p(gate2),
+                                                  gate1.stride(0), rows_per_mod, eps, _p(stats), _stream()),
+               "xd_dit_proj_mlp_bf16_tc")
+    _count()
+
+
 @_op("gemm(Tensor a, Tensor? a2, Tensor w, Tensor? bias, int act, Tensor? gate, int gate_rows, "
      "Tensor? residual, Tensor(a!) out, int force_bn) -> ()")
 def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):

@@ -7,6 +7,7 @@ block-independent), then per block LayerNorm+modulate -> QKV GEMM -> fused atten
 with gate*+residual epilogue -> LayerNorm+modulate -> fc1 GEMM (+GELU) -> fc2 GEMM (gate*+residual).
 The token residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation in TMEM.
 """
+import os
 from typing import Dict
 
 import torch
@@ -17,6 +18,10 @@ from ..layers.embedding import PatchEmbed
 from ..layers.mlp import Mlp
 from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
 from ..utils import instantiate_from_config, instantiate_partial_from_config
+
+
+# Fused half-block kernels (csrc/dit_block.cu); XDB200_DIT_FUSED=0 runs one kernel per operator (round-1 path).
+FUSED_BLOCK = os.environ.get("XDB200_DIT_FUSED", "1") == "1"
 
 
 class DiTBlock(torch.nn.Module):
@@ -127,6 +132,15 @@ class DiT(torch.nn.Module, Packed):
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
+            if FUSED_BLOCK and D == 384 and blk.mlp.act == ops.ACT_GELU and ops.MATMUL_BACKEND == "tc":
+                # one kernel for proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual
+                # (csrc/dit_block.cu): the [B*T, 4D] MLP activation never leaves the SM
+                o = blk.attn.attend(h, T, ln=(s1, sc1, T))
+                _, wp = blk.attn.weights()
+                w1, w2 = blk.mlp.weights()
+                torch.ops.xdb200.dit_proj_mlp(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h,
+                                              g1, s2, sc2, g2, T, 1e-6, None)
+                continue
             # ln=: LayerNorm + modulate feeding qkv / fc1 (layernorm_modulate kernel; fused into the GEMM with XDB200_LN_FUSED=1)
             blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))
             blk.mlp(h, ln=(s2, sc2, T), gate=g2, gate_rows=T, residual=h, out=h)        # h += g2 * mlp(modulate(norm(h)))
