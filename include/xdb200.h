@@ -62,6 +62,17 @@ int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const 
                             const float* gate1, const float* shift2, const float* scale2, const float* gate2,
                             long long mod_ld, int rows_per_mod, float eps, float* stats_out, void* stream);
 
+/* Fused first half of a DiT block (D = 384, 16 tokens per image, head dim 64): LayerNorm-modulate + QKV projection + softmax
+ * attention in one kernel, one CTA pair per (256 token rows, group of heads):
+ *   a = bf16(LN(h) * (1 + scale) + shift);  [q_i | k_i | v_i] = a Wh_i^T + bias_i;  out[:, 64i : 64i + 64] = softmax(q_i k_i^T * sm_scale) v_i
+ * Wh bf16 [heads * 192, D] and bias fp32 [heads * 192] are the reference's qkv Linear re-packed per head as [q | k | v]
+ * (64 rows each); stats = (mean, rstd) per row of h as emitted by xd_dit_proj_mlp_bf16_tc, or NULL (computed here).
+ * Replaces `attn(modulate(norm1(x), shift_msa, scale_msa))` up to (not including) attn.proj
+ * (score_networks/dit.py:46-51, layers/attention.py:350-375). */
+int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats, const float* shift, const float* scale,
+                               long long mod_ld, int rows_per_mod, float eps, const void* Wh, const float* bias, int heads,
+                               int M, int D, float sm_scale, void* out, long long ldo, void* stream);
+
 /* Scratch for split-K (fp32 partial tiles of long contractions over few output tiles, e.g. the 8x8 / 4x4 UNet convs).
  * Device pointer, 16-byte aligned, caller-owned; launches that use it must be ordered on one stream.  Optional: without
  * it every contraction runs unsplit. */

@@ -527,6 +527,36 @@ def test_dit_proj_mlp_fused(ops, B):
     assert rel_l2(stats[:, 1], torch.rsqrt(var + 1e-6)) < 2e-3
 
 
+@pytest.mark.parametrize("B", [64, 13, 128, 1024])
+@pytest.mark.parametrize("with_stats", [False, True])
+def test_dit_ln_qkv_attention_fused(ops, B, with_stats):
+    """xd_dit_ln_qkv_attn_bf16_tc (LayerNorm-modulate + per-head qkv projection + softmax attention in one kernel) against
+    fp32 torch math on bf16-rounded operands (score_networks/dit.py:46-51, layers/attention.py:350-375).  B = 13: ragged
+    last tile; B = 128: heads spread over several CTA pairs (the small-M work split); B = 1024: benchmark shape."""
+    g = torch.Generator().manual_seed(200 + B)
+    T, D, H = 16, 384, 6
+    M = B * T
+    h = torch.randn(M, D, generator=g) * 1.5 + 0.3
+    wqkv = torch.randn(3 * D, D, generator=g) / math.sqrt(D)
+    bqkv = torch.randn(3 * D, generator=g) * 0.1
+    mod = torch.randn(B, 2 * D, generator=g) * 0.5
+    sh, sc = mod[:, :D], mod[:, D:]
+    rep = lambda t: t.repeat_interleave(T, dim=0)
+    a = bf(_ln(h) * (1 + rep(sc)) + rep(sh)).float()
+    qkv = bf(a @ bf(wqkv).float().T + bqkv).float().view(B, T, 3, H, 64)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(M, D)
+    wh = bf(wqkv).view(3, H, 64, D).permute(1, 0, 2, 3).reshape(3 * D, D).contiguous().to(DEV)
+    bh = bqkv.view(3, H, 64).permute(1, 0, 2).reshape(3 * D).contiguous().to(DEV)
+    md = mod.to(DEV)
+    stats = None
+    if with_stats:
+        stats = torch.stack([h.mean(1), torch.rsqrt(h.var(1, unbiased=False) + 1e-6)], 1).contiguous().to(DEV)
+    out = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.dit_attn(h.to(DEV), stats, md[:, :D], md[:, D:], T, 1e-6, wh, bh, H, 0.125, out)
+    assert rel_l2(out, ref) < 1e-2, rel_l2(out, ref)
+
+
 def test_schedule_advance_and_misc(ops):
     idx = torch.zeros(1, dtype=torch.int32, device=DEV)
     tab = torch.arange(1000, dtype=torch.int64, device=DEV) * 3

@@ -18,8 +18,8 @@
 // Warp roles (320 threads): warp 0 TMA producer (weight tiles through a 5-slot ring, in the exact order the MMA warp
 // consumes them), warp 1 MMA issuer (leader CTA), warps 2..9 epilogue (TMEM lane quadrant = warp & 3, column half =
 // (warp - 2) / 4), all in the TMEM-native layout lane = row.
-// Steady state of the MMA queue: fc1(c + 1), fc2(c), fc1(c + 2), ... -- the GELU of chunk c runs while fc1(c + 1) is
-// on the tensor pipe, so the single acc1 buffer costs one bubble at the start only.
+// Steady state of the MMA queue: fc1(c + 2), fc2(c), fc1(c + 3), fc2(c + 1), ... -- the GELU of chunk c + 1 runs while
+// fc1(c + 2) and fc2(c) are on the tensor pipe, so the single acc1 buffer costs bubbles at start-up only.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tc_common.cuh"
@@ -43,6 +43,10 @@ constexpr int RING = 5;
 constexpr int MISC_BYTES = 4096;            // barriers, tmem pointer, per-row statistics exchange
 constexpr int SMEM_BYTES = 1024 + PANEL_BYTES + 2 * HID_BYTES + RING * SLOT_BYTES + MISC_BYTES;
 constexpr int ACC1_COL = 384;
+// fc2(c) is issued FC2_LAG chunks behind fc1: with a lag of 1 the GELU of chunk c (TMEM load + bias + tanh + shared-memory
+// store, ~2500 clk) sits between fc1(c + 1) (1536 clk) and fc2(c) on the tensor pipe's critical path (measured 45.5 us per
+// launch); with a lag of 2 it has fc1(c + 1) + fc2(c - 1) = 3072 clk to finish and the pipe only waits at start-up.
+constexpr int FC2_LAG = 2;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 struct MlpParams {
@@ -219,12 +223,13 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             };
             for (int kb = 0; kb < KB; ++kb)
                 for (int nh = 0; nh < 2; ++nh) load_b(&tmWp, 96 * 128, kb * 64, nh * 192 + rank * 96);
-            for (int it = 0; it <= nch; ++it) {
+            for (int it = 0; it < nch + FC2_LAG; ++it) {
                 if (it < nch)
                     for (int kb = 0; kb < KB; ++kb) load_b(&tmW1, 64 * 128, kb * 64, it * 128 + rank * 64);
-                if (it >= 1)
+                if (it >= FC2_LAG)
                     for (int kb2 = 0; kb2 < 2; ++kb2)
-                        for (int nh = 0; nh < 2; ++nh) load_b(&tmW2, 96 * 128, (it - 1) * 128 + kb2 * 64, nh * 192 + rank * 96);
+                        for (int nh = 0; nh < 2; ++nh)
+                            load_b(&tmW2, 96 * 128, (it - FC2_LAG) * 128 + kb2 * 64, nh * 192 + rank * 96);
             }
         }
     } else if (warp == 1) {
@@ -258,10 +263,10 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             }
             if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full);
             __syncwarp();
-            // ---- MLP: fc1(it), fc2(it - 1)
+            // ---- MLP: fc1(it), fc2(it - FC2_LAG)
             ptx::mbar_wait(a_full, 0);
             ptx::tc_fence_after();
-            for (int it = 0; it <= nch; ++it) {
+            for (int it = 0; it < nch + FC2_LAG; ++it) {
                 if (it < nch) {
                     if (it >= 1) {
                         ptx::mbar_wait(acc1_empty, (it - 1) & 1);
@@ -272,8 +277,8 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                     if (ptx::elect_one()) ptx::umma_commit_2sm(acc1_full);
                     __syncwarp();
                 }
-                if (it >= 1) {
-                    const int c = it - 1, b = c & 1;
+                if (it >= FC2_LAG) {
+                    const int c = it - FC2_LAG, b = c & 1;
                     ptx::mbar_wait(&hid_full[b], (c >> 1) & 1);
                     ptx::tc_fence_after();
                     for (int kb2 = 0; kb2 < 2; ++kb2)
@@ -353,6 +358,8 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         const uint32_t hid_a = ptx::smem_u32(hid);
         for (int c = 0; c < nch; ++c) {
             const int b = c & 1;
+            if (lane < 2)                                // this chunk's 64 bias values (2 lines) into L1 before they are needed
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.b1 + c * 128 + grp * 64 + lane * 32));
             ptx::mbar_wait(acc1_full, c & 1);
             ptx::tc_fence_after();
             uint32_t r0[32], r1[32];
@@ -392,6 +399,342 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
         if (p.stats_out && grp == 0 && m0 + row < p.M) p.stats_out[m0 + row] = make_float2(mean, rstd);
         if (lane == 0) ptx::bulk_wait<0>();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+// =====================================================================================================================
+// dit_attn_kernel  (xd_dit_ln_qkv_attn_bf16_tc):   reference score_networks/dit.py:46-51, layers/attention.py:350-375
+//     a = bf16( LN(h) * (1 + scale1) + shift1 )                        LayerNorm (no affine) + adaLN modulate -> smem panel
+//     [q_h | k_h | v_h] = a Wqkv_h^T + b_h   for each head h           one 256 x 192 tcgen05 tile per head (weights packed per head)
+//     O[:, 64h : 64h + 64] = softmax(q_h k_h^T / sqrt(64)) v_h         per image (16 tokens): mma.sync m16n8k16 by the epilogue warps
+//   replaces 3 launches (LayerNorm-modulate, qkv GEMM, attention) and the [M, 1152] qkv round trip.
+// Work item = (256-row tile, group of heads): at small M the heads of a tile are spread over several CTA pairs.
+// TMEM: two 192-column accumulators (head i + 1 is on the tensor pipe while head i is drained and attended).
+constexpr int STAGE_BYTES = 4 * 3 * 4096;   // per TMEM lane quadrant: Q, K, V tiles of 32 rows x 64 columns bf16
+constexpr int RING_A = 6;
+constexpr int SMEM_A_BYTES = 1024 + PANEL_BYTES + STAGE_BYTES + RING_A * SLOT_BYTES + MISC_BYTES;
+static_assert(SMEM_A_BYTES <= 232448, "shared memory budget");
+
+struct AttnFParams {
+    int M, rows_per_mod, heads, heads_per_item, groups;
+    long long ldh, mod_ld, ldo;
+    const float* h;
+    const float2* stats;        // (mean, rstd) per row from the producer of h, or nullptr: computed here
+    const float *shift, *scale;
+    const float* bias;          // packed like the weights: [heads][q(64) | k(64) | v(64)]
+    bf16* out;
+    float eps, sm_scale;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One warp, one image: Q, K, V tiles of 16 rows x 64 columns bf16 in shared memory (128-byte rows, 16-byte chunk c of row r
+// at c ^ (r & 7)); O = softmax(scale * Q K^T) V is staged over the Q tile and stored as full 128-byte rows.  Same fragment
+// algebra as attention16_mma_kernel (attention.cu): the S accumulators are re-used as the A operand of P V.
+__device__ __forceinline__ void attend16(uint32_t aQ, uint32_t aK, uint32_t aV, float scale, bf16* op, long long ldo, int rows_ok,
+                                         int lane) {
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        {
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8, c = 2 * ks + (lane >> 4);
+            ldsm_x4(aQ + row * 128 + ((c ^ (row & 7)) << 4), a0, a1, a2, a3);
+        }
+        {
+            const int row = (lane & 7) + (lane >> 4) * 8, c = 2 * ks + ((lane >> 3) & 1);
+            ldsm_x4(aK + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
+        }
+        mma_bf16_16816(s0, a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s1, a0, a1, a2, a3, b2, b3);
+    }
+    float m_lo = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])), m_hi = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    const float c = scale * 1.4426950408889634f;
+    s0[0] = exp2f((s0[0] - m_lo) * c); s0[1] = exp2f((s0[1] - m_lo) * c); s1[0] = exp2f((s1[0] - m_lo) * c); s1[1] = exp2f((s1[1] - m_lo) * c);
+    s0[2] = exp2f((s0[2] - m_hi) * c); s0[3] = exp2f((s0[3] - m_hi) * c); s1[2] = exp2f((s1[2] - m_hi) * c); s1[3] = exp2f((s1[3] - m_hi) * c);
+    float l_lo = s0[0] + s0[1] + s1[0] + s1[1], l_hi = s0[2] + s0[3] + s1[2] + s1[3];
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const uint32_t pa0 = f2_to_bf2(s0[0], s0[1]), pa1 = f2_to_bf2(s0[2], s0[3]);
+    const uint32_t pa2 = f2_to_bf2(s1[0], s1[1]), pa3 = f2_to_bf2(s1[2], s1[3]);
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t b0, b1, b2, b3;
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8, cc = nt + (lane >> 4);
+        ldsm_x4_trans(aV + row * 128 + ((cc ^ (row & 7)) << 4), b0, b1, b2, b3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { o[nt][j] = 0.f; o[nt + 1][j] = 0.f; }
+        mma_bf16_16816(o[nt], pa0, pa1, pa2, pa3, b0, b1);
+        mma_bf16_16816(o[nt + 1], pa0, pa1, pa2, pa3, b2, b3);
+    }
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+    __syncwarp();                                         // every lane is done reading Q: stage O over it
+    {
+        const int r = lane >> 2, q4 = (lane & 3) * 4;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            ptx::sts32(aQ + r * 128 + ((nt ^ (r & 7)) << 4) + q4, f2_to_bf2(o[nt][0] * i_lo, o[nt][1] * i_lo));
+            ptx::sts32(aQ + (r + 8) * 128 + ((nt ^ ((r + 8) & 7)) << 4) + q4, f2_to_bf2(o[nt][2] * i_hi, o[nt][3] * i_hi));
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i, row = idx >> 3, cch = idx & 7;
+        const uint4 v = ptx::lds128(aQ + row * 128 + ((cch ^ (row & 7)) << 4));
+        if (row < rows_ok) *reinterpret_cast<uint4*>(op + (long long)row * ldo + cch * 8) = v;
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* panel = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage = panel + PANEL_BYTES;
+    uint8_t* ring = stage + STAGE_BYTES;
+    uint8_t* misc = ring + RING_A * SLOT_BYTES;
+    uint64_t* ring_full = reinterpret_cast<uint64_t*>(misc);     // [RING_A]
+    uint64_t* ring_empty = ring_full + RING_A;                   // [RING_A]
+    uint64_t* a_full = ring_empty + RING_A;                      // LN panel written (16 warp arrivals at the leader)
+    uint64_t* acc_full = a_full + 1;                             // [2]
+    uint64_t* acc_empty = acc_full + 2;                          // [2], 16 warp arrivals at the leader
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)ptx::cluster_ctarank();
+    const int cid = blockIdx.x >> 1;
+    const int tile = cid / p.groups, hg = cid - tile * p.groups;
+    const int m0 = tile * 256 + rank * 128;
+    const int hd0 = hg * p.heads_per_item;
+    const int nh = min(p.heads_per_item, p.heads - hd0);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmW);
+        for (int s = 0; s < RING_A; ++s) {
+            ptx::mbar_init(&ring_full[s], 2);
+            ptx::mbar_init(&ring_empty[s], 1);
+        }
+        ptx::mbar_init(a_full, 2 * EPI_WARPS);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&acc_full[b], 1);
+            ptx::mbar_init(&acc_empty[b], 2 * EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_2sm(tmem_ptr, 512);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // TMA producer: this CTA's 96 rows of every (head, k-block) weight tile
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nh; ++i)
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&ring_empty[s], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx_leader(&ring_full[s], SLOT_BYTES);
+                    ptx::tma_load_2d_2sm(ring + s * SLOT_BYTES, &tmW, &ring_full[s], kb * 64, (hd0 + i) * 192 + rank * 96);
+                    if (++s == RING_A) { s = 0; ph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {                                 // MMA issuer
+            constexpr uint32_t idesc192 = ptx::idesc_bf16_f32(256, 192);
+            const uint64_t d_panel = ptx::smem_desc_sw128(ptx::smem_u32(panel));
+            const uint64_t d_ring = ptx::smem_desc_sw128(ptx::smem_u32(ring));
+            int s = 0;
+            uint32_t ph = 0;
+            ptx::mbar_wait(a_full, 0);
+            ptx::tc_fence_after();
+            for (int i = 0; i < nh; ++i) {
+                const uint32_t buf = i & 1;
+                ptx::mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&ring_full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint64_t da = d_panel + (uint64_t)((kb * A_BYTES) >> 4);
+                    const uint64_t db = d_ring + (uint64_t)((s * SLOT_BYTES) >> 4);
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16_2sm(tmem_base + buf * 192, da + 2 * k, db + 2 * k, idesc192, (kb | k) ? 1u : 0u);
+                        ptx::umma_commit_2sm(&ring_empty[s]);
+                        if (kb == KB - 1) ptx::umma_commit_2sm(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++s == RING_A) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int e_warp = warp - 2;
+        const int grp = e_warp >> 2;
+        const int q = warp & 3;
+        // ---- LayerNorm + modulate of this CTA's 128 rows -> bf16 panel.  Warp e_warp owns rows e_warp*16 .. +15 (one image
+        // when rows_per_mod == 16); lane <-> columns (i * 32 + lane) * 4, eight rows per pass with all loads in flight.
+        {
+            const uint32_t panel_a = ptx::smem_u32(panel);
+            const int row0 = e_warp * 16;
+            float4 sc[3], sh[3];
+            int cur_mod = -1;
+            const int ldx = (int)p.ldh;
+            const unsigned rpm = (unsigned)p.rows_per_mod;
+            const int m_last = p.M - 1;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int rbase = row0 + pass * 8;
+                const int mb = m0 + rbase;
+                const int valid = p.M - mb;
+                const float* xb = p.h + (long long)mb * p.ldh + lane * 4;
+                float4 v[8][3];
+                float mean[8], rstd[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        v[rr][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rr < valid) v[rr][i] = *reinterpret_cast<const float4*>(xb + rr * ldx + i * 128);
+                    }
+                }
+                if (p.stats) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const float2 st = __ldg(p.stats + min(mb + rr, m_last));
+                        mean[rr] = st.x; rstd[rr] = st.y;
+                    }
+                } else {
+                    float red[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) acc += v[rr][i].x + v[rr][i].y + v[rr][i].z + v[rr][i].w;
+                        red[rr] = acc;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) red[rr] += __shfl_xor_sync(0xffffffffu, red[rr], o);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        mean[rr] = red[rr] / (float)DM;
+                        float qa = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float dx = v[rr][i].x - mean[rr], dy = v[rr][i].y - mean[rr], dz = v[rr][i].z - mean[rr],
+                                        dw = v[rr][i].w - mean[rr];
+                            qa += dx * dx + dy * dy + dz * dz + dw * dw;
+                        }
+                        red[rr] = qa;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) red[rr] += __shfl_xor_sync(0xffffffffu, red[rr], o);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) rstd[rr] = rsqrtf(red[rr] / (float)DM + p.eps);
+                }
+                const uint32_t a_lane = panel_a + (lane >> 4) * A_BYTES + ((lane & 1) << 3);
+                const uint32_t chunk = (lane & 15) >> 1;
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int r = rbase + rr;
+                    const int mod_row = (int)((unsigned)min(mb + rr, m_last) / rpm);
+                    if (mod_row != cur_mod) {            // warp-uniform; once per warp when rows_per_mod == 16
+                        cur_mod = mod_row;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const long long off = (long long)mod_row * p.mod_ld + (i * 32 + lane) * 4;
+                            sc[i] = __ldg(reinterpret_cast<const float4*>(p.scale + off));
+                            sh[i] = __ldg(reinterpret_cast<const float4*>(p.shift + off));
+                        }
+                    }
+                    const bool live = rr < valid;
+                    const uint32_t a_row = a_lane + r * 128 + ((chunk ^ (r & 7)) << 4);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float y0 = fmaf((v[rr][i].x - mean[rr]) * rstd[rr], 1.0f + sc[i].x, sh[i].x);
+                        const float y1 = fmaf((v[rr][i].y - mean[rr]) * rstd[rr], 1.0f + sc[i].y, sh[i].y);
+                        const float y2 = fmaf((v[rr][i].z - mean[rr]) * rstd[rr], 1.0f + sc[i].z, sh[i].z);
+                        const float y3 = fmaf((v[rr][i].w - mean[rr]) * rstd[rr], 1.0f + sc[i].w, sh[i].w);
+                        ptx::sts64(a_row + 2 * i * A_BYTES, live ? f2_to_bf2(y0, y1) : 0u, live ? f2_to_bf2(y2, y3) : 0u);
+                    }
+                }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(a_full);
+        }
+        // ---- per head: drain [q | k | v] (+ bias) into the quadrant's bf16 tiles, then one image per warp
+        const uint32_t st_a = ptx::smem_u32(stage) + q * (3 * 4096);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int img_row0 = m0 + q * 32 + grp * 16;
+        for (int i = 0; i < nh; ++i) {
+            const int hd = hd0 + i;
+            const uint32_t buf = i & 1;
+            const float* bptr = p.bias + hd * 192 + grp * 96;
+            if (lane < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(bptr + lane * 32));
+            ptx::mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t r[3][32];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ptx::tmem_ld_32x32(t_lane + buf * 192 + grp * 96 + j * 32, r[j]);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
+            // this warp's 96 columns = 12 chunks of 8: column (grp * 96 + 8 * j) -> tile (col / 64), chunk (col % 64) / 8
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int col = grp * 96 + 8 * j;
+                const uint32_t* rv = r[j >> 2] + 8 * (j & 3);
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(bptr) + 2 * j);
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bptr) + 2 * j + 1);
+                const uint4 pk = make_uint4(f2_to_bf2(__uint_as_float(rv[0]) + ba.x, __uint_as_float(rv[1]) + ba.y),
+                                            f2_to_bf2(__uint_as_float(rv[2]) + ba.z, __uint_as_float(rv[3]) + ba.w),
+                                            f2_to_bf2(__uint_as_float(rv[4]) + bb.x, __uint_as_float(rv[5]) + bb.y),
+                                            f2_to_bf2(__uint_as_float(rv[6]) + bb.z, __uint_as_float(rv[7]) + bb.w));
+                ptx::sts128(st_a + (col >> 6) * 4096 + lane * 128 + ((((col & 63) >> 3) ^ (lane & 7)) << 4), pk);
+            }
+            ptx::named_bar_sync(1 + q, 64);              // both column halves of the quadrant's 32 rows are staged
+            const uint32_t io = grp * 2048;              // image `grp` of the quadrant: rows 16 * grp ..
+            attend16(st_a + io, st_a + 4096 + io, st_a + 8192 + io, p.sm_scale,
+                     p.out + (long long)img_row0 * p.ldo + hd * 64, p.ldo, p.M - img_row0, lane);
+            ptx::named_bar_sync(1 + q, 64);              // the partner warp is done with the tiles before they are rewritten
+        }
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
@@ -456,6 +799,59 @@ extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void*
     cfg.attrs = attr;
     cfg.numAttrs = xd_pdl_enabled_gemm() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, dit_mlp_kernel, tO, tWp, tW1, tW2, tH, p) != cudaSuccess) {
+        xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        return XD_ERR_CUDA;
+    }
+    return XD_OK;
+}
+
+// O[m, 64h : 64h + 64] = softmax_per_image( q_h k_h^T / sqrt(64) ) v_h  with [q_h | k_h | v_h] = LNmod(h) Wqkv_h^T + b_h:
+// LayerNorm-modulate + QKV projection + attention of a DiT block in one kernel.  h fp32 [M, 384] (rows_per_mod = tokens per
+// image = 16), Wh bf16 [heads * 192, 384] and bias fp32 [heads * 192] packed per head as [q | k | v] (64 rows each), stats
+// (mean, rstd) per row or NULL (computed in the kernel), out bf16 [M, 384] with head h in columns [64h, 64h + 64).
+extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats, const float* shift,
+                                          const float* scale, long long mod_ld, int rows_per_mod, float eps, const void* Wh,
+                                          const float* bias, int heads, int M, int D, float sm_scale, void* out,
+                                          long long ldo, void* stream) {
+    XD_CHECK_ARG(h && shift && scale && Wh && bias && out && M > 0 && D == DM && heads * 64 == DM);
+    XD_CHECK_ARG(rows_per_mod == 16 && M % 16 == 0);                  // one image = 16 token rows = one attention problem
+    XD_CHECK_ARG(ldh % 4 == 0 && mod_ld % 4 == 0 && ldo % 8 == 0);
+    XD_CHECK_ARG(aligned16(h) && aligned16(shift) && aligned16(scale) && aligned16(Wh) && aligned16(bias) && aligned16(out) &&
+                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0);
+    CUtensorMap tW;
+    int rc;
+    if ((rc = tmap_2d_bf16(&tW, Wh, (long long)heads * 192, DM, DM, 96))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(dit_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A_BYTES) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
+            return XD_ERR_CUDA;
+        }
+        configured = true;
+    }
+    // heads of a tile are spread over `groups` CTA pairs when there are fewer tiles than SM pairs
+    const int tiles = (M + 255) / 256;
+    const int pairs = sm_count() / 2;
+    int groups = 1;
+    for (int g : {2, 3, 6})
+        if (heads % g == 0 && tiles * g <= pairs) groups = g;
+    AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
+                  shift, scale, bias, (bf16*)out, eps, sm_scale};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * tiles * groups);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_A_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = xd_pdl_enabled_gemm() ? 2 : 1;
+    if (cudaLaunchKernelEx(&cfg, dit_attn_kernel, tW, p) != cudaSuccess) {
         xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
         return XD_ERR_CUDA;
     }

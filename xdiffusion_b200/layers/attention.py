@@ -25,6 +25,17 @@ class MultiHeadSelfAttention(torch.nn.Module, Packed):
         return self.packed("w", (self.qkv.weight, self.proj.weight),
                            lambda: (bf16_weight(self.qkv.weight), bf16_weight(self.proj.weight)))
 
+    def head_packed(self):
+        """qkv Linear re-packed per head as [q_h | k_h | v_h] rows (bf16 [H*3*d, D]) + bias (fp32 [H*3*d]): one head's
+        projections are then one contiguous 192-row weight tile (csrc/dit_block.cu)."""
+        def build():
+            H, d = self.num_heads, self.head_dim
+            D = H * d
+            w = self.qkv.weight.detach().view(3, H, d, D).permute(1, 0, 2, 3).reshape(3 * D, D)
+            b = self.qkv.bias.detach().float().view(3, H, d).permute(1, 0, 2).reshape(3 * D)
+            return w.to(torch.bfloat16).contiguous(), b.contiguous()
+        return self.packed("wh", (self.qkv.weight, self.qkv.bias), build)
+
     def attend(self, x, tokens: int, ln=None):
         """softmax(q k^T / sqrt(d)) v for every head, WITHOUT the output projection: bf16 [B*T, D]."""
         wq, _ = self.weights()

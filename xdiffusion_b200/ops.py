@@ -106,6 +106,22 @@ def _ln_gemm(x, shift, scale, rows_per_mod, eps, w, bias, act, out):
                                              out.stride(0), _stream()), "xd_ln_gemm_bf16_tc")
 
 
+@_op("dit_attn(Tensor h, Tensor? stats, Tensor shift, Tensor scale, int rows_per_mod, float eps, Tensor wh, Tensor bias, "
+     "int heads, float sm_scale, Tensor(a!) out) -> ()")
+def _dit_attn(h, stats, shift, scale, rows_per_mod, eps, wh, bias, heads, sm_scale, out):
+    """Fused LayerNorm-modulate + per-head QKV projection + softmax attention: h fp32 [M, 384] -> out bf16 [M, 384]."""
+    _cuda(h, stats, shift, scale, wh, bias, out)
+    M, D = h.shape
+    assert h.dtype == torch.float32 and h.stride(1) == 1 and out.dtype == torch.bfloat16 and out.shape == (M, D) and out.stride(1) == 1
+    assert wh.dtype == torch.bfloat16 and wh.is_contiguous() and wh.shape == (heads * 192, D) and bias.is_contiguous()
+    assert shift.dtype == torch.float32 and shift.stride(1) == 1 and scale.stride(1) == 1 and shift.stride(0) == scale.stride(0)
+    assert stats is None or (stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= 2 * M)
+    _lib.check(_lib.lib().xd_dit_ln_qkv_attn_bf16_tc(_p(h), h.stride(0), _p(stats), _p(shift), _p(scale), shift.stride(0),
+                                                     rows_per_mod, eps, _p(wh), _p(bias), heads, M, D, sm_scale, _p(out),
+                                                     out.stride(0), _stream()), "xd_dit_ln_qkv_attn_bf16_tc")
+    _count()
+
+
 @_op("dit_proj_mlp(Tensor o, Tensor wp, Tensor bp, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor(a!) h, Tensor gate1, "
      "Tensor shift2, Tensor scale2, Tensor gate2, int rows_per_mod, float eps, Tensor(b!)? stats) -> ()")
 def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, rows_per_mod, eps, stats):

@@ -129,17 +129,28 @@ class DiT(torch.nn.Module, Packed):
             ops.linear(silu_c, w_ada, b_ada, out=mod)
         h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
         main.wait_stream(side)
+        fused = FUSED_BLOCK and D == 384 and ops.MATMUL_BACKEND == "tc"
+        fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
+        # (mean, rstd) of every row of h: emitted by the fused MLP kernel of block n, consumed by the LayerNorm of block n + 1
+        stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32) if fused else None
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
-            if FUSED_BLOCK and D == 384 and blk.mlp.act == ops.ACT_GELU and ops.MATMUL_BACKEND == "tc":
-                # one kernel for proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual
-                # (csrc/dit_block.cu): the [B*T, 4D] MLP activation never leaves the SM
-                o = blk.attn.attend(h, T, ln=(s1, sc1, T))
+            if fused and blk.mlp.act == ops.ACT_GELU:
+                # two kernels per block (csrc/dit_block.cu): LayerNorm-modulate + qkv + attention, then proj + gated
+                # residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual; neither the [B*T, 3D] qkv nor the
+                # [B*T, 4D] MLP activation leaves the SM
+                if fused_attn:
+                    wh, bh = blk.attn.head_packed()
+                    o = torch.empty((B * T, D), device=x.device, dtype=torch.bfloat16)
+                    torch.ops.xdb200.dit_attn(h, stats if n > 0 else None, s1, sc1, T, 1e-6, wh, bh, self.num_heads,
+                                              blk.attn.scale, o)
+                else:
+                    o = blk.attn.attend(h, T, ln=(s1, sc1, T))
                 _, wp = blk.attn.weights()
                 w1, w2 = blk.mlp.weights()
                 torch.ops.xdb200.dit_proj_mlp(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h,
-                                              g1, s2, sc2, g2, T, 1e-6, None)
+                                              g1, s2, sc2, g2, T, 1e-6, stats)
                 continue
             # ln=: LayerNorm + modulate feeding qkv / fc1 (layernorm_modulate kernel; fused into the GEMM with XDB200_LN_FUSED=1)
             blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))
