@@ -227,9 +227,37 @@ def _time_in_graph(call, reps=20):
     return sorted(ts)[len(ts) // 2]                       # ms per launch
 
 
+def dit_block_roofline(batch, device):
+    """The two kernels of one DiT block as the sampling loop launches them (csrc/dit_block.cu), at this per-GPU batch,
+    in-graph, operands L2-resident as they are between the kernels of a timestep:
+      dit_mlp_kernel   proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual
+                       algorithmic FLOPs = 2 M (D^2 + 2 D * 4D)                (the dominant kernel: ~60 % of the step)
+      dit_attn_kernel  LayerNorm-modulate + per-head qkv + softmax attention
+                       algorithmic FLOPs = 2 M 3 D^2 + 4 M T D                 (projection + q k^T + p v)
+    Returns (TFLOP/s of the dominant kernel, TFLOP/s of the pair, per-kernel record)."""
+    T, D, Hd, H = 16, 384, 1536, 6
+    M = batch * T
+    bf = lambda *s: torch.randn(*s, device=device).bfloat16()
+    o, h, h2 = bf(M, D), torch.randn(M, D, device=device), torch.empty(M, D, device=device)
+    wh, wp, w1, w2 = bf(3 * D, D) * D ** -0.5, bf(D, D) * D ** -0.5, bf(Hd, D) * D ** -0.5, bf(D, Hd) * Hd ** -0.5
+    bh, bp, b1, b2 = (torch.randn(n, device=device) * 0.1 for n in (3 * D, D, Hd, D))
+    mod = torch.randn(batch, 6 * D, device=device) * 0.1
+    s1, sc1, g1, s2, sc2, g2 = (mod[:, i * D:(i + 1) * D] for i in range(6))
+    stats = torch.zeros(M, 2, device=device)
+    X = torch.ops.xdb200
+    t_mlp = _time_in_graph(lambda: X.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h2, g1, s2, sc2, g2, T, 1e-6, stats, 0))
+    t_att = _time_in_graph(lambda: X.dit_attn(h, stats, s1, sc1, T, 1e-6, wh, bh, H, 0.125, o))
+    f_mlp = 2.0 * M * (D * D + 2 * D * Hd)
+    f_att = 2.0 * M * 3 * D * D + 4.0 * M * T * D
+    per = {"dit_mlp_kernel": {"us": round(t_mlp * 1e3, 2), "tflops": round(f_mlp / t_mlp / 1e9, 1), "gflop": round(f_mlp / 1e9, 2)},
+           "dit_attn_kernel": {"us": round(t_att * 1e3, 2), "tflops": round(f_att / t_att / 1e9, 1), "gflop": round(f_att / 1e9, 2)}}
+    return f_mlp / t_mlp / 1e9, (f_mlp + f_att) / (t_mlp + t_att) / 1e9, per
+
+
 def gemm_roofline(batch, device):
     """The four contractions of one DiT block at this per-GPU batch WITH their real epilogues (bias; bias + GELU; bias +
-    gate + fp32 residual in place), operands L2-resident as they are between the kernels of a timestep."""
+    gate + fp32 residual in place), operands L2-resident as they are between the kernels of a timestep.  (PixArt path; the
+    DiT path runs the fused kernels of dit_block_roofline.)"""
     from xdiffusion_b200 import ops
     M = batch * 16
     shapes = [(1152, 384, "qkv", False, 0), (384, 384, "proj", True, 0), (1536, 384, "fc1", False, ops.ACT_GELU),
@@ -411,7 +439,15 @@ class Runner:
                 "gpu_launches": rec["gpu_launches"], "launches_per_timestep": rec["launches_per_timestep"],
                 "ms_per_timestep": rec["ms_per_timestep"],
                 "step_tensor_frac_of_sustained": rec["step_tensor_frac_of_sustained"]}
-        if main in ("dit", "pixart"):
+        if main == "dit":
+            tf, tf_block, per = dit_block_roofline(per_gpu, self.device)
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                                "traffic": ncu_dram_bytes("ditmlp"), "peak_source": src, "per_shape": per,
+                                "block_achieved": tf_block, "block_frac": tf_block / burst,
+                                "kernel": "dit_mlp_kernel (tcgen05 cta_group::2, TMA, TMEM-resident MLP): proj + gated residual + "
+                                          "LayerNorm-modulate + fc1 + GELU + fc2 + gated residual of one DiT block at "
+                                          f"M = {per_gpu * 16} rows; block_* = with dit_attn_kernel (LN + qkv + attention)"}
+        elif main == "pixart":
             tf, per = gemm_roofline(per_gpu, self.device)
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
                                 "traffic": ncu_dram_bytes("gemm"), "peak_source": src, "per_shape": per,

@@ -56,11 +56,15 @@ int xd_ln_gemm_bf16_tc(const float* X, long long ldx, const float* shift, const 
  * O bf16 [M, D] (attention output), Wp [D, D], W1 [hidden, D], W2 [D, hidden] bf16 row-major, hidden % 128 == 0; gate / shift /
  * scale are fp32 rows of D values, row index m / rows_per_mod, mod_ld floats apart.  The [M, hidden] activation never leaves
  * the SM.  Replaces `x + gate_msa * attn.proj(.)` and `x + gate_mlp * mlp(modulate(norm2(x), shift_mlp, scale_mlp))`
- * (score_networks/dit.py:46-59, layers/attention.py:376-380, layers/mlp.py:30-45). */
+ * (score_networks/dit.py:46-59, layers/attention.py:376-380, layers/mlp.py:30-45).
+ * h_out may equal h_in (in place: one CTA pair per 256-row tile).  With distinct buffers and few tiles (a small shard of a
+ * strong-scaled batch) the hidden units of a tile are split over `split` = 2, 3 or 4 CTA pairs of one thread-block cluster
+ * whose partial fc2 tiles are reduced through distributed shared memory in a fixed order; split = 0 chooses (1 = never). */
 int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1, const float* b1,
-                            const void* W2, const float* b2, int hidden, float* h, long long ldh, int M, int D,
-                            const float* gate1, const float* shift2, const float* scale2, const float* gate2,
-                            long long mod_ld, int rows_per_mod, float eps, float* stats_out, void* stream);
+                            const void* W2, const float* b2, int hidden, const float* h_in, float* h_out, long long ldh,
+                            int M, int D, const float* gate1, const float* shift2, const float* scale2,
+                            const float* gate2, long long mod_ld, int rows_per_mod, float eps, float* stats_out,
+                            int split, void* stream);
 
 /* Fused first half of a DiT block (D = 384, 16 tokens per image, head dim 64): LayerNorm-modulate + QKV projection + softmax
  * attention in one kernel, one CTA pair per (256 token rows, group of heads):
@@ -77,8 +81,8 @@ int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats
  * Device pointer, 16-byte aligned, caller-owned; launches that use it must be ordered on one stream.  Optional: without
  * it every contraction runs unsplit. */
 int xd_set_workspace(void* ptr, long long bytes);
-/* Split-K makes the summation order (hence the low-order bits of a sample) depend on the batch size; 0 disables it and
- * restores bit-exact batch independence.  Default: on (environment XDB200_SPLITK=0 turns it off). */
+/* Split-K (and the automatic hidden-unit split of xd_dit_proj_mlp_bf16_tc, split = 0) makes the summation order (hence the
+ * low-order bits of a sample) depend on the batch size; 0 disables both and restores bit-exact batch independence.  Default: on (environment XDB200_SPLITK=0 turns it off). */
 int xd_set_split_k(int enabled);
 
 /* Implicit-GEMM conv3x3, stride 1, pad 1, NHWC bf16 (pixel stride ldx), packed weights
@@ -173,7 +177,11 @@ int xd_avgpool2x2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int
                        void* stream);
 int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out, long long ldo,
                        void* stream);
-int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, int C, void* out, long long ldo, void* stream);
+/* Strided bf16 row copy: row r = (batch r / rows_per_batch, row r % rows_per_batch), batch strides x_bs / o_bs, row strides
+ * ldx / ldo (elements).  Appends the self-attention [q | k | v] rows of every image behind that image's encoder rows:
+ * `torch.cat([ek, k], dim=-1)` of QKVAttention (layers/attention.py:166-180). */
+int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, long long rows, long long rows_per_batch, int C,
+                      void* out, long long ldo, long long o_bs, void* stream);
 /* eps = u + w (c - u)  (samplers/ancestral.py:229-231, samplers/ddim.py:69-71) */
 int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, long long n, void* stream);
 

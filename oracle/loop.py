@@ -41,7 +41,7 @@ class OracleModel:
     def score(self, x, t, ctx):
         if self.kind == "unet":
             tin = ctx["logsnr_t"] if nets.time_input_key(self.p) == "logsnr_t" else t
-            return nets.unet_forward(self.sd, self.p, x, tin)
+            return nets.unet_forward(self.sd, self.p, x, tin, text=ctx.get("text_embeddings"))
         if self.kind == "dit":
             return nets.dit_forward(self.sd, self.p, x, t, ctx["classes"])
         if self.kind == "pixart":

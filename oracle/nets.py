@@ -131,12 +131,70 @@ def qkv_attention_interleaved(qkv, heads):
     return torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
 
 
-def _spatial_attn(sd, pre, x, dim_head=64):
+def chan_layer_norm(x, g, dim):
+    """layers/attention.py:284-310 (LayerNorm with an axis; gain only, eps 1e-5 in fp32, biased variance)."""
+    var = torch.var(x, dim=dim, unbiased=False, keepdim=True)
+    mean = torch.mean(x, dim=dim, keepdim=True)
+    return (x - mean) * (var + 1e-5).rsqrt() * g
+
+
+def _spatial_attn(sd, pre, x, dim_head=64, text=None):
+    """SpatialCrossAttention (layers/attention.py:100-141).  ``text`` (B, L, Ctx): TextEmbeddingsAdapter with
+    swap_context_channels (context.py:115-140) -> (B, Ctx, L), ChanLayerNorm over the channel axis, ``_encoder_kv``
+    conv1d -> per-head [k | v], concatenated IN FRONT of the self-attention keys / values (attention.py:166-180)."""
     b, c = x.shape[:2]
+    heads = c // dim_head
     qkv = F.conv1d(_gn(sd, pre + "_norm", x).view(b, c, -1), sd[pre + "_qkv.weight"], sd[pre + "_qkv.bias"])
-    a = qkv_attention_interleaved(qkv, c // dim_head)
+    if text is not None and pre + "_encoder_kv.weight" in sd:
+        ctx = text.permute(0, 2, 1)
+        if pre + "_context_layer_norm.g" in sd:
+            ctx = chan_layer_norm(ctx, sd[pre + "_context_layer_norm.g"], -2)
+        ekv = F.conv1d(ctx, sd[pre + "_encoder_kv.weight"], sd[pre + "_encoder_kv.bias"])
+        bs, width, length = qkv.shape
+        ch = width // (3 * heads)
+        q, k, v = qkv.reshape(bs * heads, ch * 3, length).split(ch, dim=1)
+        ek, ev = ekv.reshape(bs * heads, ch * 2, -1).split(ch, dim=1)
+        k, v = torch.cat([ek, k], dim=-1), torch.cat([ev, v], dim=-1)
+        s = 1 / math.sqrt(math.sqrt(ch))
+        w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s).float(), dim=-1)
+        a = torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
+    else:
+        a = qkv_attention_interleaved(qkv, heads)
     h = F.conv1d(a, sd[pre + "_proj_out.weight"], sd[pre + "_proj_out.bias"])
     return x + h.reshape(x.shape)
+
+
+def attention_pooling(sd, pre, x, heads):
+    """AttentionPooling (layers/attention.py:231-283): a class token (mean over the sequence + positional embedding)
+    attends over [class token, sequence]; q and k are both scaled by d^-1/4; returns the class token (B, C)."""
+    bs, length, width = x.shape
+    d = width // heads
+
+    def shape(t):
+        return t.view(bs, -1, heads, d).transpose(1, 2).reshape(bs * heads, -1, d).transpose(1, 2)
+
+    cls = x.mean(dim=1, keepdim=True) + sd[pre + "positional_embedding"]
+    xx = torch.cat([cls, x], dim=1)
+    q, k, v = shape(_lin(sd, pre + "q_proj", cls)), shape(_lin(sd, pre + "k_proj", xx)), shape(_lin(sd, pre + "v_proj", xx))
+    s = 1 / math.sqrt(math.sqrt(d))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s).float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", w, v)
+    return a.reshape(bs, -1, 1).transpose(1, 2)[:, 0, :]
+
+
+def pooled_text_to_timestep(sd, p, text):
+    """PooledTextEmbeddingsToTimestep (layers/embedding.py:146-169): LayerNorm -> AttentionPooling -> Linear -> LayerNorm,
+    added to the timestep embedding.  Returns the (B, time_embedding_dim) addend, or None if the config has no such head."""
+    head = p["conditioning"]["context_transformer_head"]
+    head = head if isinstance(head, list) else [head]
+    for n, h in enumerate(head):
+        if h["target"].endswith("PooledTextEmbeddingsToTimestep"):
+            pre = f"_context_transformers.{n}._encoder_pooling."
+            y = F.layer_norm(text, text.shape[-1:], sd[pre + "0.weight"], sd[pre + "0.bias"], 1e-5)
+            y = attention_pooling(sd, pre + "1.", y, h["params"]["attention_pooling_heads"])
+            y = _lin(sd, pre + "2", y)
+            return F.layer_norm(y, y.shape[-1:], sd[pre + "3.weight"], sd[pre + "3.bias"], 1e-5)
+    return None
 
 
 def time_input_key(p):
@@ -159,11 +217,16 @@ def unet_time_embedding(sd, p, t):
     return _lin(sd, pre + "3", F.silu(_lin(sd, pre + "1", s)))
 
 
-def unet_forward(sd, p, x, t, taps=None):
+def unet_forward(sd, p, x, t, taps=None, text=None):
     """x (B,C,H,W) fp32; t (B,) = context[time_input_key(p)]: int64 loop index (discrete),
     fp32 time (flow) or fp32 logsnr_t (continuous).  ``taps`` (optional dict) receives
-    named intermediate activations for layer-level parity tests."""
+    named intermediate activations for layer-level parity tests.  ``text`` (B, L, Ctx): text embeddings of the
+    text-conditioned configs (Imagen base / GLIDE: unet.py:87-98 with context_dim > 0)."""
     emb = unet_time_embedding(sd, p, t)
+    if text is not None:
+        pooled = pooled_text_to_timestep(sd, p, text)
+        if pooled is not None:
+            emb = emb + pooled
     downs, _, ups = unet_layout(p)
     h = F.conv2d(x, sd["_initial_convolution.weight"], None, padding=1)
     if taps is not None:
@@ -176,7 +239,7 @@ def unet_forward(sd, p, x, t, taps=None):
             if op[0] == "res":
                 h = _resblock2d(sd, f"{pre}.{j}.", h, emb)
             elif op[0] == "attn":
-                h = _spatial_attn(sd, f"{pre}.{j}.", h)
+                h = _spatial_attn(sd, f"{pre}.{j}.", h, text=text)
             elif op[0] == "down":
                 h = F.avg_pool2d(h, 2, 2)
             elif op[0] == "up":
@@ -189,7 +252,7 @@ def unet_forward(sd, p, x, t, taps=None):
         if taps is not None:
             taps[f"downs.{n}"] = h
     h = _resblock2d(sd, "middle.0.", h, emb)
-    h = _spatial_attn(sd, "middle.1.", h)
+    h = _spatial_attn(sd, "middle.1.", h, text=text)
     h = _resblock2d(sd, "middle.2.", h, emb)
     if taps is not None:
         taps["middle"] = h

@@ -64,3 +64,16 @@ def strip_t5_from_pixart(d):
     cond["context_transformer_head"] = [
         c for c in cond["context_transformer_head"]
         if c["params"].get("projection_key") not in ("text_tokens", "text_prompts")]
+
+
+def strip_t5_from_imagen(d):
+    """C7 (configs/image/mnist/imagen_base.yaml): the T5 tokenizer (context preprocessor) and encoder (``text_tokens``
+    projection + TextTokenProjectionAdapter) need HF weights.  Drop them and feed ``text_embeddings`` (B, 77, 768)
+    directly; PooledTextEmbeddingsToTimestep and every SpatialCrossAttention(context_dim=768) stay as they are."""
+    diff = d["diffusion"]
+    diff["context_preprocessing"] = [{"target": "xdiffusion.context.IgnoreContextAdapter", "params": {}}]
+    cond = diff["score_network"]["params"]["conditioning"]
+    cond["signals"] = ["timestep"]
+    cond["projections"].pop("text_tokens", None)
+    cond["context_transformer_head"] = [c for c in cond["context_transformer_head"]
+                                        if not c["target"].endswith("TextTokenProjectionAdapter")]

@@ -28,7 +28,11 @@ CONFIGS = {
     "c5": ("configs/video/moving_mnist/video_diffusion_models.yaml", "unet3d"),
     # DDIM needs the continuous scheduler (samplers/ddim.py:43-45)
     "c6": ("configs/image/mnist/ddpm_32x32_v_continuous.yaml", "unet"),
+    # text-conditioned UNet (Imagen base stage, 8x8): encoder K/V in front of the self-attention K/V,
+    # attention-pooled text embedding added to the timestep embedding; synthetic T5-shaped embeddings
+    "c7": ("configs/image/mnist/imagen_base.yaml", "unet"),
 }
+PATCH = {"c4": ref_bootstrap.strip_t5_from_pixart, "c7": ref_bootstrap.strip_t5_from_imagen}
 
 
 class NoiseFeeder:
@@ -78,8 +82,7 @@ def patch_cfg_bug():
 
 def build(name):
     rel, kind = CONFIGS[name]
-    model = ref_bootstrap.load_reference_model(
-        rel, ref_bootstrap.strip_t5_from_pixart if name == "c4" else None)
+    model = ref_bootstrap.load_reference_model(rel, PATCH.get(name))
     manifest = canonical_manifest(model.state_dict())
     sd = synth_state_dict(manifest, seed=0)
     missing, unexpected = model.load_state_dict({"_score_network." + k: v for k, v in sd.items()}, strict=False)
@@ -92,7 +95,8 @@ def make(name):
     model, kind, manifest = build(name)
     cfg = model.config().to_dict()
     B = 1 if kind == "unet3d" else 2
-    shape = (B, 1, 16, 32, 32) if kind == "unet3d" else (B, 1, 32, 32)
+    size = cfg["diffusion"]["sampling"]["output_spatial_size"]
+    shape = (B, 1, 16, size, size) if kind == "unet3d" else (B, 1, size, size)
     g = torch.Generator().manual_seed(4321)
     out = {"manifest": manifest, "config": cfg, "kind": kind}
     ctx = {}
@@ -100,6 +104,9 @@ def make(name):
         ctx["classes"] = torch.tensor([3, 7])
     if kind == "pixart":
         ctx["classes"] = torch.tensor([3, 7])
+        ctx["text_prompts"] = ["", ""]
+        ctx["text_embeddings"] = torch.randn(B, 77, 768, generator=g)
+    if name == "c7":
         ctx["text_prompts"] = ["", ""]
         ctx["text_embeddings"] = torch.randn(B, 77, 768, generator=g)
     out["ctx"] = {k: v for k, v in ctx.items() if torch.is_tensor(v)}
@@ -152,10 +159,10 @@ def make(name):
     out["loop"] = {"K": K, "x_T": x_T, "noises": zs, "samples": samples}
 
     # ---- classifier-free guidance (C2 classes, C4 text embeddings) -------------------------
-    if kind in ("dit", "pixart"):
+    if kind in ("dit", "pixart") or name == "c7":
         patch_cfg_bug()
         w = 2.0
-        if kind == "pixart":
+        if kind == "pixart" or name == "c7":
             from xdiffusion.context import UnconditionalEmbeddingAdapter
             adapter = UnconditionalEmbeddingAdapter([77, 768])
             with torch.no_grad():

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(built):
     l = ctypes.CDLL(built)
     for name in _lib.parse_header():
         assert hasattr(l, name), name
-    assert _lib.lib().xd_abi_version() == 2
+    assert _lib.lib().xd_abi_version() == 3
 
 
 def test_sass_is_blackwell_native(built):

@@ -76,11 +76,12 @@ def _medium(name, golden, B, K, sampler=None, cfg=None):
     fx = golden(name)
     m, om = product_model(fx), oracle_model(fx)
     g = torch.Generator().manual_seed(31)
-    shape = (B, 1, 16, 32, 32) if fx["kind"] == "unet3d" else (B, 1, 32, 32)
+    size = fx["config"]["diffusion"]["sampling"]["output_spatial_size"]
+    shape = (B, 1, 16, size, size) if fx["kind"] == "unet3d" else (B, 1, size, size)
     x_T = torch.randn(shape, generator=g)
     noise = torch.randn((K,) + shape, generator=g)
     ctx, uncond = {}, None
-    if fx["kind"] == "pixart":
+    if "null_embedding" in fx:                           # text-conditioned: c4 (PixArt), c7 (Imagen-base UNet)
         ctx["text_embeddings"] = torch.randn(B, 77, 768, generator=g)
         if cfg is not None:
             from xdiffusion_b200.context import UnconditionalEmbeddingAdapter
@@ -113,6 +114,12 @@ def test_medium_loop_c3_rectified_flow(golden):
 def test_medium_loop_c4_pixart_cfg(golden):
     assert _medium("c4", golden, 4, 50) < MEDIUM_TOL
     assert _medium("c4", golden, 4, 50, cfg=2.0) < MEDIUM_TOL
+
+
+def test_medium_loop_c7_text_conditioned_unet_cfg(golden):
+    """Imagen-base UNet (8x8) with encoder K/V in front of the self-attention K/V and the attention-pooled
+    text embedding in the timestep embedding, classifier-free guidance w = 2, 50 steps with dynamic thresholding."""
+    assert _medium("c7", golden, B=8, K=50, cfg=2.0) < MEDIUM_TOL
 
 
 def test_medium_loop_c5_video(golden):

@@ -494,11 +494,15 @@ def _ln(x, eps=1e-6):
     return F.layer_norm(x, (x.shape[-1],), eps=eps)
 
 
-@pytest.mark.parametrize("B", [64, 13, 1024])
-def test_dit_proj_mlp_fused(ops, B):
+@pytest.mark.parametrize("B,split", [(64, None), (13, None), (1024, None), (13, 2), (13, 3), (13, 4), (128, 2), (128, 3),
+                                     (128, 4), (128, 0), (256, 0), (512, 0), (64, 1)])
+def test_dit_proj_mlp_fused(ops, B, split):
     """xd_dit_proj_mlp_bf16_tc (proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual in one
     kernel) against fp32 torch math on the same bf16-rounded operands (score_networks/dit.py:46-59); B = 13 leaves a
-    ragged last 256-row tile.  The emitted (mean, rstd) row statistics are checked against torch too."""
+    ragged last 256-row tile.  The emitted (mean, rstd) row statistics are checked against torch too.
+    split = None: in place, one CTA pair per tile.  split = 2 / 3 / 4: separate output buffer, the hidden units of a tile
+    spread over that many CTA pairs of a cluster and reduced through distributed shared memory (0 = the library chooses);
+    the split kernels must also be deterministic (two launches, identical bits)."""
     g = torch.Generator().manual_seed(100 + B)
     T, D, Hd = 16, 384, 1536
     M = B * T
@@ -519,8 +523,16 @@ def test_dit_proj_mlp_fused(ops, B):
     md = mod.to(DEV)
     g1d, s2d, sc2d, g2d = (md[:, i * D:(i + 1) * D] for i in (2, 3, 4, 5))
     stats = torch.zeros(M, 2, device=DEV)
-    torch.ops.xdb200.dit_proj_mlp(o.to(DEV), wp.to(DEV), bp.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), hd,
-                                  g1d, s2d, sc2d, g2d, T, 1e-6, stats)
+    dev_args = [t.to(DEV) for t in (o, wp, bp, w1, b1, w2, b2)]
+    if split is None:
+        torch.ops.xdb200.dit_proj_mlp(*dev_args, hd, hd, g1d, s2d, sc2d, g2d, T, 1e-6, stats, 0)
+    else:
+        h_in, hd = hd, torch.full_like(hd, float("nan"))
+        torch.ops.xdb200.dit_proj_mlp(*dev_args, h_in, hd, g1d, s2d, sc2d, g2d, T, 1e-6, stats, split)
+        again, stats2 = torch.full_like(hd, float("nan")), torch.zeros_like(stats)
+        torch.ops.xdb200.dit_proj_mlp(*dev_args, h_in, again, g1d, s2d, sc2d, g2d, T, 1e-6, stats2, split)
+        assert torch.equal(again, hd) and torch.equal(stats, stats2)
+        assert torch.equal(h_in.cpu(), h)                        # the input buffer is left untouched
     assert rel_l2(hd, ref) < 3e-3, rel_l2(hd, ref)
     mean, var = ref.mean(1), ref.var(1, unbiased=False)
     assert float((stats[:, 0].cpu() - mean).abs().max()) < 2e-3

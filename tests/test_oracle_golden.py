@@ -66,7 +66,7 @@ def _model(fx):
     return OracleModel(kind, fx["config"], sd)
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6", "c7"])
 def test_single_steps(name, golden):
     if not have(name):
         pytest.skip("fixture not generated")
@@ -103,7 +103,7 @@ def test_single_steps(name, golden):
         assert torch.equal(xn, s["x_next"]), (name, i, float((xn - s["x_next"]).abs().max()))
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6", "c7"])
 def test_short_loop(name, golden):
     if not have(name):
         pytest.skip("fixture not generated")

@@ -46,8 +46,13 @@ s1, sc1, g1, s2, sc2, g2 = (mod[:, i * D:(i + 1) * D] for i in range(6))
 stats = torch.zeros(M, 2, device=dev)
 
 flop_mlp = 2.0 * M * (D * D + 2 * D * Hd)
-us = timed(lambda: torch.ops.xdb200.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, g1, s2, sc2, g2, T, 1e-6, stats))
+us = timed(lambda: torch.ops.xdb200.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h, g1, s2, sc2, g2, T, 1e-6, stats, 1))
 print(f"B={B}: fused proj+LN+fc1+GELU+fc2      {us:7.1f} us   {flop_mlp / us / 1e6:7.1f} TFLOP/s")
+h2 = torch.empty_like(h)
+for split in (2, 3, 4):
+    if (M + 255) // 256 * 2 * split <= 148:
+        us = timed(lambda: torch.ops.xdb200.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h2, g1, s2, sc2, g2, T, 1e-6, stats, split))
+        print(f"B={B}:   split over {split} CTA pairs per tile  {us:7.1f} us   {flop_mlp / us / 1e6:7.1f} TFLOP/s")
 
 
 def unfused():

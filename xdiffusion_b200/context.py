@@ -65,3 +65,22 @@ class UnconditionalEmbeddingAdapter(torch.nn.Module):
         new_context["text_embeddings"] = y.unsqueeze(0).expand(emb.shape[0], -1, -1).contiguous()
         assert new_context["text_embeddings"].shape == emb.shape
         return new_context
+
+
+class TextEmbeddingsAdapter(torch.nn.Module):
+    """context["text_embeddings"] (B, L, C) -> (B, C, L) if ``swap_context_channels``, optionally projected
+    (reference: context.py:115-140).  Timestep-invariant: evaluated once per sampling loop, not per step."""
+
+    def __init__(self, swap_context_channels: bool = False, input_projection_dim: int = -1,
+                 output_projection_dim: int = -1, **kwargs):
+        super().__init__()
+        self._swap_context_channels = swap_context_channels
+        if output_projection_dim > 0 and input_projection_dim > 0:
+            self._projection = torch.nn.Linear(input_projection_dim, output_projection_dim)
+        else:
+            self._projection = torch.nn.Identity()
+
+    def forward(self, context: Dict):
+        x = context["text_embeddings"]
+        x = x.permute(0, 2, 1) if self._swap_context_channels else x
+        return self._projection(x)

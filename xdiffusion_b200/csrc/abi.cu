@@ -13,7 +13,7 @@ void xd_set_error(const char* file, int line, const char* msg) {
 }
 
 extern "C" const char* xd_last_error(void) { return g_err; }
-extern "C" int xd_abi_version(void) { return 2; }
+extern "C" int xd_abi_version(void) { return 3; }
 
 // Programmatic dependent launch: XDB200_PDL=0 off, 1 every kernel, 2 (default) only the tcgen05 GEMM / conv launches.
 // Measured (profiles/README.md): GEMM-only gains ~2 % on the DiT step; on every kernel it costs the UNet 6 %.

@@ -25,6 +25,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
 
 bool xd_pdl_enabled();       // XDB200_PDL=1: every kernel (abi.cu)
+bool xd_split_enabled();     // xd_set_split_k / XDB200_SPLITK: batch-size-dependent work splits allowed (gemm_tc.cu)
 bool xd_pdl_enabled_gemm();  // XDB200_PDL=1 or 2 (default): the tcgen05 GEMM / conv launches
 
 template <typename... KArgs, typename... Args>

@@ -56,39 +56,56 @@ struct MlpParams {
     const float *gate1, *shift2, *scale2, *gate2;
     float2* stats_out;
     float eps;
+    float* h_out;               // split kernels (G > 1): the final pass addresses h_out directly
+    long long ldh;
+    long long* prof;            // -DXDB200_INSTRUMENT + XDB200_DIT_PROF=<device pointer>: 64 clock64() stamps per CTA
 };
 
+// phase stamps for tools/prof_dit_phases.py (compiled out of the product build)
+#ifdef XDB200_INSTRUMENT
+#define DIT_STAMP(slot) do { if (p.prof) p.prof[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#else
+#define DIT_STAMP(slot) do { } while (0)
+#endif
+
 // Warp-level pass over this warp's 32 rows x 192 columns of acc2 (six 32-column chunks):
-//   v = res + gate * (acc + bias),  res = the h box (TMA load, prefetched one chunk ahead), v -> h (TMA store),
+//   v = res + gate * (acc + bias),  res = the h box (TMA load), v -> h (TMA store from the same box),
 // optionally v -> TMEM (parked for a second pass), and the shifted sums  s = sum(v - c0), qq = sum((v - c0)^2).
-template <bool TO_TMEM>
-__device__ __forceinline__ void gated_residual_pass(const CUtensorMap* tmH, uint32_t wbuf_a, uint64_t* rbar, uint32_t& cc,
-                                                    uint32_t t_addr, int m0w, int col_base, const float* bias,
-                                                    const float* gp, int lane, float& c0, float& s, float& qq) {
+// Every chunk has its own mbarrier and (except one) its own 4 KB box, so all residual loads are in flight at once: with
+// two boxes the load of chunk i + 1 could only be issued after the store of chunk i - 1 had drained its box, a
+// store-drain + load-latency chain of ~1.2 us per chunk (the pass then cost ~7 us of the kernel's 45).
+//   FINAL = false (first pass): the caller issued the loads of chunks 0 and 1 before it waited for the accumulator; chunks
+//           2..4 are issued here and chunk 5 re-uses the box of chunk 0 once that chunk's store has drained it.
+//   FINAL = true: six distinct boxes, all six loads issued here.
+template <bool TO_TMEM, bool FINAL>
+__device__ __forceinline__ void gated_residual_pass(const CUtensorMap* tmIn, const CUtensorMap* tmH, const uint32_t (&box)[6],
+                                                    uint64_t* rbar, uint32_t parity, uint32_t t_addr, int m0w, int col_base,
+                                                    const float* bias, const float* gp, int lane, float& c0, float& s,
+                                                    float& qq) {
     if (lane == 0) {
-        ptx::bulk_wait_read<1>();                        // the store that last read this box (chunk cc - 2)
-        const uint32_t b = cc & 1;
-        ptx::mbar_arrive_expect_tx(&rbar[b], 4096);
-        ptx::tma_load_2d_u32(wbuf_a + b * 4096, tmH, ptx::smem_u32(&rbar[b]), col_base, m0w);
+#pragma unroll
+        for (int ci = FINAL ? 0 : 2; ci < (FINAL ? 6 : 5); ++ci) {
+            ptx::mbar_arrive_expect_tx(&rbar[ci], 4096);
+            ptx::tma_load_2d_u32(box[ci], tmIn, ptx::smem_u32(&rbar[ci]), col_base + ci * 32, m0w);
+        }
     }
     __syncwarp();
     uint32_t rr[2][32];
     ptx::tmem_ld_32x32(t_addr, rr[0]);
     s = 0.f; qq = 0.f; c0 = 0.f;
 #pragma unroll
-    for (int ci = 0; ci < 6; ++ci, ++cc) {
+    for (int ci = 0; ci < 6; ++ci) {
         const int nc = col_base + ci * 32;
-        const uint32_t b = cc & 1;
-        const uint32_t wb = wbuf_a + b * 4096;
+        const uint32_t wb = box[ci];
         uint32_t* r = rr[ci & 1];
-        if (lane == 0 && ci + 1 < 6) {                   // prefetch the next h box into the other buffer
-            ptx::bulk_wait_read<0>();
-            ptx::mbar_arrive_expect_tx(&rbar[b ^ 1], 4096);
-            ptx::tma_load_2d_u32(wbuf_a + (b ^ 1) * 4096, tmH, ptx::smem_u32(&rbar[b ^ 1]), nc + 32, m0w);
+        if (!FINAL && ci == 2 && lane == 0) {            // box[5] == box[0]: free once the store of chunk 0 has read it
+            ptx::bulk_wait_read<1>();
+            ptx::mbar_arrive_expect_tx(&rbar[5], 4096);
+            ptx::tma_load_2d_u32(box[5], tmIn, ptx::smem_u32(&rbar[5]), col_base + 5 * 32, m0w);
         }
         ptx::tmem_ld_wait();
         if (ci + 1 < 6) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, rr[(ci + 1) & 1]);
-        ptx::mbar_wait(&rbar[b], (cc >> 1) & 1);
+        ptx::mbar_wait(&rbar[ci], parity);
         const uint32_t rowa = wb + lane * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                    // 16 columns per half
@@ -144,11 +161,19 @@ __device__ __forceinline__ void combine_stats(float2* stat_sm, int grp, int row,
     rstd = rsqrtf(m2 / (2.0f * n) + eps);
 }
 
+// G > 1 ("split" kernels, small M): a cluster of G CTA pairs shares one 256-row tile.  Every pair computes the projection,
+// h1 and the LayerNorm panel redundantly (1/9 of the work), runs fc1 -> GELU -> fc2 over ITS 1/G of the hidden units, and the
+// G partial fc2 tiles are reduced through distributed shared memory: pair g owns columns [g * 384/G, (g + 1) * 384/G) of
+// the tile, every CTA pushes the matching slices of its TMEM partial into the owner's shared memory (st.shared::cluster),
+// and the owner adds them in pair order (deterministic), applies bias / gate / residual and writes h.  h_in and h_out are
+// distinct buffers here (another pair may still be reading h while this one writes h1).
+template <int G>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWp,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-               const __grid_constant__ CUtensorMap tmH, const MlpParams p) {
+               const __grid_constant__ CUtensorMap tmHin, const __grid_constant__ CUtensorMap tmH, const MlpParams p) {
     pdl_launch_dependents();
+    if (threadIdx.x == 64) DIT_STAMP(63);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* panel = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* hid = panel + PANEL_BYTES;                 // [2][HID_BYTES]; aliased by the epilogue staging boxes
@@ -163,22 +188,27 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
     uint64_t* acc1_empty = acc1_full + 1;                        // 16 warp arrivals at the leader
     uint64_t* hid_full = acc1_empty + 1;                         // [2], 16 warp arrivals at the leader
     uint64_t* hid_empty = hid_full + 2;                          // [2], tcgen05.commit multicast
-    uint64_t* res_bar = hid_empty + 2;                           // [EPI_WARPS][2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+    uint64_t* res_bar = hid_empty + 2;                           // [EPI_WARPS][6]: one per residual box of a pass
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 6 * EPI_WARPS);
     float2* stat_sm = reinterpret_cast<float2*>(misc + 1024);    // [2][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int rank = (int)ptx::cluster_ctarank();
-    const int tile = blockIdx.x >> 1;
+    const int crank = (int)ptx::cluster_ctarank();               // pair g = crank / 2, CTA `rank` of the pair
+    const int rank = crank & 1;
+    const int grp_id = crank >> 1;
+    const int tile = blockIdx.x / (2 * G);
     const int m0 = tile * 256 + rank * 128;                      // this CTA's first row
-    const int nch = p.hidden / 128;
+    const int nch = p.hidden / (128 * G);                        // hidden chunks of this pair
+    const int ch0 = grp_id * nch;                                // ... starting at this chunk of the full hidden dimension
+    const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1));
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmO);
         ptx::prefetch_tmap(&tmWp);
         ptx::prefetch_tmap(&tmW1);
         ptx::prefetch_tmap(&tmW2);
+        ptx::prefetch_tmap(&tmHin);
         ptx::prefetch_tmap(&tmH);
         for (int s = 0; s < RING; ++s) {
             ptx::mbar_init(&ring_full[s], 2);
@@ -193,7 +223,7 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             ptx::mbar_init(&hid_full[b], 2 * EPI_WARPS);
             ptx::mbar_init(&hid_empty[b], 1);
         }
-        for (int k = 0; k < 2 * EPI_WARPS; ++k) ptx::mbar_init(&res_bar[k], 1);
+        for (int k = 0; k < 6 * EPI_WARPS; ++k) ptx::mbar_init(&res_bar[k], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -204,7 +234,9 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 64) DIT_STAMP(61);
     pdl_wait();
+    if (threadIdx.x == 64) DIT_STAMP(62);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs: own rows / own tile halves)
@@ -225,11 +257,11 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                 for (int nh = 0; nh < 2; ++nh) load_b(&tmWp, 96 * 128, kb * 64, nh * 192 + rank * 96);
             for (int it = 0; it < nch + FC2_LAG; ++it) {
                 if (it < nch)
-                    for (int kb = 0; kb < KB; ++kb) load_b(&tmW1, 64 * 128, kb * 64, it * 128 + rank * 64);
+                    for (int kb = 0; kb < KB; ++kb) load_b(&tmW1, 64 * 128, kb * 64, (ch0 + it) * 128 + rank * 64);
                 if (it >= FC2_LAG)
                     for (int kb2 = 0; kb2 < 2; ++kb2)
                         for (int nh = 0; nh < 2; ++nh)
-                            load_b(&tmW2, 96 * 128, (it - FC2_LAG) * 128 + kb2 * 64, nh * 192 + rank * 96);
+                            load_b(&tmW2, 96 * 128, (ch0 + it - FC2_LAG) * 128 + kb2 * 64, nh * 192 + rank * 96);
             }
         }
     } else if (warp == 1) {
@@ -250,22 +282,26 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                 if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) ptx::umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
-                    ptx::umma_commit_2sm(&ring_empty[s]);
+                    ptx::umma_commit_2sm(&ring_empty[s], pair_mask);
                 }
                 __syncwarp();
                 if (++s == RING) { s = 0; ph ^= 1; }
             };
             // ---- proj: acc2 = O Wp^T
+            if (lane == 0) DIT_STAMP(48);
             for (int kb = 0; kb < KB; ++kb) {
                 ptx::mbar_wait(&panel_full[kb], 0);
+                if (kb == 0 && lane == 0) DIT_STAMP(49);
                 for (int nh = 0; nh < 2; ++nh)
                     mma_block(tmem_base + nh * 192, d_panel + (uint64_t)((kb * A_BYTES) >> 4), idesc192, kb == 0);
             }
-            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full);
+            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full, pair_mask);
             __syncwarp();
             // ---- MLP: fc1(it), fc2(it - FC2_LAG)
+            if (lane == 0) DIT_STAMP(50);
             ptx::mbar_wait(a_full, 0);
             ptx::tc_fence_after();
+            if (lane == 0) DIT_STAMP(51);
             for (int it = 0; it < nch + FC2_LAG; ++it) {
                 if (it < nch) {
                     if (it >= 1) {
@@ -274,7 +310,7 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                     }
                     for (int kb = 0; kb < KB; ++kb)
                         mma_block(tmem_base + ACC1_COL, d_panel + (uint64_t)((kb * A_BYTES) >> 4), idesc128, kb == 0);
-                    if (ptx::elect_one()) ptx::umma_commit_2sm(acc1_full);
+                    if (ptx::elect_one()) ptx::umma_commit_2sm(acc1_full, pair_mask);
                     __syncwarp();
                 }
                 if (it >= FC2_LAG) {
@@ -285,12 +321,13 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                         for (int nh = 0; nh < 2; ++nh)
                             mma_block(tmem_base + nh * 192, d_hid + (uint64_t)((b * HID_BYTES + kb2 * A_BYTES) >> 4), idesc192,
                                       c == 0 && kb2 == 0);
-                    if (ptx::elect_one()) ptx::umma_commit_2sm(&hid_empty[b]);
+                    if (ptx::elect_one()) ptx::umma_commit_2sm(&hid_empty[b], pair_mask);
                     __syncwarp();
                 }
             }
-            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full);
+            if (ptx::elect_one()) ptx::umma_commit_2sm(acc2_full, pair_mask);
             __syncwarp();
+            if (lane == 0) DIT_STAMP(52);
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
@@ -301,18 +338,35 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         const int m0w = m0 + q * 32;
         const int gm = min(m0 + row, p.M - 1);
         const long long mod_off = (long long)(gm / p.rows_per_mod) * p.mod_ld;
-        const uint32_t wbuf_a = ptx::smem_u32(hid + e_warp * 8192);
-        uint64_t* rbar = res_bar + 2 * e_warp;
+        // residual boxes of this warp (4 KB each, 1 KB aligned): two in the hidden buffers (idle until the first GELU), three
+        // in the panel -- the very area this warp's LayerNorm pass fills afterwards (rows 32q.., k-blocks 3 grp..), idle between
+        // the last proj MMA and that pass -- and, for the final pass (nothing else is live then), one in the weight ring
+        const uint32_t hbox = ptx::smem_u32(hid + e_warp * 8192);
+        const uint32_t pbox = ptx::smem_u32(panel) + 3 * grp * A_BYTES + q * 4096;
+        const uint32_t box1[6] = {hbox, hbox + 4096, pbox, pbox + A_BYTES, pbox + 2 * A_BYTES, hbox};
+        uint64_t* rbar = res_bar + 6 * e_warp;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const int col_base = grp * 192;
-        uint32_t cc = 0;
         float c0, s, qq, mean, rstd;
 
         // ---- h1 = h + gate1 * (acc2 + bp) -> h (global) and TMEM; LayerNorm statistics
+        const bool st = e_warp == 0 && lane == 0;        // the stamping thread (instrumented builds)
+        if (st) DIT_STAMP(0);
+        if (lane == 0) {                                 // the first two residual boxes travel while the projection runs
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                ptx::mbar_arrive_expect_tx(&rbar[ci], 4096);
+                ptx::tma_load_2d_u32(box1[ci], &tmHin, ptx::smem_u32(&rbar[ci]), col_base + ci * 32, m0w);
+            }
+        }
         ptx::mbar_wait(acc2_full, 0);
         ptx::tc_fence_after();
-        gated_residual_pass<true>(&tmH, wbuf_a, rbar, cc, t_lane + col_base, m0w, col_base, p.bp, p.gate1 + mod_off, lane, c0, s, qq);
+        if (st) DIT_STAMP(1);
+        gated_residual_pass<true, false>(&tmHin, &tmH, box1, rbar, 0, t_lane + col_base, m0w, col_base, p.bp, p.gate1 + mod_off, lane, c0, s, qq);
+        if (st) DIT_STAMP(2);
         combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
+        if (lane == 0) ptx::bulk_wait_read<1>();         // the stores of chunks 2..4 have drained the panel boxes
+        __syncwarp();
         // ---- second pass over the parked h1: a = LN(h1) * (1 + scale2) + shift2 -> bf16 panel (fc1's A operand)
         {
             const float* scp = p.scale2 + mod_off;
@@ -353,15 +407,17 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         if (lane == 0) ptx::bulk_wait_read<0>();         // staging boxes alias the hidden buffers: stores have read them
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(a_full);
+        if (st) DIT_STAMP(3);
 
         // ---- fc1 chunks: u = gelu(acc1 + b1) -> bf16 hidden buffer (fc2's A operand)
         const uint32_t hid_a = ptx::smem_u32(hid);
         for (int c = 0; c < nch; ++c) {
             const int b = c & 1;
             if (lane < 2)                                // this chunk's 64 bias values (2 lines) into L1 before they are needed
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.b1 + c * 128 + grp * 64 + lane * 32));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.b1 + (ch0 + c) * 128 + grp * 64 + lane * 32));
             ptx::mbar_wait(acc1_full, c & 1);
             ptx::tc_fence_after();
+            if (st) DIT_STAMP(8 + 2 * c);
             uint32_t r0[32], r1[32];
             ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64, r0);
             ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64 + 32, r1);
@@ -371,7 +427,7 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             if (lane == 0) ptx::mbar_arrive_leader(acc1_empty);
             ptx::mbar_wait(&hid_empty[b], ((c >> 1) & 1) ^ 1);
             const uint32_t hb = hid_a + b * HID_BYTES + grp * A_BYTES + row * 128;
-            const float* bptr = p.b1 + c * 128 + grp * 64;
+            const float* bptr = p.b1 + (ch0 + c) * 128 + grp * 64;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t* r = j < 4 ? r0 + 8 * j : r1 + 8 * (j - 4);
@@ -388,6 +444,7 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_leader(&hid_full[b]);
+            if (st) DIT_STAMP(9 + 2 * c);
         }
 
         // ---- h = h1 + gate2 * (acc2 + b2); statistics of the new rows for the next block's LayerNorm
@@ -395,13 +452,131 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         __syncwarp();
         ptx::mbar_wait(acc2_full, 1);
         ptx::tc_fence_after();
-        gated_residual_pass<false>(&tmH, wbuf_a, rbar, cc, t_lane + col_base, m0w, col_base, p.b2, p.gate2 + mod_off, lane, c0, s, qq);
-        combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
-        if (p.stats_out && grp == 0 && m0 + row < p.M) p.stats_out[m0 + row] = make_float2(mean, rstd);
-        if (lane == 0) ptx::bulk_wait<0>();
+        if (st) DIT_STAMP(40);
+        if constexpr (G == 1) {
+            const uint32_t box2[6] = {hbox, hbox + 4096, pbox, pbox + A_BYTES, pbox + 2 * A_BYTES, ptx::smem_u32(ring) + e_warp * 4096};
+            gated_residual_pass<false, true>(&tmH, &tmH, box2, rbar, 1, t_lane + col_base, m0w, col_base, p.b2, p.gate2 + mod_off, lane, c0, s, qq);
+            combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
+            if (p.stats_out && grp == 0 && m0 + row < p.M) p.stats_out[m0 + row] = make_float2(mean, rstd);
+            if (lane == 0) ptx::bulk_wait<0>();
+            if (st) DIT_STAMP(41);
+        }
+    }
+    if constexpr (G > 1) {
+        // ------------------------------------------------------------ cross-pair reduction of the fc2 partial tiles (DSMEM)
+        // Receive buffer (aliases panel / hidden buffers / weight ring, all idle once every MMA of the cluster has completed):
+        // [G source pairs][128 rows][W columns] fp32, rows padded by 16 bytes (conflict-free 16-byte accesses, lane = row);
+        // behind it [G][128] float2 (mean, M2) of the column slices, used by pair 0 only.
+        constexpr int W = DM / G;
+        constexpr int RS = W * 4 + 16;
+        constexpr int STATX_OFF = G * 128 * RS;
+        static_assert(W % 32 == 0 && STATX_OFF + G * 128 * 8 <= PANEL_BYTES + 2 * HID_BYTES + RING * SLOT_BYTES, "receive buffer");
+        const uint32_t recv = ptx::smem_u32(panel);
+        const int e_warp = warp - 2, grp = e_warp >> 2, q = warp & 3, row = q * 32 + lane;
+        __syncwarp();
+        ptx::tc_fence_before();
+        ptx::cluster_sync();                             // #1: nobody in the cluster reads its operand buffers any more
+        if (threadIdx.x == 64) DIT_STAMP(42);
+        if (warp >= 2) {
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 192;
+            uint32_t rr[2][32];
+            ptx::tmem_ld_32x32(t_addr, rr[0]);
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci) {
+                const int col = grp * 192 + ci * 32;
+                const int owner = col / W, cin = col - owner * W;
+                const uint32_t* r = rr[ci & 1];
+                ptx::tmem_ld_wait();
+                if (ci + 1 < 6) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, rr[(ci + 1) & 1]);
+                const uint32_t dst = ptx::mapa(recv + (grp_id * 128 + row) * RS + cin * 4, (uint32_t)(owner * 2 + rank));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ptx::sts128_cluster(dst + 16 * j, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+            }
+        }
+        __syncwarp();
+        if (threadIdx.x == 64) DIT_STAMP(43);
+        ptx::cluster_sync();                             // #2: every partial slice has landed in its owner
+        if (threadIdx.x == 64) DIT_STAMP(44);
+        if (warp >= 2) {
+            const int gm = m0 + row;
+            const bool live = gm < p.M;
+            const long long mod_off = (long long)(min(gm, p.M - 1) / p.rows_per_mod) * p.mod_ld;
+            float* hrow = p.h_out + (long long)min(gm, p.M - 1) * p.ldh + grp_id * W;
+            const float* gp = p.gate2 + mod_off + grp_id * W;
+            const float* bp2 = p.b2 + grp_id * W;
+            float c0 = 0.f, s = 0.f, qq = 0.f;
+            int ncols = 0;
+#pragma unroll 1
+            for (int ci = grp; ci < W / 32; ci += 2) {  // the two warps of a row quadrant alternate over the 32-column chunks
+                float4 acc[8], h1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h1[j] = __ldcg(reinterpret_cast<const float4*>(hrow + ci * 32) + j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = ptx::lds128(recv + row * RS + ci * 128 + 16 * j);
+                    acc[j] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+                }
+#pragma unroll
+                for (int gg = 1; gg < G; ++gg) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 v = ptx::lds128(recv + (gg * 128 + row) * RS + ci * 128 + 16 * j);
+                        acc[j].x += __uint_as_float(v.x); acc[j].y += __uint_as_float(v.y);
+                        acc[j].z += __uint_as_float(v.z); acc[j].w += __uint_as_float(v.w);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 gt = __ldg(reinterpret_cast<const float4*>(gp + ci * 32) + j);
+                    const float4 bq = __ldg(reinterpret_cast<const float4*>(bp2 + ci * 32) + j);
+                    float4 v;
+                    v.x = fmaf(acc[j].x + bq.x, gt.x, h1[j].x); v.y = fmaf(acc[j].y + bq.y, gt.y, h1[j].y);
+                    v.z = fmaf(acc[j].z + bq.z, gt.z, h1[j].z); v.w = fmaf(acc[j].w + bq.w, gt.w, h1[j].w);
+                    if (ncols == 0 && j == 0) c0 = v.x;
+                    const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
+                    s += (d0 + d1) + (d2 + d3);
+                    qq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, qq))));
+                    if (live) *(reinterpret_cast<float4*>(hrow + ci * 32) + j) = v;
+                }
+                ncols += 32;
+            }
+            // (mean, M2) of this thread's columns -> of the pair's column slice -> pushed to pair 0 of this tile half
+            const float n_a = (float)ncols;
+            const float mean_a = c0 + s / n_a, m2_a = fmaxf(qq - s * s / n_a, 0.f);
+            stat_sm[grp * 128 + row] = make_float2(mean_a, m2_a);
+            ptx::named_bar_sync(1 + q, 64);
+            if (grp == 0) {
+                const float2 o = stat_sm[128 + row];
+                const float n_b = (float)(W - ncols);     // columns taken by the partner warp (grp 1)
+                const float dm = o.x - mean_a;
+                const float mean_s = mean_a + dm * (n_b / (float)W);
+                const float m2_s = m2_a + o.y + dm * dm * (n_a * n_b / (float)W);
+                const uint32_t dst = ptx::mapa(recv + STATX_OFF + (grp_id * 128 + row) * 8, (uint32_t)rank);
+                ptx::sts64_cluster(dst, __float_as_uint(mean_s), __float_as_uint(m2_s));
+            }
+        }
+        __syncwarp();
+        if (threadIdx.x == 64) DIT_STAMP(45);
+        ptx::cluster_sync();                             // #3: slice statistics have landed in pair 0
+        if (threadIdx.x == 64) DIT_STAMP(46);
+        if (warp >= 2 && warp < 6 && grp_id == 0 && p.stats_out && m0 + row < p.M) {
+            const float2* sx = reinterpret_cast<const float2*>(panel + STATX_OFF);
+            float mean = sx[row].x, m2 = sx[row].y, n = (float)W;
+#pragma unroll
+            for (int gg = 1; gg < G; ++gg) {             // Chan's formula, slice after slice
+                const float2 o = sx[gg * 128 + row];
+                const float dm = o.x - mean, nn = n + (float)W;
+                mean += dm * ((float)W / nn);
+                m2 += o.y + dm * dm * (n * (float)W / nn);
+                n = nn;
+            }
+            p.stats_out[m0 + row] = make_float2(mean, rsqrtf(m2 / (float)DM + p.eps));
+        }
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
+    if (threadIdx.x == 64) DIT_STAMP(60);
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_2sm(tmem_base, 512);
@@ -753,56 +928,108 @@ int tmap_2d_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long col
 
 }  // namespace
 
-// h <- h1 + gate2 * (gelu(LNmod(h1) W1^T + b1) W2^T + b2),  h1 = h + gate1 * (O Wp^T + bp)   (in place on h, fp32)
+// h_out <- h1 + gate2 * (gelu(LNmod(h1) W1^T + b1) W2^T + b2),  h1 = h_in + gate1 * (O Wp^T + bp)   (fp32 rows of D = 384)
 // LNmod(x)[m, :] = LN(x[m, :]) * (1 + scale2[m / rows_per_mod]) + shift2[m / rows_per_mod]; gate / shift / scale rows are
-// mod_ld floats apart.  stats_out (optional) receives (mean, rstd) of every new h row.  D = 384.
-extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
-                                       const float* b1, const void* W2, const float* b2, int hidden, float* h,
-                                       long long ldh, int M, int D, const float* gate1, const float* shift2,
-                                       const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
-                                       float eps, float* stats_out, void* stream) {
-    XD_CHECK_ARG(O && Wp && bp && W1 && b1 && W2 && b2 && h && gate1 && shift2 && scale2 && gate2 && M > 0);
-    XD_CHECK_ARG(D == DM && hidden % 128 == 0 && hidden >= 128 && rows_per_mod > 0);
-    XD_CHECK_ARG(ldo % 8 == 0 && ldh % 4 == 0 && mod_ld % 4 == 0);
-    XD_CHECK_ARG(aligned16(O) && aligned16(Wp) && aligned16(W1) && aligned16(W2) && aligned16(h) && aligned16(bp) &&
-                 aligned16(b1) && aligned16(b2) && aligned16(gate1) && aligned16(shift2) && aligned16(scale2) &&
-                 aligned16(gate2) && (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0);
-    CUtensorMap tO, tWp, tW1, tW2, tH;
-    int rc;
-    if ((rc = tmap_2d_bf16(&tO, O, M, DM, ldo, 128))) return rc;
-    if ((rc = tmap_2d_bf16(&tWp, Wp, DM, DM, DM, 96))) return rc;
-    if ((rc = tmap_2d_bf16(&tW1, W1, hidden, DM, DM, 64))) return rc;
-    if ((rc = tmap_2d_bf16(&tW2, W2, DM, hidden, hidden, 96))) return rc;
-    if ((rc = tmap_epi(&tH, h, M, DM, ldh, true))) return rc;
+// mod_ld floats apart.  stats_out (optional) receives (mean, rstd) of every new row.  h_out may be h_in (in place) -- then one
+// CTA pair owns each 256-row tile; with DISTINCT buffers and few tiles (small M: a shard of a strong-scaled batch) the hidden
+// dimension of a tile is split over `split` CTA pairs of one cluster (2, 3 or 4; 0 = choose from M and the SM count).
+namespace {
+template <int G>
+int launch_mlp(const CUtensorMap& tO, const CUtensorMap& tWp, const CUtensorMap& tW1, const CUtensorMap& tW2,
+               const CUtensorMap& tHin, const CUtensorMap& tH, const MlpParams& p, int tiles, cudaStream_t stream, bool query,
+               int* max_clusters) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(dit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        if (cudaFuncSetAttribute(dit_mlp_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
             return XD_ERR_CUDA;
         }
         configured = true;
     }
-    MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
-                reinterpret_cast<float2*>(stats_out), eps};
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * ((M + 255) / 256));
+    cfg.gridDim = dim3(2 * G * tiles);
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = (cudaStream_t)stream;
+    cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = 2 * G;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
+    if (query) {                                         // how many clusters of 2G CTAs can be resident at once
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(max_clusters, dit_mlp_kernel<G>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            *max_clusters = 0;
+        }
+        return XD_OK;
+    }
     cfg.numAttrs = xd_pdl_enabled_gemm() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, dit_mlp_kernel, tO, tWp, tW1, tW2, tH, p) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, dit_mlp_kernel<G>, tO, tWp, tW1, tW2, tHin, tH, p) != cudaSuccess) {
         xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
         return XD_ERR_CUDA;
     }
     return XD_OK;
+}
+}  // namespace
+
+extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
+                                       const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
+                                       float* h_out, long long ldh, int M, int D, const float* gate1, const float* shift2,
+                                       const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
+                                       float eps, float* stats_out, int split, void* stream) {
+    XD_CHECK_ARG(O && Wp && bp && W1 && b1 && W2 && b2 && h_in && h_out && gate1 && shift2 && scale2 && gate2 && M > 0);
+    XD_CHECK_ARG(D == DM && hidden % 128 == 0 && hidden >= 128 && rows_per_mod > 0);
+    XD_CHECK_ARG(ldo % 8 == 0 && ldh % 4 == 0 && mod_ld % 4 == 0);
+    XD_CHECK_ARG(aligned16(O) && aligned16(Wp) && aligned16(W1) && aligned16(W2) && aligned16(h_in) && aligned16(h_out) &&
+                 aligned16(bp) && aligned16(b1) && aligned16(b2) && aligned16(gate1) && aligned16(shift2) &&
+                 aligned16(scale2) && aligned16(gate2) && (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0);
+    XD_CHECK_ARG(split >= 0 && split <= 4 && (split <= 1 || (h_in != h_out && hidden % (128 * split) == 0)));
+    CUtensorMap tO, tWp, tW1, tW2, tHin, tH;
+    int rc;
+    if ((rc = tmap_2d_bf16(&tO, O, M, DM, ldo, 128))) return rc;
+    if ((rc = tmap_2d_bf16(&tWp, Wp, DM, DM, DM, 96))) return rc;
+    if ((rc = tmap_2d_bf16(&tW1, W1, hidden, DM, DM, 64))) return rc;
+    if ((rc = tmap_2d_bf16(&tW2, W2, DM, hidden, hidden, 96))) return rc;
+    if ((rc = tmap_epi(&tHin, h_in, M, DM, ldh, true))) return rc;
+    if ((rc = tmap_epi(&tH, h_out, M, DM, ldh, true))) return rc;
+    const int tiles = (M + 255) / 256;
+    long long* prof = nullptr;
+#ifdef XDB200_INSTRUMENT
+    if (const char* e = getenv("XDB200_DIT_PROF")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
+    MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
+                reinterpret_cast<float2*>(stats_out), eps, h_out, ldh, prof};
+    cudaStream_t st = (cudaStream_t)stream;
+    int G = split;
+    if (G == 0) {
+        // widest split whose clusters are all resident at once (one wave) -- only worth it when the tiles alone leave most
+        // SM pairs idle.  Cluster capacity is a property of the device: queried once per G.
+        static int cap[5] = {0, 0, -1, -1, -1};
+        G = 1;
+        if (h_in != h_out && xd_split_enabled()) {       // (a split changes the fc2 summation order with the row count)
+            for (int g = 2; g <= 4; ++g) {
+                if (hidden % (128 * g)) continue;
+                if (cap[g] < 0) {
+                    int n = 0;
+                    if (g == 2) launch_mlp<2>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, true, &n);
+                    if (g == 3) launch_mlp<3>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, true, &n);
+                    if (g == 4) launch_mlp<4>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, true, &n);
+                    cap[g] = n;
+                }
+                if (tiles <= cap[g]) G = g;
+            }
+        }
+    }
+    switch (G) {
+        case 2: return launch_mlp<2>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, false, nullptr);
+        case 3: return launch_mlp<3>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, false, nullptr);
+        case 4: return launch_mlp<4>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, false, nullptr);
+        default: return launch_mlp<1>(tO, tWp, tW1, tW2, tHin, tH, p, tiles, st, false, nullptr);
+    }
 }
 
 // O[m, 64h : 64h + 64] = softmax_per_image( q_h k_h^T / sqrt(64) ) v_h  with [q_h | k_h | v_h] = LNmod(h) Wqkv_h^T + b_h:

@@ -186,16 +186,19 @@ __global__ void upsample2_kernel(const bf16* __restrict__ x, long long ldx, int 
         *reinterpret_cast<const bf16x8*>(x + ((img * H + ho / 2) * W + wo / 2) * ldx + j * 8);
 }
 
-// rows x C bf16 copy between strided buffers (skip-connection concat slots)
-__global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int C, bf16* out,
-                                 long long ldo) {
+// rows x C bf16 copy between strided buffers; row r = (batch r / rpb, row r % rpb) with separate batch strides (e.g. the
+// self-attention [q | k | v] rows of every image appended behind that image's encoder rows: layers/attention.py:166-180)
+__global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long long x_bs, long long rows, long long rpb,
+                                 int C, bf16* out, long long ldo, long long o_bs) {
     pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int V = C / 8;
     if (i >= rows * V) return;
     const long long r = i / V;
     const int j = (int)(i % V);
-    *reinterpret_cast<bf16x8*>(out + r * ldo + j * 8) = *reinterpret_cast<const bf16x8*>(x + r * ldx + j * 8);
+    const long long b = r / rpb, t = r - b * rpb;
+    *reinterpret_cast<bf16x8*>(out + b * o_bs + t * ldo + j * 8) =
+        *reinterpret_cast<const bf16x8*>(x + b * x_bs + t * ldx + j * 8);
 }
 
 // eps = u + w (c - u)   (samplers/ancestral.py:229-231), float4 vectorised
@@ -311,11 +314,12 @@ extern "C" int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H,
     return XD_OK;
 }
 
-extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long rows, int C, void* out, long long ldo,
-                                 void* stream) {
-    XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0);
-    xd_launch(copy_rows_kernel, blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, rows, C,
-                                                                                   (bf16*)out, ldo);
+extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, long long rows, long long rows_per_batch,
+                                 int C, void* out, long long ldo, long long o_bs, void* stream) {
+    XD_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && x_bs % 8 == 0 && o_bs % 8 == 0 &&
+                 rows_per_batch > 0 && rows > 0);
+    xd_launch(copy_rows_kernel, blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, x_bs, rows,
+              rows_per_batch, C, (bf16*)out, ldo, o_bs);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

@@ -1194,3 +1194,8 @@ extern "C" int xd_set_split_k(int enabled) {
     g_split_k = enabled ? 1 : 0;
     return XD_OK;
 }
+// Work splits whose summation order depends on the row count (split-K here, the hidden-split clusters of dit_block.cu)
+bool xd_split_enabled() {
+    static const int split_env = getenv("XDB200_SPLITK") ? atoi(getenv("XDB200_SPLITK")) : 1;
+    return (g_split_k >= 0 ? g_split_k : split_env) != 0;
+}

@@ -230,11 +230,27 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
         : "memory");
 }
 // arrive on the mbarrier at this offset in BOTH CTAs once all previously issued MMAs completed
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// (cta_mask = the two cluster ranks of the pair: 3 in a cluster of two, 3 << (rank & ~1) in a larger cluster)
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
         : "memory");
+}
+
+// ---------------------------------------------------------------- distributed shared memory (clusters)
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in the CTA with cluster rank `cta_rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void sts128_cluster(uint32_t addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts64_cluster(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
 
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes with the

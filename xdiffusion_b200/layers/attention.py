@@ -101,31 +101,111 @@ class QKVAttention(torch.nn.Module):
         self.num_heads = num_heads
 
 
-class SpatialCrossAttention(ContextBlock, Packed):
-    """UNet attention block over pixels (reference: attention.py:20-141 with context_dim = -1, i.e.
-    pure self-attention): GN32 -> qkv (1x1) -> per-head-interleaved softmax attention with
-    ch^-1/4 on q and k -> proj_out (1x1, zero-init) -> residual."""
+#: key of the per-loop store {id(layer): encoder K/V buffer} in the sampling loop's static conditioning dict
+TEXT_KV_KEY = "_xdb_unet_text_kv"
 
-    def __init__(self, in_channels, context_dim=None, heads=8, dim_head=64, dropout=0.0, **kwargs):
+
+class ChanLayerNormGain(torch.nn.Module):
+    """Parameter holder of the reference's ``LayerNorm(feats, dim)`` (attention.py:284-310): gain ``g`` only."""
+
+    def __init__(self, feats, dim=-1):
         super().__init__()
-        if context_dim not in (None, -1):
-            raise NotImplementedError("encoder (cross-attention) context in the UNet is a 'next' row (SURVEY 8f)")
-        for k in ("pre_layer_norm", "post_layer_norm", "context_layer_norm", "disable_self_attention"):
+        self.dim = dim
+        self.g = torch.nn.Parameter(torch.ones(feats, *((1,) * (-dim - 1))))
+
+    def forward(self, x):
+        var = torch.var(x, dim=self.dim, unbiased=False, keepdim=True)
+        mean = torch.mean(x, dim=self.dim, keepdim=True)
+        return (x - mean) * (var + 1e-5).rsqrt() * self.g
+
+
+class AttentionPooling(torch.nn.Module):
+    """Imagen attention pooling (reference: attention.py:231-283): a class token (sequence mean + positional embedding)
+    attends over [class token, sequence].  It only ever sees the text embeddings, which do not change during a sampling
+    loop: it runs ONCE per loop (Unet.precompute_context) in plain fp32 tensor ops, never per timestep."""
+
+    def __init__(self, num_heads, embed_dim):
+        super().__init__()
+        self.positional_embedding = torch.nn.Parameter(torch.randn(1, embed_dim) / embed_dim ** 0.5)
+        self.k_proj = torch.nn.Linear(embed_dim, embed_dim)
+        self.q_proj = torch.nn.Linear(embed_dim, embed_dim)
+        self.v_proj = torch.nn.Linear(embed_dim, embed_dim)
+        self.num_heads = num_heads
+        self.dim_per_head = embed_dim // self.num_heads
+
+    def forward(self, x):
+        bs, length, width = x.shape
+        H, d = self.num_heads, self.dim_per_head
+        cls = x.mean(dim=1, keepdim=True) + self.positional_embedding.to(x.dtype)
+        xx = torch.cat([cls, x], dim=1)
+        q = self.q_proj(cls).view(bs, 1, H, d).transpose(1, 2)                  # [bs, H, 1, d]
+        k = self.k_proj(xx).view(bs, length + 1, H, d).transpose(1, 2)
+        v = self.v_proj(xx).view(bs, length + 1, H, d).transpose(1, 2)
+        w = torch.softmax((q @ k.transpose(-1, -2)).float() / math.sqrt(d), dim=-1)   # (d^-1/4)^2 on the logits
+        # the reference returns `a.reshape(bs, -1, 1)` of a [bs*H, d, 1] tensor: channel = head * d + c
+        return (w @ v).reshape(bs, H * d)
+
+
+class SpatialCrossAttention(ContextBlock, Packed):
+    """UNet attention block over pixels (reference: attention.py:20-141): GN32 -> qkv (1x1) -> per-head-interleaved
+    softmax attention with ch^-1/4 on q and k -> proj_out (1x1, zero-init) -> residual.  With ``context_dim`` > 0
+    (Imagen / GLIDE text conditioning) the text embeddings go through the context adapter, an optional channel
+    LayerNorm and ``_encoder_kv`` (1x1), and the resulting keys / values are concatenated IN FRONT of the
+    self-attention keys / values (attention.py:107-130,166-180).  The encoder half is timestep-invariant and is
+    computed once per sampling loop (``encode_context``)."""
+
+    def __init__(self, in_channels, context_dim=None, context_projection_input_dim=None,
+                 context_projection_output_dim=None, heads=8, dim_head=64, dropout=0.0, context_layer_norm=False,
+                 context_adapter=None, **kwargs):
+        super().__init__()
+        for k in ("pre_layer_norm", "post_layer_norm", "disable_self_attention", "is_video"):
             if kwargs.get(k):
                 raise NotImplementedError(k)
+        if context_projection_input_dim is not None and context_projection_output_dim is not None:
+            raise NotImplementedError("_context_proj (factorised context projection)")
+        context_dim = None if context_dim in (None, -1) else context_dim
+        self._context_dim = context_dim
         self._channels = in_channels
         if dim_head == -1:
             self._num_heads = heads
         else:
             assert in_channels % dim_head == 0
             self._num_heads = in_channels // dim_head
+        # sub-modules are registered in the reference's order (attention.py:61-98): LoRA files list their tensors in module
+        # traversal order (xdiffusion_b200/lora.py)
         self._norm = torch.nn.GroupNorm(num_groups=32, num_channels=in_channels)
+        if context_dim is not None:
+            self._context_layer_norm = ChanLayerNormGain(context_dim, dim=-2) if context_layer_norm \
+                else torch.nn.Identity()
         self._qkv = torch.nn.Conv1d(in_channels, in_channels * 3, 1)
         self._attention = QKVAttention(self._num_heads)
+        if context_dim is not None:
+            from ..utils import instantiate_from_config
+            if not (context_adapter and "target" in context_adapter):
+                raise NotImplementedError("SpatialCrossAttention(context_dim=...) without a context_adapter")
+            self._context_adapter = instantiate_from_config(dict(context_adapter))
+            self._encoder_kv = torch.nn.Conv1d(context_dim, in_channels * 2, 1)
         self._proj_out = zero_module(torch.nn.Conv1d(in_channels, in_channels, 1))
 
-    def forward(self, x, context: Optional[Dict] = None, out=None):
-        """x bf16 NHWC [nimg, H, W, C] (a channel slice of a wider buffer is fine) -> same shape."""
+    def encode_context(self, context: Dict, tokens: int, kv=None):
+        """Encoder keys / values of this block for the loop's conditioning (timestep-invariant): returns (or refreshes in
+        place) the bf16 buffer [B, L + tokens, heads, 3, ch] whose first L rows carry [unused | k_enc | v_enc] per head;
+        the forward appends the block's own [q | k | v] rows behind them every step."""
+        ctx = self._context_layer_norm(self._context_adapter(context).float())       # [B, Cctx, L]
+        B, Cc, L = ctx.shape
+        heads = self._num_heads
+        ch = self._channels // heads
+        w = self.packed("wkv", (self._encoder_kv.weight,), lambda: bf16_weight(self._encoder_kv.weight))
+        yb = ctx.permute(0, 2, 1).reshape(B * L, Cc).to(torch.bfloat16).contiguous()
+        ekv = ops.linear(yb, w, self._encoder_kv.bias).view(B, L, heads, 2, ch)      # channel = head * 2ch + {k, v} * ch + c
+        if kv is None or kv.shape != (B, L + tokens, heads, 3, ch):
+            kv = torch.zeros((B, L + tokens, heads, 3, ch), device=ekv.device, dtype=torch.bfloat16)
+        kv[:, :L, :, 1:].copy_(ekv)
+        return kv
+
+    def forward(self, x, context: Optional[Dict] = None, out=None, kv=None):
+        """x bf16 NHWC [nimg, H, W, C] (a channel slice of a wider buffer is fine) -> same shape.
+        ``kv``: the buffer of ``encode_context`` when the block has encoder context."""
         nimg, H, W, C = x.shape
         T, heads = H * W, self._num_heads
         ch = C // heads
@@ -137,6 +217,23 @@ class SpatialCrossAttention(ContextBlock, Packed):
         n = ops.groupnorm(xs, self._norm.weight, self._norm.bias, eps=self._norm.eps)          # dense [nimg,T,C]
         qkv = ops.linear(n.view(nimg * T, C), wq, self._qkv.bias).view(nimg, T, heads, 3, ch)
         q, k, v = (qkv[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+        if self._context_dim is not None:
+            # the sampling loop keeps one buffer per block in its static conditioning (filled on the first, eager step and
+            # refreshed by Unet.precompute_context); a bare forward re-encodes the text every call, like the reference
+            store = context.get(TEXT_KV_KEY) if context is not None else None
+            if kv is None and store is not None:
+                kv = store.get(id(self))
+            if kv is None:
+                if context is None or "text_embeddings" not in context:
+                    raise RuntimeError("SpatialCrossAttention(context_dim > 0) needs text_embeddings in the context")
+                kv = self.encode_context(context, T)
+                if store is not None:
+                    store[id(self)] = kv
+            self.tokens_seen = T
+            L = kv.shape[1] - T
+            assert kv.shape[0] == nimg, "factorised (video) encoder context is not supported"
+            torch.ops.xdb200.copy_rows(qkv.view(nimg, T, 3 * C), kv.view(nimg, L + T, 3 * C)[:, L:])
+            k, v = (kv[:, :, :, i].permute(0, 2, 1, 3) for i in (1, 2))             # [nimg, heads, L + T, ch]
         a = ops.attention(q, k, v, 1.0 / math.sqrt(ch))             # (ch^-1/4)^2 on the logits
         a2 = a.permute(0, 2, 1, 3).reshape(nimg * T, C)
         if out is None:

@@ -152,6 +152,35 @@ class RunProjection(torch.nn.Module):
         return context
 
 
+class PooledTextEmbeddingsToTimestep(torch.nn.Module):
+    """timestep_embedding += LayerNorm(Linear(AttentionPooling(LayerNorm(text_embeddings))))
+    (reference: embedding.py:146-169).  The addend depends on the text only: ``pool`` computes it once per sampling
+    loop (Unet.precompute_context stores it under POOLED_KEY); per timestep only the add runs, on the device kernel."""
+    POOLED_KEY = "_xdb_pooled_text"
+
+    def __init__(self, text_embedding_dim: int, time_embedding_dim: int, attention_pooling_heads: int, **kwargs):
+        super().__init__()
+        from .attention import AttentionPooling
+        self._encoder_pooling = torch.nn.Sequential(
+            torch.nn.LayerNorm(text_embedding_dim), AttentionPooling(attention_pooling_heads, text_embedding_dim),
+            torch.nn.Linear(text_embedding_dim, time_embedding_dim), torch.nn.LayerNorm(time_embedding_dim))
+
+    @torch.no_grad()
+    def pool(self, context: Dict):
+        return self._encoder_pooling(context["text_embeddings"].float()).contiguous()
+
+    def forward(self, context: Dict, **kwargs):
+        assert "text_embeddings" in context and "timestep_embedding" in context
+        pooled = context.get(self.POOLED_KEY)
+        if pooled is None:
+            pooled = self.pool(context)
+        t = context["timestep_embedding"].contiguous()
+        out = torch.empty_like(t)
+        torch.ops.xdb200.add_rows_periodic(t, pooled, t.shape[0], out)
+        context["timestep_embedding"] = out
+        return context
+
+
 class ContextProjection(torch.nn.Module):
     """context[out] = Mlp(GELU-tanh)(context[in]) over (B, L, C) (reference: embedding.py:202-237)."""
 

@@ -122,12 +122,14 @@ def _dit_attn(h, stats, shift, scale, rows_per_mod, eps, wh, bias, heads, sm_sca
     _count()
 
 
-@_op("dit_proj_mlp(Tensor o, Tensor wp, Tensor bp, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor(a!) h, Tensor gate1, "
-     "Tensor shift2, Tensor scale2, Tensor gate2, int rows_per_mod, float eps, Tensor(b!)? stats) -> ()")
-def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, rows_per_mod, eps, stats):
-    """Fused proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual, in place on h (fp32 [M, 384])."""
-    _cuda(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, stats)
+@_op("dit_proj_mlp(Tensor o, Tensor wp, Tensor bp, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor h_in, Tensor(a!) h, "
+     "Tensor gate1, Tensor shift2, Tensor scale2, Tensor gate2, int rows_per_mod, float eps, Tensor(b!)? stats, int split) -> ()")
+def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h_in, h, gate1, shift2, scale2, gate2, rows_per_mod, eps, stats, split):
+    """Fused proj + gated residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual: h_in -> h (fp32 [M, 384]; h may be
+    h_in).  split: CTA pairs per 256-row tile (0 = chosen from M; > 1 needs distinct buffers)."""
+    _cuda(o, wp, bp, w1, b1, w2, b2, h_in, h, gate1, shift2, scale2, gate2, stats)
     M, D = h.shape
+    assert h_in.shape == h.shape and h_in.dtype == torch.float32 and h_in.stride() == h.stride()
     hidden = w1.shape[0]
     assert o.dtype == torch.bfloat16 and o.shape == (M, D) and o.stride(1) == 1 and h.dtype == torch.float32 and h.stride(1) == 1
     assert wp.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and wp.shape == (D, D)
@@ -136,8 +138,8 @@ def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, gate1, shift2, scale2, gate2, ro
     assert all(t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) == gate1.stride(0) for t in mods)
     assert stats is None or (stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= 2 * M)
     _lib.check(_lib.lib().xd_dit_proj_mlp_bf16_tc(_p(o), o.stride(0), _p(wp), _p(bp), _p(w1), _p(b1), _p(w2), _p(b2), hidden,
-                                                  _p(h), h.stride(0), M, D, _p(gate1), _p(shift2), _p(scale2), _p(gate2),
-                                                  gate1.stride(0), rows_per_mod, eps, _p(stats), _stream()),
+                                                  _p(h_in), _p(h), h.stride(0), M, D, _p(gate1), _p(shift2), _p(scale2),
+                                                  _p(gate2), gate1.stride(0), rows_per_mod, eps, _p(stats), split, _stream()),
                "xd_dit_proj_mlp_bf16_tc")
     _count()
 
@@ -356,10 +358,13 @@ def _upsample2x(x, out):
 
 @_op("copy_rows(Tensor x, Tensor(a!) out) -> ()")
 def _copy_rows(x, out):
+    """bf16 [batch, rows, C] -> [batch, rows, C], both strided (unit stride on C)."""
     _cuda(x, out)
-    rows, C = x.shape
-    _lib.check(_lib.lib().xd_copy_rows_bf16(_p(x), x.stride(0), rows, C, _p(out), out.stride(0), _stream()),
-               "xd_copy_rows_bf16")
+    nb, rows, C = x.shape
+    assert out.shape == x.shape and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    assert x.stride(2) == 1 and out.stride(2) == 1
+    _lib.check(_lib.lib().xd_copy_rows_bf16(_p(x), x.stride(1), x.stride(0), nb * rows, rows, C, _p(out), out.stride(1),
+                                            out.stride(0), _stream()), "xd_copy_rows_bf16")
     _count()
 
 

@@ -22,6 +22,8 @@ from ..utils import instantiate_from_config, instantiate_partial_from_config
 
 # Fused half-block kernels (csrc/dit_block.cu); XDB200_DIT_FUSED=0 runs one kernel per operator (round-1 path).
 FUSED_BLOCK = os.environ.get("XDB200_DIT_FUSED", "1") == "1"
+# CTA pairs per 256-row tile of the fused MLP kernel: 0 = chosen by the library from the row count, 1 = never split
+MLP_SPLIT = int(os.environ.get("XDB200_DIT_MLP_SPLIT", "0"))
 
 
 class DiTBlock(torch.nn.Module):
@@ -133,6 +135,9 @@ class DiT(torch.nn.Module, Packed):
         fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
         # (mean, rstd) of every row of h: emitted by the fused MLP kernel of block n, consumed by the LayerNorm of block n + 1
         stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32) if fused else None
+        # The fused MLP kernel reads h and writes h_next: with two buffers a small batch (few 256-row tiles, e.g. one shard of
+        # a strong-scaled batch) lets it split every tile over several CTA pairs (see csrc/dit_block.cu).
+        h_next = torch.empty_like(h) if fused else None
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
@@ -149,8 +154,9 @@ class DiT(torch.nn.Module, Packed):
                     o = blk.attn.attend(h, T, ln=(s1, sc1, T))
                 _, wp = blk.attn.weights()
                 w1, w2 = blk.mlp.weights()
-                torch.ops.xdb200.dit_proj_mlp(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h,
-                                              g1, s2, sc2, g2, T, 1e-6, stats)
+                torch.ops.xdb200.dit_proj_mlp(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h, h_next,
+                                              g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT)
+                h, h_next = h_next, h
                 continue
             # ln=: LayerNorm + modulate feeding qkv / fc1 (layernorm_modulate kernel; fused into the GEMM with XDB200_LN_FUSED=1)
             blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))

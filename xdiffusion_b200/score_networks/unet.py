@@ -11,7 +11,8 @@ from typing import Dict, List
 import torch
 
 from .. import ops
-from ..layers.embedding import ContextEmbedSequential
+from ..layers.attention import TEXT_KV_KEY, SpatialCrossAttention
+from ..layers.embedding import ContextEmbedSequential, PooledTextEmbeddingsToTimestep
 from ..layers.resnet import Downsample, ResnetBlockBigGAN, Upsample
 from ..layers.utils import Packed, bf16_weight
 from ..utils import instantiate_partial_from_config
@@ -102,8 +103,31 @@ class Unet(torch.nn.Module, Packed):
     def _from_nhwc_out(self, y, x):
         return y
 
-    def _run_attention(self, layer, h, frames, out):
-        return layer(h, out=out)
+    def _run_attention(self, layer, h, frames, out, context=None):
+        return layer(h, context=context, out=out)
+
+    # ------------------------------------------------------------------ timestep-invariant text conditioning
+    def precompute_context(self, context):
+        """Called by the sampling loop on its OWN static conditioning dict (at construction and after every in-place
+        refresh).  Text-conditioned configs (Imagen base / GLIDE): the attention-pooled text embedding that is added to the
+        timestep embedding and every attention block's encoder keys / values depend on the text only, so they are
+        computed here, once per loop, into buffers that live in that dict (a captured CUDA graph keeps reading them; a
+        refresh rewrites them in place)."""
+        if "text_embeddings" not in context:
+            return
+        for ct in self._context_transformers:
+            if isinstance(ct, PooledTextEmbeddingsToTimestep):
+                new, old = ct.pool(context), context.get(ct.POOLED_KEY)
+                if old is not None and old.shape == new.shape:
+                    old.copy_(new)
+                else:
+                    context[ct.POOLED_KEY] = new
+        layers = {id(m): m for m in self.modules() if isinstance(m, SpatialCrossAttention) and m._context_dim is not None}
+        if layers:
+            store = context.setdefault(TEXT_KV_KEY, {})
+            for key, kv in store.items():               # blocks that already ran: re-encode into their buffers
+                again = layers[key].encode_context(context, layers[key].tokens_seen, kv)
+                assert again is kv
 
     # ------------------------------------------------------------------ forward
     def _emb_all(self):
@@ -128,7 +152,7 @@ class Unet(torch.nn.Module, Packed):
         emb = ops.linear(st, w, b, out_dtype=torch.float32)
         return lambda blk: emb[:, offs[id(blk)][0]: offs[id(blk)][0] + offs[id(blk)][1]]
 
-    def _run_entry(self, entry, h, emb_of, samples, frames, out):
+    def _run_entry(self, entry, h, emb_of, samples, frames, out, context=None):
         mods = list(entry)
         for j, layer in enumerate(mods):
             dst = out if j == len(mods) - 1 else None
@@ -137,7 +161,7 @@ class Unet(torch.nn.Module, Packed):
             elif isinstance(layer, (Downsample, Upsample)):
                 h = layer(h, out=dst)
             else:
-                h = self._run_attention(layer, h, frames, dst)
+                h = self._run_attention(layer, h, frames, dst, context)
         return h
 
     def forward(self, x, context: Dict):
@@ -177,10 +201,10 @@ class Unet(torch.nn.Module, Packed):
             if isinstance(entry[0], Downsample):
                 hh, ww = hh // 2, ww // 2
             cats[j] = cat_buffer(j, hh, ww)
-            h = self._run_entry(entry, h, emb_of, samples, frames, cats[j][..., h_w[n_skip - 1 - j]:])
+            h = self._run_entry(entry, h, emb_of, samples, frames, cats[j][..., h_w[n_skip - 1 - j]:], context)
             if taps is not None:
                 taps[f"downs.{j - 1}"] = h.float().clone()
-        h = self._run_entry(self.middle, h, emb_of, samples, frames, cats[n_skip - 1][..., :h_w[0]])
+        h = self._run_entry(self.middle, h, emb_of, samples, frames, cats[n_skip - 1][..., :h_w[0]], context)
         if taps is not None:
             taps["middle"] = h.float().clone()
         for k, entry in enumerate(self.ups):
@@ -189,7 +213,7 @@ class Unet(torch.nn.Module, Packed):
                 dst = nxt[..., :h_w[k + 1]]
             else:
                 dst = None
-            h = self._run_entry(entry, cats[n_skip - 1 - k], emb_of, samples, frames, dst)
+            h = self._run_entry(entry, cats[n_skip - 1 - k], emb_of, samples, frames, dst, context)
             if taps is not None:
                 taps[f"ups.{k}"] = h.float().clone()
         gn = self.final_projection[0]

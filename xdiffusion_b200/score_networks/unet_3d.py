@@ -47,7 +47,7 @@ class Unet(Unet2D):
         B, C, F, H, W = x.shape
         return y.view(B, F, -1, H, W).permute(0, 2, 1, 3, 4).contiguous()
 
-    def _run_attention(self, layer, h, frames, out):
+    def _run_attention(self, layer, h, frames, out, context=None):
         fn = layer.fn
         if isinstance(fn, TemporalSelfAttention):
             return fn(h, frames, out=out)
