@@ -245,7 +245,8 @@ def dit_block_roofline(batch, device):
     s1, sc1, g1, s2, sc2, g2 = (mod[:, i * D:(i + 1) * D] for i in range(6))
     stats = torch.zeros(M, 2, device=device)
     X = torch.ops.xdb200
-    t_mlp = _time_in_graph(lambda: X.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h2, g1, s2, sc2, g2, T, 1e-6, stats, 0))
+    from xdiffusion_b200.score_networks.dit import MLP_SPLIT
+    t_mlp = _time_in_graph(lambda: X.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h2, g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT))
     t_att = _time_in_graph(lambda: X.dit_attn(h, stats, s1, sc1, T, 1e-6, wh, bh, H, 0.125, o))
     f_mlp = 2.0 * M * (D * D + 2 * D * Hd)
     f_att = 2.0 * M * 3 * D * D + 4.0 * M * T * D
@@ -439,7 +440,15 @@ class Runner:
                 "gpu_launches": rec["gpu_launches"], "launches_per_timestep": rec["launches_per_timestep"],
                 "ms_per_timestep": rec["ms_per_timestep"],
                 "step_tensor_frac_of_sustained": rec["step_tensor_frac_of_sustained"]}
-        if main == "dit":
+        from xdiffusion_b200.score_networks import dit as dit_mod
+        if main == "dit" and per_gpu * 16 < dit_mod.FUSED_MIN_ROWS:   # small shards run one kernel per operator
+            tf, per = gemm_roofline(per_gpu, self.device)
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                                "traffic": ncu_dram_bytes("gemm"), "peak_source": src, "per_shape": per,
+                                "kernel": "gemm_tc_kernel (tcgen05, TMA epilogue): qkv + proj + fc1 + fc2 of one DiT block "
+                                          f"at M = {per_gpu * 16} rows with their real epilogues (shards below "
+                                          f"{dit_mod.FUSED_MIN_ROWS} rows do not use the fused half-block kernels)"}
+        elif main == "dit":
             tf, tf_block, per = dit_block_roofline(per_gpu, self.device)
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
                                 "traffic": ncu_dram_bytes("ditmlp"), "peak_source": src, "per_shape": per,

@@ -182,6 +182,11 @@ int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int
  * `torch.cat([ek, k], dim=-1)` of QKVAttention (layers/attention.py:166-180). */
 int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, long long rows, long long rows_per_batch, int C,
                       void* out, long long ldo, long long o_bs, void* stream);
+/* Video-mask blend of the autoregressive / conditional video loops: x[b, c, f] = mask[b, f] ? x[b, c, f] : x0[b, c, f],
+ * in place on x (fp32 [B, C, F, HW]), mask = B x F bytes (non-zero = generate, zero = keep the conditioning frame).
+ * Replaces `torch.where(video_mask[:, None, :, None, None], x_t, x0)` before and after every reverse-process step
+ * (diffusion/ddpm.py:963-982). */
+int xd_blend_frames(float* x, const float* x0, const void* mask, int B, int C, int F, int HW, void* stream);
 /* eps = u + w (c - u)  (samplers/ancestral.py:229-231, samplers/ddim.py:69-71) */
 int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, long long n, void* stream);
 

@@ -60,7 +60,12 @@ class OracleModel:
         N = num_sampling_steps or self.steps
         B = x_T.shape[0]
         x = x_T
+        mask = ctx.get("video_mask")                      # (B, F) bool: True = generate, False = keep ctx["x0"]
+        if mask is not None:
+            mask = mask[:, None, :, None, None]
         for i in reversed(range(N)):
+            if mask is not None:                          # ddpm.py:963-967
+                x = torch.where(mask, x, ctx["x0"])
             c = dict(ctx)
             if self.sched_kind == "ContinuousNoiseScheduler":
                 idx_s, idx_t = schedules.continuous_indices(i, N, self.steps)
@@ -90,4 +95,6 @@ class OracleModel:
             if trace is not None:
                 trace.append((i, o, x_next))
             x = x_next
+            if mask is not None:                          # ddpm.py:979-982
+                x = torch.where(mask, x, ctx["x0"])
         return samplers.unnormalize(x)

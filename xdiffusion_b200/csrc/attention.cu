@@ -388,8 +388,11 @@ attention_kernel(const AttnParams p) {
 }
 
 
-// ---- Tq == 16, Tk <= 16 * KT (cross-attention over a short context, e.g. PixArt: 16 latent tokens x 77 text tokens):
-// one warp per (batch, head), same mma.sync structure as above with KT key blocks; keys >= Tk are masked to -inf.
+// ---- Tq <= 16, Tk <= 16 * KT (cross-attention over a short context, e.g. PixArt: 16 latent tokens x 77 text tokens; the
+// text-conditioned UNet: 16 or 4 pixels x (77 text + own) keys): one warp per (batch, head), same mma.sync structure as
+// above with KT key blocks; keys >= Tk are masked to -inf, query rows >= Tq are zero and never stored.  Longer query
+// sequences (the 8x8 level of the video UNet: 64 x 64) are cut into blocks of 16 rows, one warp each (the keys / values
+// of a head are staged once per block: 16 KB from L2 per 2 x 16 x 64 x 64 MACs).
 // Replaces the generic SIMT kernel, which took 131 us per launch on the PixArt workload (46 % of its step).
 template <int KT>
 __global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(const AttnParams p) {
@@ -397,13 +400,17 @@ __global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(con
     constexpr int W = KT > 5 ? 1 : 2;                      // warps per CTA (48 KB of static shared memory)
     __shared__ __align__(128) uint8_t sm[W][(1 + 2 * KT) * 2048];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long bh = (long long)blockIdx.x * W + warp;
-    if (bh >= (long long)p.B * p.H) return;
+    const int nqb = (p.Tq + 15) >> 4;                      // query blocks of 16 rows per (batch, head)
+    const long long item = (long long)blockIdx.x * W + warp;
+    if (item >= (long long)p.B * p.H * nqb) return;
+    const long long bh = item / nqb;
+    const int q0 = (int)(item - bh * nqb) * 16;
+    const int tq = min(16, p.Tq - q0);                     // live query rows of this block
     const int b = (int)(bh / p.H), h = (int)(bh % p.H);
     uint8_t* sQ = sm[warp];
     uint8_t* sK = sQ + 2048;
     uint8_t* sV = sK + KT * 2048;
-    const bf16* qp = p.q + b * p.q_bs + h * p.q_hs;
+    const bf16* qp = p.q + b * p.q_bs + h * p.q_hs + (long long)q0 * p.q_rs;
     const bf16* kp = p.k + b * p.k_bs + h * p.k_hs;
     const bf16* vp = p.v + b * p.v_bs + h * p.v_hs;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(con
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int idx = lane + 32 * i, row = idx >> 3, c = idx & 7;
-            rq[i] = *reinterpret_cast<const uint4*>(qp + (long long)row * p.q_rs + c * 8);
+            rq[i] = row < tq ? *reinterpret_cast<const uint4*>(qp + (long long)row * p.q_rs + c * 8) : zero;
         }
 #pragma unroll
         for (int i = 0; i < 4 * KT; ++i) {
@@ -528,12 +535,13 @@ __global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(con
         }
     }
     __syncwarp();
-    bf16* op = p.o + b * p.o_bs + h * p.o_hs;
+    bf16* op = p.o + b * p.o_bs + h * p.o_hs + (long long)q0 * p.o_rs;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int idx = lane + 32 * i, row = idx >> 3, cch = idx & 7;
-        *reinterpret_cast<uint4*>(op + (long long)row * p.o_rs + cch * 8) =
-            *reinterpret_cast<const uint4*>(sQ + row * 128 + ((cch ^ (row & 7)) << 4));
+        if (row < tq)
+            *reinterpret_cast<uint4*>(op + (long long)row * p.o_rs + cch * 8) =
+                *reinterpret_cast<const uint4*>(sQ + row * 128 + ((cch ^ (row & 7)) << 4));
     }
 }
 
@@ -575,8 +583,8 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
         }
         return XD_OK;
     }
-    if (Tq == T16 && Tk <= 128 && !relk && !scramble && !in_f32) {  // short-context cross-attention (PixArt 16 x 77)
-        const long long nbh = (long long)B * H;
+    if (Tq <= 128 && Tk <= 128 && !relk && !scramble && !in_f32) {  // short-context (cross-)attention (PixArt 16 x 77,
+        const long long nbh = (long long)B * H * ((Tq + 15) / 16);  // video 64 x 64): one warp per 16 query rows
         cudaError_t e;
         if (Tk <= 32) e = xd_launch(attention16xn_mma_kernel<2>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);
         else if (Tk <= 80) e = xd_launch(attention16xn_mma_kernel<5>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);

@@ -48,6 +48,7 @@ constexpr int ACC1_COL = 384;
 // launch); with a lag of 2 it has fc1(c + 1) + fc2(c - 1) = 3072 clk to finish and the pipe only waits at start-up.
 constexpr int FC2_LAG = 2;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(RING < 2 * KB, "the producer waits for the preceding kernel after RING projection weight tiles");
 
 struct MlpParams {
     int M, hidden, rows_per_mod;
@@ -59,7 +60,17 @@ struct MlpParams {
     float* h_out;               // split kernels (G > 1): the final pass addresses h_out directly
     long long ldh;
     long long* prof;            // -DXDB200_INSTRUMENT + XDB200_DIT_PROF=<device pointer>: 64 clock64() stamps per CTA
+    const uint8_t *wp, *w1, *w2;   // the three weight matrices (bytes), for the L2 prefetch at kernel entry
 };
+
+// Every CTA pulls its share of a weight matrix into L2 (4 KB pieces, round-robin over the grid).  Issued before
+// griddepcontrol.wait: weights do not depend on the preceding kernel, so the prefetch overlaps its tail.  Between two uses
+// of a block's weights (one timestep, ~1 ms) some 0.5 GB of activations stream through the 126 MB L2, so the first CTA
+// to touch a weight tile would otherwise pay DRAM latency on the 5-slot operand ring, and all CTAs run in lockstep.
+__device__ __forceinline__ void prefetch_weights_l2(const uint8_t* w, uint32_t bytes) {
+    for (uint32_t off = blockIdx.x * 4096u; off < bytes; off += gridDim.x * 4096u)
+        ptx::prefetch_l2(w + off, min(4096u, bytes - off));
+}
 
 // phase stamps for tools/prof_dit_phases.py (compiled out of the product build)
 #ifdef XDB200_INSTRUMENT
@@ -76,7 +87,8 @@ struct MlpParams {
 // store-drain + load-latency chain of ~1.2 us per chunk (the pass then cost ~7 us of the kernel's 45).
 //   FINAL = false (first pass): the caller issued the loads of chunks 0 and 1 before it waited for the accumulator; chunks
 //           2..4 are issued here and chunk 5 re-uses the box of chunk 0 once that chunk's store has drained it.
-//   FINAL = true: six distinct boxes, all six loads issued here.
+//   FINAL = true: six distinct boxes; the caller issued chunks 0..2 (into the panel, idle after the last fc1 MMA) while the
+//           last fc2 MMAs were still running, chunks 3..5 are issued here.
 template <bool TO_TMEM, bool FINAL>
 __device__ __forceinline__ void gated_residual_pass(const CUtensorMap* tmIn, const CUtensorMap* tmH, const uint32_t (&box)[6],
                                                     uint64_t* rbar, uint32_t parity, uint32_t t_addr, int m0w, int col_base,
@@ -84,7 +96,7 @@ __device__ __forceinline__ void gated_residual_pass(const CUtensorMap* tmIn, con
                                                     float& qq) {
     if (lane == 0) {
 #pragma unroll
-        for (int ci = FINAL ? 0 : 2; ci < (FINAL ? 6 : 5); ++ci) {
+        for (int ci = FINAL ? 3 : 2; ci < (FINAL ? 6 : 5); ++ci) {
             ptx::mbar_arrive_expect_tx(&rbar[ci], 4096);
             ptx::tma_load_2d_u32(box[ci], tmIn, ptx::smem_u32(&rbar[ci]), col_base + ci * 32, m0w);
         }
@@ -230,21 +242,22 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         ptx::tmem_alloc_2sm(tmem_ptr, 512);
         ptx::tmem_relinquish_2sm();
     }
+    if (warp == 2 && lane == 0) {
+        prefetch_weights_l2(p.wp, DM * DM * 2);
+        prefetch_weights_l2(p.w1, (uint32_t)p.hidden * DM * 2);
+        prefetch_weights_l2(p.w2, (uint32_t)p.hidden * DM * 2);
+    }
     ptx::tc_fence_before();
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     if (threadIdx.x == 64) DIT_STAMP(61);
-    pdl_wait();
-    if (threadIdx.x == 64) DIT_STAMP(62);
+    // griddepcontrol.wait is executed per role, by every thread that touches activations: the producer first fills the
+    // operand ring with projection weights (constant data), the MMA warp only ever reads shared memory / TMEM.
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs: own rows / own tile halves)
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                ptx::mbar_arrive_expect_tx_leader(&panel_full[kb], A_BYTES);
-                ptx::tma_load_2d_2sm(panel + kb * A_BYTES, &tmO, &panel_full[kb], kb * 64, m0);
-            }
             int s = 0;
             uint32_t ph = 0;
             auto load_b = [&](const CUtensorMap* tm, uint32_t bytes, int ck, int cn) {
@@ -253,8 +266,16 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
                 ptx::tma_load_2d_2sm(ring + s * SLOT_BYTES, tm, &ring_full[s], ck, cn);
                 if (++s == RING) { s = 0; ph ^= 1; }
             };
-            for (int kb = 0; kb < KB; ++kb)
-                for (int nh = 0; nh < 2; ++nh) load_b(&tmWp, 96 * 128, kb * 64, nh * 192 + rank * 96);
+            for (int i = 0; i < 2 * KB; ++i) {
+                if (i == RING) {                         // the ring is full of weights: now wait for the producer of O
+                    pdl_wait();
+                    for (int kb = 0; kb < KB; ++kb) {
+                        ptx::mbar_arrive_expect_tx_leader(&panel_full[kb], A_BYTES);
+                        ptx::tma_load_2d_2sm(panel + kb * A_BYTES, &tmO, &panel_full[kb], kb * 64, m0);
+                    }
+                }
+                load_b(&tmWp, 96 * 128, (i >> 1) * 64, (i & 1) * 192 + rank * 96);
+            }
             for (int it = 0; it < nch + FC2_LAG; ++it) {
                 if (it < nch)
                     for (int kb = 0; kb < KB; ++kb) load_b(&tmW1, 64 * 128, kb * 64, (ch0 + it) * 128 + rank * 64);
@@ -351,6 +372,7 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
 
         // ---- h1 = h + gate1 * (acc2 + bp) -> h (global) and TMEM; LayerNorm statistics
         const bool st = e_warp == 0 && lane == 0;        // the stamping thread (instrumented builds)
+        pdl_wait();
         if (st) DIT_STAMP(0);
         if (lane == 0) {                                 // the first two residual boxes travel while the projection runs
 #pragma unroll
@@ -411,6 +433,8 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
 
         // ---- fc1 chunks: u = gelu(acc1 + b1) -> bf16 hidden buffer (fc2's A operand)
         const uint32_t hid_a = ptx::smem_u32(hid);
+        // boxes of the final pass: the panel first (free as soon as the last fc1 chunk has been accumulated)
+        const uint32_t box2[6] = {pbox, pbox + A_BYTES, pbox + 2 * A_BYTES, hbox, hbox + 4096, ptx::smem_u32(ring) + e_warp * 4096};
         for (int c = 0; c < nch; ++c) {
             const int b = c & 1;
             if (lane < 2)                                // this chunk's 64 bias values (2 lines) into L1 before they are needed
@@ -418,6 +442,14 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
             ptx::mbar_wait(acc1_full, c & 1);
             ptx::tc_fence_after();
             if (st) DIT_STAMP(8 + 2 * c);
+            if (G == 1 && c == nch - 1 && lane == 0) {   // no MMA reads the panel any more: h1 boxes 0..2 of the final pass
+                ptx::bulk_wait<0>();                     // (this warp's h1 stores have landed before they are re-read)
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    ptx::mbar_arrive_expect_tx(&rbar[ci], 4096);
+                    ptx::tma_load_2d_u32(box2[ci], &tmH, ptx::smem_u32(&rbar[ci]), col_base + ci * 32, m0w);
+                }
+            }
             uint32_t r0[32], r1[32];
             ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64, r0);
             ptx::tmem_ld_32x32(t_lane + ACC1_COL + grp * 64 + 32, r1);
@@ -454,11 +486,10 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         ptx::tc_fence_after();
         if (st) DIT_STAMP(40);
         if constexpr (G == 1) {
-            const uint32_t box2[6] = {hbox, hbox + 4096, pbox, pbox + A_BYTES, pbox + 2 * A_BYTES, ptx::smem_u32(ring) + e_warp * 4096};
             gated_residual_pass<false, true>(&tmH, &tmH, box2, rbar, 1, t_lane + col_base, m0w, col_base, p.b2, p.gate2 + mod_off, lane, c0, s, qq);
             combine_stats(stat_sm, grp, row, q, c0, s, qq, p.eps, mean, rstd);
             if (p.stats_out && grp == 0 && m0 + row < p.M) p.stats_out[m0 + row] = make_float2(mean, rstd);
-            if (lane == 0) ptx::bulk_wait<0>();
+            if (lane == 0) ptx::bulk_wait_read<0>();     // the stores have read their boxes (grid completion publishes them)
             if (st) DIT_STAMP(41);
         }
     }
@@ -598,6 +629,7 @@ static_assert(SMEM_A_BYTES <= 232448, "shared memory budget");
 
 struct AttnFParams {
     int M, rows_per_mod, heads, heads_per_item, groups;
+    const uint8_t* w;           // packed qkv weights (bytes), for the L2 prefetch at kernel entry
     long long ldh, mod_ld, ldo;
     const float* h;
     const float2* stats;        // (mean, rstd) per row from the producer of h, or nullptr: computed here
@@ -724,11 +756,13 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
         ptx::tmem_alloc_2sm(tmem_ptr, 512);
         ptx::tmem_relinquish_2sm();
     }
+    if (warp == 2 && lane == 0) prefetch_weights_l2(p.w, (uint32_t)p.heads * 192 * DM * 2);
     ptx::tc_fence_before();
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();
+    // the producer streams weights only (no dependence on the preceding kernel): griddepcontrol.wait is executed by the
+    // epilogue warps, the only ones that touch activations
 
     if (warp == 0) {
         if (lane == 0) {                                 // TMA producer: this CTA's 96 rows of every (head, k-block) weight tile
@@ -776,6 +810,7 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
         const int e_warp = warp - 2;
         const int grp = e_warp >> 2;
         const int q = warp & 3;
+        pdl_wait();
         // ---- LayerNorm + modulate of this CTA's 128 rows -> bf16 panel.  Warp e_warp owns rows e_warp*16 .. +15 (one image
         // when rows_per_mod == 16); lane <-> columns (i * 32 + lane) * 4, eight rows per pass with all loads in flight.
         {
@@ -1002,7 +1037,8 @@ extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void*
     if (const char* e = getenv("XDB200_DIT_PROF")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
 #endif
     MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
-                reinterpret_cast<float2*>(stats_out), eps, h_out, ldh, prof};
+                reinterpret_cast<float2*>(stats_out), eps, h_out, ldh, prof,
+                static_cast<const uint8_t*>(Wp), static_cast<const uint8_t*>(W1), static_cast<const uint8_t*>(W2)};
     cudaStream_t st = (cudaStream_t)stream;
     int G = split;
     if (G == 0) {
@@ -1062,7 +1098,7 @@ extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const f
     int groups = 1;
     for (int g : {2, 3, 6})
         if (heads % g == 0 && tiles * g <= pairs) groups = g;
-    AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
+    AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, static_cast<const uint8_t*>(Wh), ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
                   shift, scale, bias, (bf16*)out, eps, sm_scale};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * tiles * groups);

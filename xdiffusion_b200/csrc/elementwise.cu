@@ -201,6 +201,18 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long
         *reinterpret_cast<const bf16x8*>(x + b * x_bs + t * ldx + j * 8);
 }
 
+// x[b, c, f, :] = mask[b, f] ? x[b, c, f, :] : x0[b, c, f, :]   (video-mask blend, diffusion/ddpm.py:963-982), float4
+__global__ void blend_frames_kernel(float4* __restrict__ x, const float4* __restrict__ x0, const uint8_t* __restrict__ mask,
+                                    int C, int F, int hw4, long long n4) {
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long plane = i / hw4;                       // (b, c, f)
+    const int f = (int)(plane % F);
+    const long long b = plane / ((long long)F * C);
+    if (!mask[b * F + f]) x[i] = x0[i];
+}
+
 // eps = u + w (c - u)   (samplers/ancestral.py:229-231), float4 vectorised
 __global__ void cfg_kernel(const float4* __restrict__ c, const float4* __restrict__ u, float w, float4* out,
                            long long n4) {
@@ -320,6 +332,15 @@ extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, l
                  rows_per_batch > 0 && rows > 0);
     xd_launch(copy_rows_kernel, blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, x_bs, rows,
               rows_per_batch, C, (bf16*)out, ldo, o_bs);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_blend_frames(float* x, const float* x0, const void* mask, int B, int C, int F, int HW, void* stream) {
+    XD_CHECK_ARG(x && x0 && mask && B > 0 && C > 0 && F > 0 && HW > 0 && HW % 4 == 0);
+    const long long n4 = (long long)B * C * F * (HW / 4);
+    xd_launch(blend_frames_kernel, blocks_for(n4), 256, 0, (cudaStream_t)stream, (float4*)x, (const float4*)x0,
+              (const uint8_t*)mask, C, F, HW / 4, n4);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

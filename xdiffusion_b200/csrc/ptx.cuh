@@ -86,6 +86,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
                  ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar_smem)
                  : "memory");
 }
+// pull `bytes` (multiple of 16) of global memory into L2 without a destination (weights ahead of their first TMA load)
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N> __device__ __forceinline__ void bulk_wait_read() {

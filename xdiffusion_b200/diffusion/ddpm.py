@@ -211,7 +211,12 @@ class GaussianDiffusion_DDPM(DiffusionModel):
                        use_cuda_graph: bool = True, seed: Optional[int] = None, row_offset: int = 0):
         device = next(self.parameters()).device
         if "video_mask" in context:
-            raise NotImplementedError("video_mask blending (autoregressive extension) is a 'next' row")
+            # conditional / autoregressive video sampling (reference ddpm.py:963-982): frames with mask 0 are held at
+            # context["x0"]; the blend runs on the device before and after every step (xd_blend_frames)
+            assert "x0" in context, "video_mask needs the conditioning frames in context['x0']"
+            if len(shape) != 5 or tuple(context["x0"].shape) != tuple(shape) or \
+                    tuple(context["video_mask"].shape) != (shape[0], shape[2]):
+                raise ValueError("video_mask must be [B, F] and x0 [B, C, F, H, W] of the sampled shape")
         s = self._config.diffusion.sampling
         initial_timestep = s.initial_timestep if "initial_timestep" in s else 0
         if initial_timestep != 0:
@@ -290,7 +295,10 @@ class _DeviceLoop:
 
     @staticmethod
     def _static(ctx, dev):
-        return {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in ctx.items()}
+        out = {k: (v.to(dev).contiguous().clone() if torch.is_tensor(v) else v) for k, v in ctx.items()}
+        if "x0" in out and torch.is_tensor(out["x0"]):
+            out["x0"] = out["x0"].float()
+        return out
 
     def load_context(self, context, uncond_context):
         """Refresh the static conditioning buffers of an already captured loop."""
@@ -337,8 +345,13 @@ class _DeviceLoop:
         if self.noise is not None:
             c["noise"] = self.noise
         u = self._ctx(self.uncond) if self.uncond is not None else None
+        mask = self.context.get("video_mask")
+        if mask is not None:
+            torch.ops.xdb200.blend_frames(self.x, self.context["x0"], mask)
         self.sampler.p_sample(self.x, context=c, unconditional_context=u, diffusion_model=self.model,
                               classifier_free_guidance=self.cfg)
+        if mask is not None:
+            torch.ops.xdb200.blend_frames(self.x, self.context["x0"], mask)
         self._advance(-1)
 
     def run(self, x0, noise, seed, use_graph):

@@ -63,8 +63,15 @@ def _ensure_workspace(t):
         _workspace["device"], _workspace["buf"] = dev, buf
 
 
+#: batch-size-dependent work splits / kernel choices allowed (split-K, hidden-split MLP clusters, the small-batch DiT path)
+BATCH_DEPENDENT_PATHS = os.environ.get("XDB200_SPLITK", "1") != "0"
+
+
 def set_split_k(enabled: bool):
-    """Split-K for long contractions over few tiles (default on).  Off = bit-exact batch independence."""
+    """Split-K for long contractions over few tiles, and every other choice that depends on the row count (default on).
+    Off = bit-exact batch independence: a sub-batch reproduces the rows of the full batch."""
+    global BATCH_DEPENDENT_PATHS
+    BATCH_DEPENDENT_PATHS = bool(enabled)
     _lib.check(_lib.lib().xd_set_split_k(int(bool(enabled))), "xd_set_split_k")
 
 
@@ -365,6 +372,17 @@ def _copy_rows(x, out):
     assert x.stride(2) == 1 and out.stride(2) == 1
     _lib.check(_lib.lib().xd_copy_rows_bf16(_p(x), x.stride(1), x.stride(0), nb * rows, rows, C, _p(out), out.stride(1),
                                             out.stride(0), _stream()), "xd_copy_rows_bf16")
+    _count()
+
+
+@_op("blend_frames(Tensor(a!) x, Tensor x0, Tensor mask) -> ()")
+def _blend_frames(x, x0, mask):
+    """x[b, c, f] = mask[b, f] ? x[b, c, f] : x0[b, c, f] in place (x, x0 fp32 [B, C, F, H, W]; mask bool / uint8 [B, F])."""
+    _cuda(x, x0, mask)
+    B, C, F, H, W = x.shape
+    assert x.dtype == torch.float32 and x0.dtype == torch.float32 and x.is_contiguous() and x0.is_contiguous()
+    assert x0.shape == x.shape and mask.shape == (B, F) and mask.is_contiguous() and mask.element_size() == 1
+    _lib.check(_lib.lib().xd_blend_frames(_p(x), _p(x0), _p(mask), B, C, F, H * W, _stream()), "xd_blend_frames")
     _count()
 
 

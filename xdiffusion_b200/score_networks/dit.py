@@ -22,8 +22,13 @@ from ..utils import instantiate_from_config, instantiate_partial_from_config
 
 # Fused half-block kernels (csrc/dit_block.cu); XDB200_DIT_FUSED=0 runs one kernel per operator (round-1 path).
 FUSED_BLOCK = os.environ.get("XDB200_DIT_FUSED", "1") == "1"
-# CTA pairs per 256-row tile of the fused MLP kernel: 0 = chosen by the library from the row count, 1 = never split
-MLP_SPLIT = int(os.environ.get("XDB200_DIT_MLP_SPLIT", "0"))
+# CTA pairs per 256-row tile of the fused MLP kernel: 1 = never split (default: measured, the distributed-shared-memory
+# reduction costs what the shorter MLP loop saves, profiles/README.md), 0 = chosen by the library, 2..4 = forced
+MLP_SPLIT = int(os.environ.get("XDB200_DIT_MLP_SPLIT", "1"))
+# The fused kernels walk one 256-row tile per CTA pair through a whole half-block: ~43 us however few tiles there are.
+# Below this many token rows (768 images; e.g. the 128-image shards of a batch sharded 8 ways) one kernel per operator,
+# each spread over all SMs along N, is faster (B = 128: 0.56 vs 0.71 ms per timestep; B = 1024: 1.42 vs 1.12).
+FUSED_MIN_ROWS = int(os.environ.get("XDB200_DIT_FUSED_MIN_ROWS", "12288"))
 
 
 class DiTBlock(torch.nn.Module):
@@ -132,6 +137,8 @@ class DiT(torch.nn.Module, Packed):
         h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
         main.wait_stream(side)
         fused = FUSED_BLOCK and D == 384 and ops.MATMUL_BACKEND == "tc"
+        if ops.BATCH_DEPENDENT_PATHS and B * T < FUSED_MIN_ROWS:
+            fused = False                                 # (never when bit-exact batch independence is requested)
         fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
         # (mean, rstd) of every row of h: emitted by the fused MLP kernel of block n, consumed by the LayerNorm of block n + 1
         stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32) if fused else None
