@@ -246,7 +246,8 @@ def dit_block_roofline(batch, device):
     stats = torch.zeros(M, 2, device=device)
     X = torch.ops.xdb200
     from xdiffusion_b200.score_networks.dit import MLP_SPLIT
-    t_mlp = _time_in_graph(lambda: X.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h2, g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT))
+    h_dst = h if MLP_SPLIT == 1 else h2                    # as the sampling loop calls it: in place unless split
+    t_mlp = _time_in_graph(lambda: X.dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h, h_dst, g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT))
     t_att = _time_in_graph(lambda: X.dit_attn(h, stats, s1, sc1, T, 1e-6, wh, bh, H, 0.125, o))
     f_mlp = 2.0 * M * (D * D + 2 * D * Hd)
     f_att = 2.0 * M * 3 * D * D + 4.0 * M * T * D

@@ -192,6 +192,22 @@ int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, 
 
 /* ---- fused sampler step --------------------------------------------------------------------- */
 
+/* EDM (Karras et al. 2022) stochastic sampler, fp64 state (samplers/edm.py:85-137), with the EDMPrecond arithmetic
+ * (score_networks/edm.py:663-693) folded in.  F = raw network output (fp32) at the state the stage names:
+ *   D = c_skip * float(x) + c_out * F
+ *   stage 0 (Euler):  d_out = (x_hat - D) / t_div;            x_out = x_hat + h * d_out           (t_div = t_hat)
+ *   stage 1 (Heun):   d' = (x_mid - D') / t_div;              x_out = x_hat + h * (0.5 d_in + 0.5 d')   (t_div = t_next)
+ *   stage 2:          den_out = D                              (EDMPrecond.forward alone)
+ * xin_out (optional) = c_in_next * float(x_out): the next network input.  Every operation is the reference's un-fused IEEE
+ * operation in the reference's order: bit-identical to it given the same F. */
+int xd_edm_step(int stage, const double* x_hat, const double* x_mid, const double* d_in, const float* F, double* d_out,
+                double* x_out, float* den_out, float* xin_out, double t_div, double h, float c_skip, float c_out,
+                float c_in_next, long long n, void* stream);
+/* x_hat = x + c_noise * z (fp64; z NULL: x_hat = x, nothing written) and xin = c_in * float(x_hat) (fp32, optional):
+ * the temporary noise increase of samplers/edm.py:108-120 and the network-input scaling of EDMPrecond.forward. */
+int xd_edm_prepare(const double* x, const double* z, double c_noise, double* x_hat, float c_in, float* xin, long long n,
+                   void* stream);
+
 /* mode 0 ancestral (samplers/ancestral.py:21-72,189-267), 1 DDIM (samplers/ddim.py:43-123), 2 Euler
  * (samplers/rectified_flow.py:46-84).  coefs fp32 [N][8], row = loop index, read from *idx_dev when
  * non-NULL else idx_host.  z NULL -> in-kernel Philox normals keyed by *seed_dev when non-NULL (graph replay), else seed.  threshold=1 -> dynamic thresholding

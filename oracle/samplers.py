@@ -106,3 +106,47 @@ def euler_flow(x, o, N=1000):
 def unnormalize(x):
     """utils.py:62-64"""
     return (torch.clamp(x, -1.0, 1.0) + 1) * 0.5
+
+
+# ----------------------------------------------------------------------------- EDM (samplers/edm.py:10-137)
+def edm_time_steps(num_steps, sigma_min, sigma_max, rho):
+    """samplers/edm.py:49-62 (round_sigma of EDMPrecond is the identity, score_networks/edm.py:695-696)."""
+    idx = torch.arange(num_steps, dtype=torch.float64)
+    t = (sigma_max ** (1 / rho) + idx / (num_steps - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+    return torch.cat([torch.as_tensor(t), torch.zeros_like(t[:1])])
+
+
+def edm_precond(raw_model, x, sigma, sigma_data=0.5):
+    """EDMPrecond.forward (score_networks/edm.py:663-693), fp32."""
+    x = x.to(torch.float32)
+    sigma = sigma.to(torch.float32).reshape(-1, 1, 1, 1)
+    c_skip = sigma_data ** 2 / (sigma ** 2 + sigma_data ** 2)
+    c_out = sigma * sigma_data / (sigma ** 2 + sigma_data ** 2).sqrt()
+    c_in = 1 / (sigma_data ** 2 + sigma ** 2).sqrt()
+    c_noise = sigma.log() / 4
+    f = raw_model((c_in * x).to(torch.float32), c_noise.flatten())
+    return c_skip * x + c_out * f.to(torch.float32)
+
+
+def edm_sample(raw_model, latents, num_steps=18, sigma_min=0.002, sigma_max=80.0, rho=7, S_churn=0, S_min=0,
+               S_max=float("inf"), S_noise=1, sigma_data=0.5, noise=None, trace=None):
+    """StochasticSampler.p_sample_loop + p_sample (samplers/edm.py:36-137); ``noise[i]`` replaces randn_like at step i."""
+    import numpy as np
+    t_steps = edm_time_steps(num_steps, sigma_min, sigma_max, rho)
+    x_next = latents.to(torch.float64) * t_steps[0]
+    for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
+        x_cur = x_next
+        gamma = min(S_churn / num_steps, np.sqrt(2) - 1) if S_min <= t_cur <= S_max else 0
+        t_hat = torch.as_tensor(t_cur + gamma * t_cur)
+        z = noise[i] if noise is not None else torch.randn_like(x_cur)
+        x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * S_noise * z
+        denoised = edm_precond(raw_model, x_hat, t_hat, sigma_data).to(torch.float64)
+        d_cur = (x_hat - denoised) / t_hat
+        x_next = x_hat + (t_next - t_hat) * d_cur
+        if i < num_steps - 1:
+            denoised = edm_precond(raw_model, x_next, t_next, sigma_data).to(torch.float64)
+            d_prime = (x_next - denoised) / t_next
+            x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+        if trace is not None:
+            trace.append(x_next)
+    return x_next

@@ -1,0 +1,41 @@
+"""SURVEY 8(f2), host side: the oracle's restatement of the EDM stochastic sampler + EDMPrecond reproduces, bit for bit, the
+fp64 states the REAL reference produced (tests/golden/make_edm.py; stub raw network with exactly reproducible arithmetic),
+and the product's host-side pieces (time-step discretisation, preconditioning scalars) equal the oracle's."""
+import os
+
+import torch
+
+from oracle import samplers as osamplers
+from tests.conftest import GOLDEN
+from tests.golden.edm_stub import AffineStub
+
+
+def _fx():
+    return torch.load(os.path.join(GOLDEN, "edm.pt"), weights_only=False)
+
+
+def test_oracle_edm_sampler_bit_exact_vs_reference():
+    fx = _fx()
+    stub = AffineStub()
+    for name, run in fx["runs"].items():
+        trace = []
+        with torch.no_grad():
+            osamplers.edm_sample(lambda x, c: stub(x, c), fx["latents"], num_steps=run["num_steps"], S_churn=run["S_churn"],
+                                 noise=run["noise"], trace=trace)
+        assert len(trace) == len(run["states"])
+        for i, (a, b) in enumerate(zip(trace, run["states"])):
+            assert a.dtype == torch.float64 and torch.equal(a, b), (name, i, float((a - b).abs().max()))
+
+
+def test_product_time_steps_and_scalars_match_oracle():
+    from xdiffusion_b200.samplers.edm import StochasticSampler
+    from xdiffusion_b200.score_networks.edm import EDMPrecond
+    net = EDMPrecond(img_resolution=32, img_channels=1, model={"target": "tests.golden.edm_stub.AffineStub", "params": {}})
+    for n in (6, 18, 35):
+        t = StochasticSampler(num_steps=n).time_steps(net)
+        assert torch.equal(t, osamplers.edm_time_steps(n, 0.002, 80, 7)) and float(t[-1]) == 0.0 and t.dtype == torch.float64
+    t = StochasticSampler(num_steps=6).time_steps(net)
+    for sigma in t[:-1]:
+        s = sigma.to(torch.float32).reshape(-1, 1, 1, 1)
+        want = (0.25 / (s ** 2 + 0.25), s * 0.5 / (s ** 2 + 0.25).sqrt(), 1 / (0.25 + s ** 2).sqrt(), s.log() / 4)
+        assert net.precond_scalars(sigma) == tuple(float(w) for w in want)

@@ -283,6 +283,22 @@ def test_cross_attention_short_context(ops, Tk):
     assert rel_l2(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("Tq,Tk,B,H", [(64, 64, 7, 4), (4, 81, 3, 4), (16, 93, 5, 4), (48, 48, 2, 2), (4, 4, 9, 4)])
+def test_attention_query_blocks_on_tensor_cores(ops, Tq, Tk, B, H):
+    """The warp-level mma.sync kernel with 16-row query blocks: the 8x8 level of the video UNet (64 x 64), the
+    text-conditioned UNet (4 or 16 pixels against 77 text + own keys) and ragged sizes, per-head interleaved
+    layout, against fp32 softmax attention on the same bf16 operands."""
+    g = torch.Generator().manual_seed(1000 + Tq + Tk)
+    q = bf(torch.randn(B, Tq, H, 64, generator=g))
+    kv = bf(torch.randn(B, Tk, H, 2, 64, generator=g))
+    ref = ((q.float().permute(0, 2, 1, 3) @ kv[:, :, :, 0].float().permute(0, 2, 3, 1)) / 8.0).softmax(-1) \
+        @ kv[:, :, :, 1].float().permute(0, 2, 1, 3)                                      # B, H, Tq, 64
+    kd = kv.to(DEV)
+    out = ops.attention(q.to(DEV).permute(0, 2, 1, 3), kd[:, :, :, 0].permute(0, 2, 1, 3), kd[:, :, :, 1].permute(0, 2, 1, 3),
+                        1 / 8.0)
+    assert rel_l2(out, ref) < 4e-3, rel_l2(out, ref)
+
+
 def test_attention_relative_position_scrambled(ops):
     """TemporalSelfAttention core incl. the reference's raw reshape (oracle.nets.relpos_attention)."""
     g = torch.Generator().manual_seed(21)

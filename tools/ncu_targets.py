@@ -37,6 +37,19 @@ for (n, k, nm, rmw, act) in [(1152, 384, "qkv", False, 0), (384, 384, "proj", Tr
         out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
         targets.append((f"gemm {nm}", lambda a=a, w=w, bias=bias, act=act, out=out: ops.linear(a, w, bias, act=act, out=out)))
 
+# ---- fused DiT half-blocks (csrc/dit_block.cu): the kernels the DiT sampling loop runs at batch >= 768 ----------------
+T_, D_, Hd_ = 16, 384, 1536
+o_, h_, h2_ = bf(M, D_), torch.randn(M, D_, device=dev), torch.empty(M, D_, device=dev)
+wh_, wp_, w1_, w2_ = bf(3 * D_, D_) * D_ ** -0.5, bf(D_, D_) * D_ ** -0.5, bf(Hd_, D_) * D_ ** -0.5, bf(D_, Hd_) * Hd_ ** -0.5
+bh_, bp_, b1_, b2_ = (torch.randn(n, device=dev) * 0.1 for n in (3 * D_, D_, Hd_, D_))
+mod_ = torch.randn(1024, 6 * D_, device=dev) * 0.1
+s1_, sc1_, g1_, s2_, sc2_, g2_ = (mod_[:, i * D_:(i + 1) * D_] for i in range(6))
+stats_ = torch.zeros(M, 2, device=dev)
+targets.append(("dit mlp fused (proj+LN+fc1+GELU+fc2)", lambda: torch.ops.xdb200.dit_proj_mlp(
+    o_, wp_, bp_, w1_, b1_, w2_, b2_, h_, h2_, g1_, s2_, sc2_, g2_, T_, 1e-6, stats_, 1)))
+targets.append(("dit attn fused (LN+qkv+attention)", lambda: torch.ops.xdb200.dit_attn(
+    h_, stats_, s1_, sc1_, T_, 1e-6, wh_, bh_, 6, 0.125, o_)))
+
 # ---- conv3x3, one per UNet resolution (batch 64) -----------------------------------------------------------------
 for (hw, c, cs, co) in [(32, 128, 0, 128), (32, 384, 384, 128), (16, 256, 0, 256), (8, 256, 0, 256), (4, 256, 0, 256)]:
     x, wp, bias = bf(64, hw, hw, c), bf(co, 9 * c + cs) * (9 * c) ** -0.5, torch.randn(co, device=dev)
@@ -64,6 +77,9 @@ targets.append(("attention T=16 (DiT)", lambda: ops.attention(q16, k16, v16, 0.1
 qkv2 = bf(64, 256, 4, 3, 64)
 q256, k256, v256 = (qkv2[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
 targets.append(("attention T=256 (UNet 16x16)", lambda: ops.attention(q256, k256, v256, 0.125)))
+qkv3 = bf(8 * 16, 64, 4, 3, 64)                                     # video UNet 8x8 level: 8 clips x 16 frames, T = 64
+q64, k64, v64 = (qkv3[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+targets.append(("attention T=64 (video 8x8, query blocks)", lambda: ops.attention(q64, k64, v64, 0.125)))
 qx = bf(512, 16, 6, 64).permute(0, 2, 1, 3)
 kv = bf(512, 77, 2, 6, 64)
 targets.append(("attention 16x77 (PixArt cross)", lambda: ops.attention(qx, kv[:, :, 0].permute(0, 2, 1, 3),

@@ -42,6 +42,19 @@ names = {63: "entry", 61: "setup done (tmem, barriers, cluster sync)", 62: "pdl_
 for c in range(8, 8 + 2 * (Hd // 128), 2):
     names[c] = f"epi: fc1 chunk {(c - 8) // 2} accumulator ready"
     names[c + 1] = f"epi: fc1 chunk {(c - 8) // 2} GELU -> hidden buffer done"
+if len(sys.argv) > 3 and sys.argv[3] == "attn":
+    prof.zero_()
+    wq, bq = bf(3 * D, D) * D ** -0.5, torch.randn(3 * D, device=dev) * 0.1
+    for _ in range(3):
+        torch.ops.xdb200.dit_attn(h, stats, s1, sc1, T, 1e-6, wq, bq, 6, 0.125, o)
+    torch.cuda.synchronize()
+    p = prof.view(-1, 64).cpu()
+    names = {63: "entry", 61: "setup done", 0: "epilogue warp starts (pdl_wait returned)", 1: "epi: LayerNorm panel written",
+             48: "mma warp starts", 51: "mma: panel ready seen", 60: "exit"}
+    for i in range(6):
+        names[8 + 3 * i] = f"epi: head {i} accumulator ready"
+        names[9 + 3 * i] = f"epi: head {i} q|k|v staged (both halves)"
+        names[10 + 3 * i] = f"epi: head {i} attention done"
 for cta in sorted({0, 1, (tiles * 2 * G) // 2, tiles * 2 * G - 2}):
     row = p[cta]
     t0 = int(row[63])

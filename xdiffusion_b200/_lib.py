@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "xdb200.h")
 _CTYPES = {
     "int": ctypes.c_int,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "long long": ctypes.c_longlong,
     "unsigned long long": ctypes.c_ulonglong,
 }

@@ -561,7 +561,6 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
     XD_CHECK_ARG(q && k && v && o && head_dim == D && B > 0 && H > 0 && Tq > 0 && Tk > 0);
     const int in_f32 = qkv_dtype == XD_F32;
     XD_CHECK_ARG(!in_f32 || (Tq == 16 && Tk == 16));            // fp32 q/k/v: SIMT T = 16 kernel only
-    XD_CHECK_ARG((Tq >= ROWS && Tq % ROWS == 0) || (Tq < ROWS && ROWS % Tq == 0));
     XD_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && q_hs % 8 == 0 && k_hs % 8 == 0 && v_hs % 8 == 0 &&
                  q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0);
     XD_CHECK_ARG(scramble || (o_rs % 8 == 0 && o_hs % 8 == 0 && o_bs % 8 == 0));
@@ -607,6 +606,7 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
         XD_CHECK_LAUNCH();
         return XD_OK;
     }
+    XD_CHECK_ARG((Tq >= ROWS && Tq % ROWS == 0) || (Tq < ROWS && ROWS % Tq == 0 && ROWS / Tq <= 8));   // generic kernel
     const int pairs = Tq >= ROWS ? 1 : ROWS / Tq;
     const long long nbh = (long long)B * H;
     const long long blocks = Tq >= ROWS ? nbh * (Tq / ROWS) : (nbh + pairs - 1) / pairs;

@@ -630,6 +630,7 @@ static_assert(SMEM_A_BYTES <= 232448, "shared memory budget");
 struct AttnFParams {
     int M, rows_per_mod, heads, heads_per_item, groups;
     const uint8_t* w;           // packed qkv weights (bytes), for the L2 prefetch at kernel entry
+    long long* prof;            // instrumented builds: clock64() stamps (see MlpParams)
     long long ldh, mod_ld, ldo;
     const float* h;
     const float2* stats;        // (mean, rstd) per row from the producer of h, or nullptr: computed here
@@ -718,6 +719,7 @@ __device__ __forceinline__ void attend16(uint32_t aQ, uint32_t aK, uint32_t aV, 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
     pdl_launch_dependents();
+    if (threadIdx.x == 64) DIT_STAMP(63);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* panel = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage = panel + PANEL_BYTES;
@@ -761,6 +763,7 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 64) DIT_STAMP(61);
     // the producer streams weights only (no dependence on the preceding kernel): griddepcontrol.wait is executed by the
     // epilogue warps, the only ones that touch activations
 
@@ -783,8 +786,10 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
             const uint64_t d_ring = ptx::smem_desc_sw128(ptx::smem_u32(ring));
             int s = 0;
             uint32_t ph = 0;
+            if (lane == 0) DIT_STAMP(48);
             ptx::mbar_wait(a_full, 0);
             ptx::tc_fence_after();
+            if (lane == 0) DIT_STAMP(51);
             for (int i = 0; i < nh; ++i) {
                 const uint32_t buf = i & 1;
                 ptx::mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
@@ -811,6 +816,8 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
         const int grp = e_warp >> 2;
         const int q = warp & 3;
         pdl_wait();
+        const bool st = e_warp == 0 && lane == 0;
+        if (st) DIT_STAMP(0);
         // ---- LayerNorm + modulate of this CTA's 128 rows -> bf16 panel.  Warp e_warp owns rows e_warp*16 .. +15 (one image
         // when rows_per_mod == 16); lane <-> columns (i * 32 + lane) * 4, eight rows per pass with all loads in flight.
         {
@@ -907,6 +914,7 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_leader(a_full);
+            if (st) DIT_STAMP(1);
         }
         // ---- per head: drain [q | k | v] (+ bias) into the quadrant's bf16 tiles, then one image per warp
         const uint32_t st_a = ptx::smem_u32(stage) + q * (3 * 4096);
@@ -919,6 +927,7 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
             if (lane < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(bptr + lane * 32));
             ptx::mbar_wait(&acc_full[buf], (i >> 1) & 1);
             ptx::tc_fence_after();
+            if (st) DIT_STAMP(8 + 3 * i);
             uint32_t r[3][32];
 #pragma unroll
             for (int j = 0; j < 3; ++j) ptx::tmem_ld_32x32(t_lane + buf * 192 + grp * 96 + j * 32, r[j]);
@@ -940,14 +949,17 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
                 ptx::sts128(st_a + (col >> 6) * 4096 + lane * 128 + ((((col & 63) >> 3) ^ (lane & 7)) << 4), pk);
             }
             ptx::named_bar_sync(1 + q, 64);              // both column halves of the quadrant's 32 rows are staged
+            if (st) DIT_STAMP(9 + 3 * i);
             const uint32_t io = grp * 2048;              // image `grp` of the quadrant: rows 16 * grp ..
             attend16(st_a + io, st_a + 4096 + io, st_a + 8192 + io, p.sm_scale,
                      p.out + (long long)img_row0 * p.ldo + hd * 64, p.ldo, p.M - img_row0, lane);
             ptx::named_bar_sync(1 + q, 64);              // the partner warp is done with the tiles before they are rewritten
+            if (st) DIT_STAMP(10 + 3 * i);
         }
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
+    if (threadIdx.x == 64) DIT_STAMP(60);
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_2sm(tmem_base, 512);
@@ -1098,7 +1110,11 @@ extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const f
     int groups = 1;
     for (int g : {2, 3, 6})
         if (heads % g == 0 && tiles * g <= pairs) groups = g;
-    AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, static_cast<const uint8_t*>(Wh), ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
+    long long* prof = nullptr;
+#ifdef XDB200_INSTRUMENT
+    if (const char* e = getenv("XDB200_DIT_PROF")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
+    AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, static_cast<const uint8_t*>(Wh), prof, ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
                   shift, scale, bias, (bf16*)out, eps, sm_scale};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * tiles * groups);

@@ -231,7 +231,86 @@ __global__ void unnormalize_kernel(const float* x, float* out, long long n) {
     if (i < n) out[i] = __fmul_rn(__fadd_rn(fminf(fmaxf(x[i], -1.0f), 1.0f), 1.0f), 0.5f);
 }
 
+// ------------------------------------------------------------------ EDM (Karras et al.) Euler / Heun step, fp64 state
+// samplers/edm.py:85-137 with the preconditioning of score_networks/edm.py:663-693 folded in.  Every operation is the
+// un-fused IEEE operation the reference's tensor expression performs, in its order, so a step is bit-identical to it:
+//   D     = c_skip * float(x) + c_out * F                       (fp32: EDMPrecond.forward, D_x)
+//   stage 0 (Euler):  d = (x_hat - double(D)) / t_hat;          x_next = x_hat + h * d
+//   stage 1 (Heun):   d' = (x_next - double(D')) / t_next;      x_next = x_hat + h * (0.5 * d + 0.5 * d')
+//   stage 2:          D only (EDMPrecond.forward as a stand-alone call)
+// and, fused behind it, the next network input  xin = c_in_next * float(x_next)  (fp32), so the fp64 state never makes an
+// extra trip through HBM between two network evaluations.
+struct EdmParams {
+    int stage;
+    const double *x_hat, *x_mid, *d_in;
+    const float* F;
+    double *d_out, *x_out;
+    float *den_out, *xin_out;
+    double t_div, h;
+    float c_skip, c_out, c_in_next;
+    long long n;
+};
+
+__global__ void edm_step_kernel(const EdmParams p) {
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+        const double xs = p.stage == 1 ? p.x_mid[i] : p.x_hat[i];       // the state the network was evaluated at
+        const float den = __fadd_rn(__fmul_rn(p.c_skip, (float)xs), __fmul_rn(p.c_out, p.F[i]));
+        if (p.stage == 2) { p.den_out[i] = den; continue; }
+        const double d = __ddiv_rn(__dsub_rn(xs, (double)den), p.t_div);
+        double xn;
+        if (p.stage == 0) {
+            xn = __dadd_rn(p.x_hat[i], __dmul_rn(p.h, d));
+            p.d_out[i] = d;
+        } else {
+            const double mix = __dadd_rn(__dmul_rn(0.5, p.d_in[i]), __dmul_rn(0.5, d));
+            xn = __dadd_rn(p.x_hat[i], __dmul_rn(p.h, mix));
+        }
+        p.x_out[i] = xn;
+        if (p.xin_out) p.xin_out[i] = __fmul_rn(p.c_in_next, (float)xn);
+    }
+}
+
+// xin = c_in * float(x)                                            (EDMPrecond.forward: (c_in * x).to(dtype))
+// x_hat = x + c_noise * z, fp64                                     (samplers/edm.py:117-120, S_churn > 0)
+__global__ void edm_in_kernel(const double* x, const double* z, double c_noise, double* x_hat, float c_in, float* xin,
+                              long long n) {
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (z) {
+            v = __dadd_rn(v, __dmul_rn(c_noise, z[i]));
+            x_hat[i] = v;
+        }
+        if (xin) xin[i] = __fmul_rn(c_in, (float)v);
+    }
+}
+
 }  // namespace
+
+extern "C" int xd_edm_step(int stage, const double* x_hat, const double* x_mid, const double* d_in, const float* F,
+                           double* d_out, double* x_out, float* den_out, float* xin_out, double t_div, double h,
+                           float c_skip, float c_out, float c_in_next, long long n, void* stream) {
+    XD_CHECK_ARG(stage >= 0 && stage <= 2 && x_hat && F && n > 0);
+    XD_CHECK_ARG(stage != 0 || (d_out && x_out));
+    XD_CHECK_ARG(stage != 1 || (x_mid && d_in && x_out));
+    XD_CHECK_ARG(stage != 2 || den_out);
+    XD_CHECK_ARG(stage == 2 || t_div != 0.0);
+    EdmParams p{stage, x_hat, x_mid, d_in, F, d_out, x_out, den_out, xin_out, t_div, h, c_skip, c_out, c_in_next, n};
+    const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 8);
+    xd_launch(edm_step_kernel, grid, 256, 0, (cudaStream_t)stream, p);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_edm_prepare(const double* x, const double* z, double c_noise, double* x_hat, float c_in, float* xin,
+                              long long n, void* stream) {
+    XD_CHECK_ARG(x && n > 0 && (xin || z) && (!z || x_hat));
+    const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 8);
+    xd_launch(edm_in_kernel, grid, 256, 0, (cudaStream_t)stream, x, z, c_noise, x_hat, c_in, xin, n);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
 
 extern "C" int xd_sampler_step(int mode, int form, int pred_v, const float* x, const float* o, const float* z,
                                long long z_step_stride, float* out, const float* coefs, const int* idx_dev,

@@ -415,6 +415,32 @@ def _sampler_step(mode, form, pred_v, x, o, z, z_step_stride, out, coefs, idx_de
     _count()
 
 
+@_op("edm_step(int stage, Tensor x_hat, Tensor? x_mid, Tensor? d_in, Tensor f, Tensor(a!)? d_out, Tensor(b!)? x_out, "
+     "Tensor(c!)? den_out, Tensor(d!)? xin_out, float t_div, float h, float c_skip, float c_out, float c_in_next) -> ()")
+def _edm_step(stage, x_hat, x_mid, d_in, f, d_out, x_out, den_out, xin_out, t_div, h, c_skip, c_out, c_in_next):
+    """EDM Euler (stage 0) / Heun (stage 1) update on the fp64 state, or the preconditioned denoiser output alone (stage 2)."""
+    _cuda(x_hat, x_mid, d_in, f, d_out, x_out, den_out, xin_out)
+    for t in (x_hat, x_mid, d_in, d_out, x_out):
+        assert t is None or (t.dtype == torch.float64 and t.is_contiguous() and t.numel() == x_hat.numel())
+    for t in (f, den_out, xin_out):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x_hat.numel())
+    _lib.check(_lib.lib().xd_edm_step(stage, _p(x_hat), _p(x_mid), _p(d_in), _p(f), _p(d_out), _p(x_out), _p(den_out),
+                                      _p(xin_out), float(t_div), float(h), float(c_skip), float(c_out), float(c_in_next),
+                                      x_hat.numel(), _stream()), "xd_edm_step")
+    _count()
+
+
+@_op("edm_prepare(Tensor x, Tensor? z, float c_noise, Tensor(a!)? x_hat, float c_in, Tensor(b!)? xin) -> ()")
+def _edm_prepare(x, z, c_noise, x_hat, c_in, xin):
+    _cuda(x, z, x_hat, xin)
+    assert x.dtype == torch.float64 and x.is_contiguous()
+    assert z is None or (z.dtype == torch.float64 and z.is_contiguous() and x_hat is not None and x_hat.dtype == torch.float64)
+    assert xin is None or (xin.dtype == torch.float32 and xin.is_contiguous())
+    _lib.check(_lib.lib().xd_edm_prepare(_p(x), _p(z), float(c_noise), _p(x_hat), float(c_in), _p(xin), x.numel(),
+                                         _stream()), "xd_edm_prepare")
+    _count()
+
+
 @_op("schedule_advance(Tensor(a!) idx_dev, int set_to, Tensor? tab_i64, Tensor? tab_a, Tensor? tab_b, "
      "Tensor(b!)? out_i64, Tensor(c!)? out_a, Tensor(d!)? out_b, int B) -> ()")
 def _schedule_advance(idx_dev, set_to, tab_i64, tab_a, tab_b, out_i64, out_a, out_b, B):

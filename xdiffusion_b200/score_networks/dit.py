@@ -142,9 +142,10 @@ class DiT(torch.nn.Module, Packed):
         fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
         # (mean, rstd) of every row of h: emitted by the fused MLP kernel of block n, consumed by the LayerNorm of block n + 1
         stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32) if fused else None
-        # The fused MLP kernel reads h and writes h_next: with two buffers a small batch (few 256-row tiles, e.g. one shard of
-        # a strong-scaled batch) lets it split every tile over several CTA pairs (see csrc/dit_block.cu).
-        h_next = torch.empty_like(h) if fused else None
+        # The fused MLP kernel reads h and writes h_next.  In place by default: a second 25 MB fp32 stream (batch 1024) does
+        # not fit the 126 MB L2 next to h, the attention output and the weights, and costs 9 % of the step (838 vs 914
+        # img/s).  Only the hidden-split kernels (XDB200_DIT_MLP_SPLIT != 1) need distinct buffers.
+        h_next = h if MLP_SPLIT == 1 or not fused else torch.empty_like(h)
         for n, blk in enumerate(self.blocks):
             m = mod[:, n * 6 * D:(n + 1) * 6 * D]
             s1, sc1, g1, s2, sc2, g2 = (m[:, i * D:(i + 1) * D] for i in range(6))
