@@ -10,6 +10,12 @@
 //   warps 1..4  one thread per query row = TMEM lane: tcgen05.ld of the 256 logits (two passes: max,
 //               then exp2 / sum / bf16 pack into smem), later the 64 output columns, scaled by 1/sum
 // The whole 256-key row is resident in TMEM, so the softmax is exact (no online rescaling).
+//
+// Two CTAs per SM (round 2): a CTA is a serial chain (TMA round trip -> S -> two TMEM passes of softmax -> P V -> store) that
+// keeps the tensor pipe busy for ~10 % of its life; with 145 KB of shared memory and a 512-column TMEM allocation only one
+// fitted an SM.  P (64 KB, written after the last S MMA has read Q and K) now aliases the Q and K tiles, O (64 columns)
+// aliases the first S columns (the P V MMAs are issued after every softmax thread has read S), so a CTA needs 96 KB and
+// 256 TMEM columns and two of them overlap each other's latencies.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -20,7 +26,8 @@ namespace attn_tc {
 
 constexpr int T = 256, D = 64, BM = 128;
 constexpr int SQ = BM * 128, SK = T * 128, SV = T * 128, SP = 4 * BM * 128;     // bytes
-constexpr int SMEM = SQ + SK + SV + SP + 1024 + 128;
+static_assert(SQ + SK <= SP, "P aliases the Q and K tiles");
+constexpr int SMEM = SP + SV + 1024 + 128;
 constexpr int THREADS = 160;
 
 struct Params {
@@ -35,17 +42,17 @@ __device__ __forceinline__ uint32_t idesc(int M, int N, bool b_mn_major) {
     return ptx::idesc_bf16_f32(M, N) | (b_mn_major ? (1u << 16) : 0u);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 attention_tc256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sP = smem;                                  // [4 k-blocks of 64 keys][128 rows][128 B]; aliases Q and K
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + SQ;
-    uint8_t* sV = sK + SK;
-    uint8_t* sP = sV + SV;
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + SP);
+    uint8_t* sV = smem + SP;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sV + SV);
     uint64_t* bar_s = bar_load + 1;
     uint64_t* bar_p = bar_load + 2;
     uint64_t* bar_o = bar_load + 3;
@@ -68,14 +75,14 @@ attention_tc256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             ptx::fence_barrier_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_ptr, 512);
+        ptx::tmem_alloc(tmem_ptr, 256);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t tmem_s = tmem, tmem_o = tmem + 256;
+    const uint32_t tmem_s = tmem, tmem_o = tmem;         // O re-uses the first 64 S columns (see the header)
     pdl_wait();                                          // prologue above overlaps the previous kernel's tail
 
     if (warp == 0) {
@@ -171,7 +178,7 @@ attention_tc256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncthreads();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem, 512);
+        ptx::tmem_dealloc(tmem, 256);
     }
 }
 
