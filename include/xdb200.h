@@ -182,6 +182,14 @@ int xd_upsample2x_nhwc(const void* x, long long ldx, int nimg, int H, int W, int
  * `torch.cat([ek, k], dim=-1)` of QKVAttention (layers/attention.py:166-180). */
 int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, long long rows, long long rows_per_batch, int C,
                       void* out, long long ldo, long long o_bs, void* stream);
+/* Stride-2 3x3 convolution (pad 1) = this im2col + xd_gemm_bf16_tc: out bf16 [nimg * H/2 * W/2, 9 * C], column tap * C + c
+ * (tap = 3 dy + dx, the K order of the packed conv weights) = X[n, 2y + dy - 1, 2x + dx - 1, c], zero outside.  Replaces
+ * `Conv2d(C, C, 3, stride=2, padding=1)` of DBlock (layers/resnet.py:272-280, Imagen efficient UNet). */
+int xd_im2col3x3_s2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out, void* stream);
+/* out[n, p, :] = x[n, p, :] + b[n, :]: bf16 rows of C channels (row strides ldx / ldo), fp32 per-sample bias (row stride ldb).
+ * Replaces `h + Linear(SiLU(timestep_embedding))[..., None, None]` of DBlock / UBlock (layers/resnet.py:303-310,395-402). */
+int xd_add_channel_bias_nhwc(const void* x, long long ldx, const float* b, long long ldb, int nsamples, long long P, int C,
+                             void* out, long long ldo, void* stream);
 /* Video-mask blend of the autoregressive / conditional video loops: x[b, c, f] = mask[b, f] ? x[b, c, f] : x0[b, c, f],
  * in place on x (fp32 [B, C, F, HW]), mask = B x F bytes (non-zero = generate, zero = keep the conditioning frame).
  * Replaces `torch.where(video_mask[:, None, :, None, None], x_t, x0)` before and after every reverse-process step
@@ -192,6 +200,14 @@ int xd_cfg_combine(const float* cond, const float* uncond, float w, float* out, 
 
 /* ---- fused sampler step --------------------------------------------------------------------- */
 
+/* Input of a cascade's super-resolution stage (layers/super_resolution.py:47-121): out[b] = [x[b] (nx floats) | a * low[b] +
+ * c * z[b] (nl floats)], i.e. `torch.cat([x, q_sample(low_res_x_0, s)], dim=1)` with a = sqrt_alphas_cumprod[s], c =
+ * sqrt_one_minus_alphas_cumprod[s].  The reference re-draws the conditioning noise z at EVERY network evaluation: z = row
+ * *idx_dev (else idx_host) of an injected table (rows z_step_stride floats apart), or NULL -> in-kernel Philox normals keyed
+ * like xd_sampler_step's (distinct stream).  `low` = resized, normalised low-resolution images (timestep-invariant). */
+int xd_sr_input(const float* x, const float* low, const float* z, long long z_step_stride, float* out, int B, int nx, int nl,
+                float a, float c, const int* idx_dev, int idx_host, unsigned long long seed,
+                const unsigned long long* seed_dev, long long elem_offset, void* stream);
 /* EDM (Karras et al. 2022) stochastic sampler, fp64 state (samplers/edm.py:85-137), with the EDMPrecond arithmetic
  * (score_networks/edm.py:663-693) folded in.  F = raw network output (fp32) at the state the stage names:
  *   D = c_skip * float(x) + c_out * F

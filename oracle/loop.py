@@ -34,6 +34,9 @@ class OracleModel:
             self.steps = sp["steps"]
             self.N = d["sde"]["params"]["N"]
             self.T = d["sde"]["params"]["T"]
+        sr = cfg.get("super_resolution")                  # cascade stage: low-resolution conditioning (ddpm.py:613-618)
+        self.sr = None if sr is None else {"key": sr["conditioning_key"], "size": sr["super_resolution_size"],
+                                           "level": sr.get("sampling_augmentation_level")}
         dt = d.get("dynamic_thresholding")
         self.threshold = (dt["p"], dt["c"]) if dt and dt.get("enable") else None
 
@@ -42,6 +45,13 @@ class OracleModel:
         if self.kind == "unet":
             tin = ctx["logsnr_t"] if nets.time_input_key(self.p) == "logsnr_t" else t
             return nets.unet_forward(self.sd, self.p, x, tin, text=ctx.get("text_embeddings"))
+        if self.kind == "effunet":
+            # InputPreprocessor + GaussianConditioningAugmentationToTimestep (layers/super_resolution.py): the augmentation
+            # timestep is (ones(B, long) * steps * level).to(long); ctx["z_cond"] is the noise q_sample draws at this call
+            B = x.shape[0]
+            s = (torch.ones(B, dtype=torch.long) * self.steps * self.sr["level"]).to(torch.long)
+            xin = nets.sr_input(x, ctx[self.sr["key"]], self.sr["size"], self.tables, s, ctx["z_cond"])
+            return nets.effunet_forward(self.sd, self.p, xin, t, text=ctx.get("text_embeddings"), augmentation_timestep=s)
         if self.kind == "dit":
             return nets.dit_forward(self.sd, self.p, x, t, ctx["classes"])
         if self.kind == "pixart":
@@ -52,7 +62,7 @@ class OracleModel:
 
     @torch.no_grad()
     def sample(self, x_T, noises, ctx=None, num_sampling_steps=None, sampler="ancestral",
-               cfg_scale=None, uncond_ctx=None, trace=None):
+               cfg_scale=None, uncond_ctx=None, trace=None, cond_noises=None):
         """noises[i] is the z used at loop index i (ignored by ddim / euler).  Returns the
         un-normalised samples in [0,1] (ddpm.py:667).  ``trace`` (list) receives
         (i, score, x_next) per step."""
@@ -67,6 +77,8 @@ class OracleModel:
             if mask is not None:                          # ddpm.py:963-967
                 x = torch.where(mask, x, ctx["x0"])
             c = dict(ctx)
+            if cond_noises is not None:                   # super-resolution stage: conditioning noise of this step
+                c["z_cond"] = cond_noises[i]
             if self.sched_kind == "ContinuousNoiseScheduler":
                 idx_s, idx_t = schedules.continuous_indices(i, N, self.steps)
                 lam_s, lam_t = self.gammas[idx_s], self.gammas[idx_t]

@@ -10,6 +10,8 @@ Functional fp32 restatements driven by a state dict (keys relative to
                    layers/utils.py:90-121
   pixart_forward   score_networks/pixart.py:76-120,227-268, layers/attention.py:209-228,
                    layers/embedding.py:202-237
+  effunet_forward  score_networks/efficient_unet.py:219-256, layers/resnet.py:204-437,
+                   layers/super_resolution.py:47-157
   unet3d_forward   score_networks/unet_3d.py:316-353, layers/resnet_3d.py:103-254,
                    layers/attention.py:457-676, layers/embedding.py:108-143
 """
@@ -262,6 +264,75 @@ def unet_forward(sd, p, x, t, taps=None, text=None):
             taps[f"ups.{n}"] = h
     h = F.silu(_gn(sd, "final_projection.0", h))
     return F.conv2d(h, sd["final_projection.2.weight"], None, padding=1)
+
+
+# ----------------------------------------------------------------------------- efficient UNet (Imagen SR stage)
+def _resblock_efficient(sd, pre, x):
+    """ResnetBlockEfficient (layers/resnet.py:204-250): no time embedding inside, always a 1x1 skip, sum scaled by 0.7071."""
+    p = pre + "_resnet_path."
+    h = F.conv2d(F.silu(_gn(sd, p + "0", x)), sd[p + "2.weight"], sd[p + "2.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn(sd, p + "3", h)), sd[p + "6.weight"], sd[p + "6.bias"], padding=1)
+    r = F.conv2d(x, sd[pre + "_skip_connection.weight"], sd[pre + "_skip_connection.bias"]) + h
+    return r * 0.7071
+
+
+def effunet_forward(sd, p, x, t, text=None, augmentation_timestep=None):
+    """score_networks/efficient_unet.py:219-256 with DBlock / UBlock of layers/resnet.py:253-437: every DBlock starts with a
+    stride-2 conv, adds Linear(SiLU(temb)) per channel, runs its ResnetBlockEfficient chain and (where configured) a
+    SpatialCrossAttention; every UBlock does the same and ends with nearest x2 + conv.  The timestep embedding carries the
+    Gaussian-conditioning-augmentation level (layers/super_resolution.py:124-157)."""
+    emb = unet_time_embedding(sd, p, t)
+    head = p["conditioning"]["context_transformer_head"]
+    head = head if isinstance(head, list) else [head]
+    for n, hcfg in enumerate(head):
+        if hcfg["target"].endswith("GaussianConditioningAugmentationToTimestep"):
+            tp = hcfg["params"]
+            pre = f"_context_transformers.{n}._embedding_projection._projection."
+            s_emb = sinusoid_unet(augmentation_timestep, tp["num_features"], 1000.0)
+            emb = emb + _lin(sd, pre + "3", F.silu(_lin(sd, pre + "1", s_emb)))
+        elif hcfg["target"].endswith("PooledTextEmbeddingsToTimestep") and text is not None:
+            emb = emb + pooled_text_to_timestep(sd, p, text)
+    mults = p["channel_multipliers"]
+    nres = p["num_resnet_blocks"]
+    nres = nres if isinstance(nres, list) else [nres] * len(mults)
+    h = F.conv2d(x, sd["_initial_convolution.weight"], None, padding=1)
+
+    def block(pre, h, n_res):
+        e = _lin(sd, pre + "_embedding_layers.1", F.silu(emb))
+        h = h + e[:, :, None, None]
+        for r in range(n_res):
+            h = _resblock_efficient(sd, f"{pre}_resnet_blocks.{r}.", h)
+        if pre + "_attention._qkv.weight" in sd:
+            h = _spatial_attn(sd, pre + "_attention.", h, text=text)
+        return h
+
+    hs = []
+    for lvl in range(len(mults)):
+        pre = f"downs.{lvl}."
+        h = F.conv2d(h, sd[pre + "_downsampling_convolution.weight"], sd[pre + "_downsampling_convolution.bias"],
+                     stride=2, padding=1)
+        h = block(pre, h, nres[lvl])
+        hs.append(h)
+    hs.pop()
+    for idx, lvl in enumerate(reversed(range(len(mults)))):
+        pre = f"ups.{idx}."
+        h = h if idx == 0 else torch.cat([h, hs.pop()], dim=1)
+        h = block(pre, h, nres[lvl] + 1)
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+        h = F.conv2d(h, sd[pre + "_upsample.conv.weight"], sd[pre + "_upsample.conv.bias"], padding=1)
+    h = F.silu(_gn(sd, "final_projection.0", h))
+    return F.conv2d(h, sd["final_projection.2.weight"], None, padding=1)
+
+
+def sr_input(x, low_resolution_images, size, tables, s, z_cond):
+    """InputPreprocessor (layers/super_resolution.py:47-121): bilinear (antialias) resize of the [0, 1] low-resolution images,
+    normalise to [-1, 1], q_sample at the augmentation timestep s with noise z_cond (scheduler.py:289-308), concatenate behind
+    x on the channel axis."""
+    low = F.interpolate(low_resolution_images, size=(size, size), mode="bilinear", antialias=True, align_corners=False)
+    low = low * 2 - 1
+    a = tables["sqrt_alphas_cumprod"][s][:, None, None, None]
+    c = tables["sqrt_one_minus_alphas_cumprod"][s][:, None, None, None]
+    return torch.cat([x, a * low + c * z_cond], dim=1)
 
 
 # ----------------------------------------------------------------------------- DiT

@@ -31,8 +31,11 @@ CONFIGS = {
     # text-conditioned UNet (Imagen base stage, 8x8): encoder K/V in front of the self-attention K/V,
     # attention-pooled text embedding added to the timestep embedding; synthetic T5-shaped embeddings
     "c7": ("configs/image/mnist/imagen_base.yaml", "unet"),
+    # ... and its 8x8 -> 32x32 super-resolution stage (efficient UNet; fixture written by make_cascade.py)
+    "c8": ("configs/image/mnist/imagen_8x8_to_32x32.yaml", "effunet"),
 }
-PATCH = {"c4": ref_bootstrap.strip_t5_from_pixart, "c7": ref_bootstrap.strip_t5_from_imagen}
+PATCH = {"c4": ref_bootstrap.strip_t5_from_pixart, "c7": ref_bootstrap.strip_t5_from_imagen,
+         "c8": ref_bootstrap.strip_t5_from_imagen}
 
 
 class NoiseFeeder:

@@ -26,7 +26,7 @@ def test_target_paths_resolve_to_dropins():
     assert s.steps() == 1000 and not s.continuous()
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6", "c7"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c6", "c7", "c8"])
 def test_state_dict_keys_match_reference(name, golden):
     fx = golden(name)
     try:

@@ -608,3 +608,34 @@ def test_cpu_tensors_are_rejected(ops):
     a = torch.randn(128, 64).bfloat16()
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.xdb200.gemm(a, None, a, None, 0, None, 1, None, torch.empty(128, 128), 0)
+
+
+def test_strided_conv_channel_bias_and_sr_input(ops):
+    """The three small kernels of the cascade's super-resolution stage against torch: stride-2 conv3x3 as im2col + GEMM,
+    per-sample channel bias, and the input assembly [x | a * low + c * z] (bit-exact: un-fused fp32 like q_sample)."""
+    g = torch.Generator().manual_seed(4)
+    n, H, W, C, Co = 3, 8, 8, 64, 128
+    x = bf(torch.randn(n, C, H, W, generator=g))
+    w = bf(torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    b = torch.randn(Co, generator=g) * 0.1
+    ref = F.conv2d(x.float(), w.float(), b, stride=2, padding=1)                     # [n, Co, 4, 4]
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    cols = torch.empty(n * 16, 9 * C, dtype=torch.bfloat16, device=DEV)
+    torch.ops.xdb200.im2col3x3_s2(xd, cols)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous().to(DEV)
+    out = ops.linear(cols, wp, b.to(DEV)).view(n, 4, 4, Co)
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 4e-3
+    e = torch.randn(n, C, generator=g)
+    y = torch.empty_like(xd)
+    torch.ops.xdb200.add_channel_bias(xd.view(n, H * W, C), e.to(DEV), y.view(n, H * W, C))
+    assert torch.equal(y.cpu(), bf(xd.cpu().float() + e[:, None, None, :]))
+    xx, low, z = (torch.randn(n, 1, 32, 32, generator=g) for _ in range(3))
+    a, c = 0.8314696550369263, 0.5555702447891235
+    want = torch.cat([xx, torch.tensor(a) * low + torch.tensor(c) * z], 1)
+    got = torch.empty(n, 2, 32, 32, device=DEV)
+    torch.ops.xdb200.sr_input(xx.to(DEV), low.to(DEV), z.to(DEV), 0, got, a, c, None, 0, 0, None, 0)
+    assert torch.equal(got.cpu(), want)
+    p1, p2 = torch.empty_like(got), torch.empty_like(got)                            # in-kernel noise: N(0, 1), keyed by step
+    torch.ops.xdb200.sr_input(xx.to(DEV), torch.zeros_like(low).to(DEV), None, 0, p1, 1.0, 1.0, None, 5, 9, None, 0)
+    torch.ops.xdb200.sr_input(xx.to(DEV), torch.zeros_like(low).to(DEV), None, 0, p2, 1.0, 1.0, None, 6, 9, None, 0)
+    assert not torch.equal(p1[:, 1], p2[:, 1]) and abs(float(p1[:, 1].std()) - 1.0) < 0.1 and torch.equal(p1[:, 0].cpu(), xx[:, 0])

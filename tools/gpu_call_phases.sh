@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/s8_pytest.log 2>&1
-echo "tests rc=$?"; tail -12 gpurun_out/s8_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "strided_conv or super_resolution or cascade or query_blocks or c7" > gpurun_out/s9_pytest.log 2>&1
+echo "tests rc=$?"; tail -25 gpurun_out/s9_pytest.log

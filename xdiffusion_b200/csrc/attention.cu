@@ -582,12 +582,13 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
         }
         return XD_OK;
     }
-    if (Tq <= 128 && Tk <= 128 && !relk && !scramble && !in_f32) {  // short-context (cross-)attention (PixArt 16 x 77,
+    if (Tq <= 128 && Tk <= 144 && !relk && !scramble && !in_f32) {  // short-context (cross-)attention (PixArt 16 x 77,
         const long long nbh = (long long)B * H * ((Tq + 15) / 16);  // video 64 x 64): one warp per 16 query rows
         cudaError_t e;
         if (Tk <= 32) e = xd_launch(attention16xn_mma_kernel<2>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);
         else if (Tk <= 80) e = xd_launch(attention16xn_mma_kernel<5>, (unsigned)((nbh + 1) / 2), 64, 0, (cudaStream_t)stream, p);
-        else e = xd_launch(attention16xn_mma_kernel<8>, (unsigned)nbh, 32, 0, (cudaStream_t)stream, p);
+        else if (Tk <= 128) e = xd_launch(attention16xn_mma_kernel<8>, (unsigned)nbh, 32, 0, (cudaStream_t)stream, p);
+        else e = xd_launch(attention16xn_mma_kernel<9>, (unsigned)nbh, 32, 0, (cudaStream_t)stream, p);   // 64 + 77 keys (SR stage)
         if (e != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
             return XD_ERR_CUDA;

@@ -201,6 +201,44 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, long
         *reinterpret_cast<const bf16x8*>(x + b * x_bs + t * ldx + j * 8);
 }
 
+// Stride-2 3x3 convolution (pad 1) as im2col + GEMM: out[(n, y, x), tap * C + c] = X[n, 2y + dy - 1, 2x + dx - 1, c] (0 outside),
+// tap = 3 (dy) + dx, the K order of pack_conv3x3.  (DBlock._downsampling_convolution of the Imagen efficient UNet,
+// layers/resnet.py:272-280; 8 channels = 16 bytes per thread.)
+__global__ void im2col3x3_s2_kernel(const bf16* __restrict__ x, long long ldx, int H, int W, int C, bf16* __restrict__ out,
+                                    long long total) {
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int V = C / 8, Ho = H / 2, Wo = W / 2;
+    const int j = (int)(i % V);
+    long long r = i / V;
+    const int tap = (int)(r % 9);
+    r /= 9;                                                 // output pixel (n, y, x)
+    const int xo = (int)(r % Wo), yo = (int)((r / Wo) % Ho);
+    const long long n = r / ((long long)Wo * Ho);
+    const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+    bf16x8 v = {};
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = *reinterpret_cast<const bf16x8*>(x + ((n * H + yi) * W + xi) * ldx + j * 8);
+    *reinterpret_cast<bf16x8*>(out + (r * 9 + tap) * C + j * 8) = v;
+}
+
+// out[n, p, :] = x[n, p, :] + b[n, :]   (bf16 rows, fp32 per-sample channel bias: `h + Linear(SiLU(temb))[..., None, None]`,
+// layers/resnet.py:303-310,395-402)
+__global__ void add_channel_bias_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ b, long long ldb,
+                                        long long P, int C, bf16* __restrict__ out, long long ldo, long long total) {
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int V = C / 8;
+    const int j = (int)(i % V);
+    const long long row = i / V, n = row / P;
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + j * 8), f);
+    const float4 b0 = *reinterpret_cast<const float4*>(b + n * ldb + j * 8), b1 = *reinterpret_cast<const float4*>(b + n * ldb + j * 8 + 4);
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    *reinterpret_cast<bf16x8*>(out + row * ldo + j * 8) = pack8(f);
+}
+
 // x[b, c, f, :] = mask[b, f] ? x[b, c, f, :] : x0[b, c, f, :]   (video-mask blend, diffusion/ddpm.py:963-982), float4
 __global__ void blend_frames_kernel(float4* __restrict__ x, const float4* __restrict__ x0, const uint8_t* __restrict__ mask,
                                     int C, int F, int hw4, long long n4) {
@@ -332,6 +370,25 @@ extern "C" int xd_copy_rows_bf16(const void* x, long long ldx, long long x_bs, l
                  rows_per_batch > 0 && rows > 0);
     xd_launch(copy_rows_kernel, blocks_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, x_bs, rows,
               rows_per_batch, C, (bf16*)out, ldo, o_bs);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_im2col3x3_s2_nhwc(const void* x, long long ldx, int nimg, int H, int W, int C, void* out, void* stream) {
+    XD_CHECK_ARG(x && out && nimg > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && ldx % 8 == 0);
+    const long long total = (long long)nimg * (H / 2) * (W / 2) * 9 * (C / 8);
+    xd_launch(im2col3x3_s2_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, H, W, C, (bf16*)out,
+              total);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_add_channel_bias_nhwc(const void* x, long long ldx, const float* b, long long ldb, int nsamples, long long P,
+                                        int C, void* out, long long ldo, void* stream) {
+    XD_CHECK_ARG(x && b && out && nsamples > 0 && P > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldb % 4 == 0);
+    const long long total = (long long)nsamples * P * (C / 8);
+    xd_launch(add_channel_bias_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, b, ldb, P, C,
+              (bf16*)out, ldo, total);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

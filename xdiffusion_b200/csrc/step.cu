@@ -271,6 +271,49 @@ __global__ void edm_step_kernel(const EdmParams p) {
     }
 }
 
+// Super-resolution stage input (layers/super_resolution.py:47-121): out[b] = [ x[b] | a * low[b] + c * z[b] ] on the channel
+// axis; z = the Gaussian conditioning augmentation, RE-DRAWN at every network evaluation: row `idx` of an injected noise table
+// (parity runs), or Philox normals keyed by (seed ^ kSrKey, element, loop index).  Un-fused fp32 multiply / add like q_sample.
+struct SrParams {
+    const float *x, *low, *z;
+    float* out;
+    const int* idx_dev;
+    int idx_host;
+    long long z_step_stride;
+    int B, nx, nl;              // per sample: elements of x (Cx * HW) and of low (Cl * HW), multiples of 4
+    float a, c;
+    unsigned long long seed;
+    const unsigned long long* seed_dev;
+    unsigned long long vec_offset;
+};
+constexpr unsigned long long kSrKey = 0x9E3779B97F4A7C15ULL;
+
+__global__ void sr_input_kernel(const SrParams p) {
+    pdl_prologue();
+    const int per = (p.nx + p.nl) / 4;
+    const long long total = (long long)p.B * per;
+    const int idx = p.idx_dev ? *p.idx_dev : p.idx_host;
+    const unsigned long long seed = (p.seed_dev ? *p.seed_dev : p.seed) ^ kSrKey;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / per;
+        const int e = (int)(i - b * per) * 4;
+        float4 v;
+        if (e < p.nx) {
+            v = *reinterpret_cast<const float4*>(p.x + b * p.nx + e);
+        } else {
+            const long long li = b * p.nl + (e - p.nx);
+            const float4 l = *reinterpret_cast<const float4*>(p.low + li);
+            const float4 z = p.z ? *reinterpret_cast<const float4*>(p.z + (long long)idx * p.z_step_stride + li)
+                                 : philox_normal4(seed, p.vec_offset + (unsigned long long)(li >> 2), (uint32_t)idx);
+            v.x = __fadd_rn(__fmul_rn(p.a, l.x), __fmul_rn(p.c, z.x));
+            v.y = __fadd_rn(__fmul_rn(p.a, l.y), __fmul_rn(p.c, z.y));
+            v.z = __fadd_rn(__fmul_rn(p.a, l.z), __fmul_rn(p.c, z.z));
+            v.w = __fadd_rn(__fmul_rn(p.a, l.w), __fmul_rn(p.c, z.w));
+        }
+        *reinterpret_cast<float4*>(p.out + b * (p.nx + p.nl) + e) = v;
+    }
+}
+
 // xin = c_in * float(x)                                            (EDMPrecond.forward: (c_in * x).to(dtype))
 // x_hat = x + c_noise * z, fp64                                     (samplers/edm.py:117-120, S_churn > 0)
 __global__ void edm_in_kernel(const double* x, const double* z, double c_noise, double* x_hat, float c_in, float* xin,
@@ -299,6 +342,20 @@ extern "C" int xd_edm_step(int stage, const double* x_hat, const double* x_mid, 
     EdmParams p{stage, x_hat, x_mid, d_in, F, d_out, x_out, den_out, xin_out, t_div, h, c_skip, c_out, c_in_next, n};
     const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 8);
     xd_launch(edm_step_kernel, grid, 256, 0, (cudaStream_t)stream, p);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_sr_input(const float* x, const float* low, const float* z, long long z_step_stride, float* out, int B,
+                           int nx, int nl, float a, float c, const int* idx_dev, int idx_host, unsigned long long seed,
+                           const unsigned long long* seed_dev, long long elem_offset, void* stream) {
+    XD_CHECK_ARG(x && low && out && B > 0 && nx > 0 && nl > 0 && nx % 4 == 0 && nl % 4 == 0 && (idx_dev || idx_host >= 0));
+    XD_CHECK_ARG(elem_offset >= 0 && elem_offset % 4 == 0);
+    SrParams p{x, low, z, out, idx_dev, idx_host, z_step_stride, B, nx, nl, a, c, seed, seed_dev,
+               (unsigned long long)(elem_offset / 4)};
+    const long long total = (long long)B * ((nx + nl) / 4);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 8);
+    xd_launch(sr_input_kernel, grid, 256, 0, (cudaStream_t)stream, p);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

@@ -166,7 +166,7 @@ class GaussianDiffusion_DDPM(DiffusionModel):
                sampler: Optional[ReverseProcessSampler] = None, initial_noise: Optional[torch.Tensor] = None,
                context_preprocessor: Optional[torch.nn.Module] = None, noise: Optional[torch.Tensor] = None,
                use_cuda_graph: bool = True, seed: Optional[int] = None, row_offset: int = 0,
-               ) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
+               cond_noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
         """Same contract as the reference's ``sample()`` (diffusion/ddpm.py:544-669).  Extras:
         ``noise`` [N, *shape] injects the per-step Gaussian noise (row = loop index) for parity runs,
         ``seed`` keys the in-kernel Philox noise (and x_T when ``initial_noise`` is None) otherwise,
@@ -189,7 +189,15 @@ class GaussianDiffusion_DDPM(DiffusionModel):
         else:
             unconditional_context = None
         if "super_resolution" in self._config:
-            raise NotImplementedError("cascade / super-resolution stages are a 'next' row (SURVEY 8f)")
+            # a cascade's super-resolution stage (reference ddpm.py:613-618): the low-resolution conditioning arrives in the
+            # context; ``cond_noise`` [N, B, C, H, W] injects the per-evaluation conditioning-augmentation noise (parity runs)
+            context = dict(context)
+            if "sampling_augmentation_level" in self._config.super_resolution:
+                context["augmentation_level"] = self._config.super_resolution.sampling_augmentation_level
+            if cond_noise is not None:
+                if classifier_free_guidance is not None:
+                    raise NotImplementedError("injected conditioning noise with classifier-free guidance (two draws per step)")
+                context["sr_noise"] = cond_noise.to(device=device, dtype=torch.float32).contiguous()
         if context_preprocessor is not None:
             context = context_preprocessor(context, device)
         for pre in self._context_preprocessors:
@@ -316,10 +324,14 @@ class _DeviceLoop:
         """Timestep-invariant conditioning (e.g. PixArt cross-attention K/V) is refreshed eagerly,
         in place, so that graph replays read the new values."""
         net = self.model._score_network
-        if hasattr(net, "precompute_context"):
-            for ctx in (self.context, self.uncond):
-                if ctx is not None:
-                    net.precompute_context(ctx)
+        pre = self.model._input_preprocessor
+        for ctx in (self.context, self.uncond):
+            if ctx is None:
+                continue
+            if hasattr(pre, "precompute"):
+                pre.precompute(ctx, self.model._noise_scheduler)
+            if hasattr(net, "precompute_context"):
+                net.precompute_context(ctx)
 
     def _advance(self, set_to):
         t = self.tabs["timestep"]

@@ -88,18 +88,115 @@ class Downsample(torch.nn.Module):
         return out
 
 
-class Upsample(torch.nn.Module):
-    """Nearest x2 over (H, W) (reference: resnet.py:470-502)."""
+class Upsample(torch.nn.Module, Packed):
+    """Nearest x2 over (H, W), optionally followed by a 3x3 convolution (reference: resnet.py:470-502)."""
 
     def __init__(self, channels, use_conv, dims=2):
         super().__init__()
+        if use_conv and dims != 2:
+            raise NotImplementedError("resamp_with_conv=True for video")
+        self.channels, self.dims, self.use_conv = channels, dims, use_conv
         if use_conv:
-            raise NotImplementedError("resamp_with_conv=True")
-        self.channels, self.dims = channels, dims
+            self.conv = torch.nn.Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x, out=None):
         nimg, H, W, C = x.shape
-        if out is None:
-            out = torch.empty((nimg, H * 2, W * 2, C), device=x.device, dtype=torch.bfloat16)
-        torch.ops.xdb200.upsample2x(x, out)
-        return out
+        up = out if out is not None and not self.use_conv else \
+            torch.empty((nimg, H * 2, W * 2, C), device=x.device, dtype=torch.bfloat16)
+        torch.ops.xdb200.upsample2x(x, up)
+        if not self.use_conv:
+            return up
+        w = self.packed("w", (self.conv.weight,), lambda: pack_conv3x3(self.conv.weight))
+        return ops.conv3x3(up, w, self.conv.bias, out=out)
+
+
+class ResnetBlockEfficient(ContextBlock, Packed):
+    """Imagen "efficient" residual block (reference: resnet.py:204-250, figure A.27): GN32 + SiLU -> conv3x3 -> GN32 + SiLU ->
+    conv3x3 (zero-init), always a 1x1 skip projection, (skip + h) * 0.7071, no time embedding.  The skip projection is an
+    extra K segment of the second conv's tensor-core tile and the 0.7071 is folded into its weights and bias."""
+    SKIP_SCALE = 0.7071
+
+    def __init__(self, dim_in, dropout=0.0, dim_out=None, scale_skip_connection: bool = True, **kwargs):
+        super().__init__()
+        self._input_channels, self._output_channels = dim_in, dim_out or dim_in
+        co = self._output_channels
+        self._resnet_path = torch.nn.Sequential(
+            torch.nn.GroupNorm(32, dim_in), torch.nn.SiLU(), torch.nn.Conv2d(dim_in, co, 3, padding=1),
+            torch.nn.GroupNorm(32, co), torch.nn.SiLU(), torch.nn.Dropout(p=dropout),
+            zero_module(torch.nn.Conv2d(co, co, 3, padding=1)))
+        self._scale_skip_connection = scale_skip_connection
+        self._skip_connection = torch.nn.Conv2d(dim_in, co, 1)
+
+    def forward(self, x, samples, out=None):
+        g1, c1, g2, c2, skip = self._resnet_path[0], self._resnet_path[2], self._resnet_path[3], self._resnet_path[6], \
+            self._skip_connection
+        s = self.SKIP_SCALE if self._scale_skip_connection else 1.0
+        w1, w2, b2 = self.packed("w", (c1.weight, c2.weight, c2.bias, skip.weight, skip.bias), lambda: (
+            pack_conv3x3(c1.weight), pack_conv3x3(c2.weight * s, skip.weight * s), ((c2.bias + skip.bias) * s).detach().float()))
+        h = ops.groupnorm(_as_samples(x, samples), g1.weight, g1.bias, eps=g1.eps, silu=True).view(x.shape)
+        h = ops.conv3x3(h, w1, c1.bias)
+        h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, eps=g2.eps, silu=True).view(h.shape)
+        return ops.conv3x3(h, w2, b2, xs=x, out=out)
+
+
+class _EfficientStage(ContextBlock, Packed):
+    """Shared body of DBlock / UBlock: + Linear(SiLU(temb)) per channel -> ResnetBlockEfficient chain -> optional attention."""
+
+    def _build(self, dim_in, dim_out, num_resnet_blocks, time_embedding_dim, attention_type, attention_kwargs, dropout):
+        self._input_channels, self._output_channels = dim_in, dim_out or dim_in
+        self._embedding_layers = torch.nn.Sequential(torch.nn.SiLU(), torch.nn.Linear(time_embedding_dim, dim_in))
+        self._resnet_blocks = torch.nn.Sequential(*[
+            ResnetBlockEfficient(dim_in=dim_in if i == 0 else self._output_channels, dim_out=self._output_channels,
+                                 dropout=dropout) for i in range(num_resnet_blocks)])
+        self._attention = attention_type(in_channels=self._output_channels, **attention_kwargs) \
+            if attention_type is not None else torch.nn.Identity()
+
+    def emb_linear(self):
+        return self._embedding_layers[1].weight, self._embedding_layers[1].bias
+
+    def _body(self, h, emb, samples, context):
+        """h bf16 NHWC [n, H, W, C_in]; emb fp32 [samples, C_in] = this stage's slice of the batched embedding GEMM."""
+        n, H, W, C = h.shape
+        biased = torch.empty((n, H, W, C), device=h.device, dtype=torch.bfloat16)
+        torch.ops.xdb200.add_channel_bias(_as_samples(h, samples), emb, biased.view(samples, -1, C))
+        h = biased
+        for rb in self._resnet_blocks:
+            h = rb(h, samples)
+        if not isinstance(self._attention, torch.nn.Identity):
+            h = self._attention(h, context=context)
+        return h
+
+
+class DBlock(_EfficientStage):
+    """reference: resnet.py:253-330 (figure A.28): stride-2 conv3x3 first (im2col + tensor-core GEMM)."""
+
+    def __init__(self, dim_in, num_resnet_blocks, time_embedding_dim, downsample: bool, attention_type=None,
+                 attention_kwargs=None, dropout=0.0, dim_out=None, **kwargs):
+        super().__init__()
+        self._downsampling_convolution = torch.nn.Conv2d(dim_in, dim_in, 3, padding=1, stride=2) if downsample \
+            else torch.nn.Identity()
+        self._build(dim_in, dim_out, num_resnet_blocks, time_embedding_dim, attention_type, attention_kwargs or {}, dropout)
+
+    def forward(self, x, emb, samples, context):
+        conv = self._downsampling_convolution
+        if not isinstance(conv, torch.nn.Identity):
+            n, H, W, C = x.shape
+            w = self.packed("wd", (conv.weight,), lambda: pack_conv3x3(conv.weight))
+            cols = torch.empty((n * (H // 2) * (W // 2), 9 * C), device=x.device, dtype=torch.bfloat16)
+            torch.ops.xdb200.im2col3x3_s2(x, cols)
+            x = ops.linear(cols, w, conv.bias).view(n, H // 2, W // 2, C)
+        return self._body(x, emb, samples, context)
+
+
+class UBlock(_EfficientStage):
+    """reference: resnet.py:333-437 (figure A.29): nearest x2 + conv3x3 last."""
+
+    def __init__(self, dim_in, num_resnet_blocks, time_embedding_dim, upsample: bool, attention_type=None,
+                 attention_kwargs=None, dropout=0.0, dim_out=None, **kwargs):
+        super().__init__()
+        self._upsample = Upsample(channels=dim_out or dim_in, use_conv=True) if upsample else torch.nn.Identity()
+        self._build(dim_in, dim_out, num_resnet_blocks, time_embedding_dim, attention_type, attention_kwargs or {}, dropout)
+
+    def forward(self, x, emb, samples, context):
+        h = self._body(x, emb, samples, context)
+        return h if isinstance(self._upsample, torch.nn.Identity) else self._upsample(h)

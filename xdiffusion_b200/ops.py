@@ -375,6 +375,45 @@ def _copy_rows(x, out):
     _count()
 
 
+@_op("im2col3x3_s2(Tensor x, Tensor(a!) out) -> ()")
+def _im2col3x3_s2(x, out):
+    """x bf16 NHWC [n, H, W, C] (pixel stride x.stride(2)) -> out bf16 [n * H/2 * W/2, 9 * C] (stride-2, pad-1 taps)."""
+    _cuda(x, out)
+    n, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape == (n * (H // 2) * (W // 2), 9 * C)
+    _lib.check(_lib.lib().xd_im2col3x3_s2_nhwc(_p(x), x.stride(2), n, H, W, C, _p(out), _stream()), "xd_im2col3x3_s2_nhwc")
+    _count()
+
+
+@_op("add_channel_bias(Tensor x, Tensor bias, Tensor(a!) out) -> ()")
+def _add_channel_bias(x, bias, out):
+    """x bf16 [n, P, C] (uniform row stride) + bias fp32 [n, C] -> out bf16 [n, P, C]."""
+    _cuda(x, bias, out)
+    n, P, C = x.shape
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert x.stride(2) == 1 and out.stride(2) == 1 and x.stride(0) == P * x.stride(1) and out.stride(0) == P * out.stride(1)
+    assert bias.shape == (n, C) and bias.stride(1) == 1 and out.shape == x.shape
+    _lib.check(_lib.lib().xd_add_channel_bias_nhwc(_p(x), x.stride(1), _p(bias), bias.stride(0), n, P, C, _p(out),
+                                                   out.stride(1), _stream()), "xd_add_channel_bias_nhwc")
+    _count()
+
+
+@_op("sr_input(Tensor x, Tensor low, Tensor? z, int z_step_stride, Tensor(a!) out, float a, float c, Tensor? idx_dev, "
+     "int idx_host, int seed, Tensor? seed_dev, int elem_offset) -> ()")
+def _sr_input(x, low, z, z_step_stride, out, a, c, idx_dev, idx_host, seed, seed_dev, elem_offset):
+    """out[b] = [x[b] | a * low[b] + c * z[b]] on the channel axis (fp32 NCHW), z injected or in-kernel Philox."""
+    _cuda(x, low, z, out, idx_dev, seed_dev)
+    B = x.shape[0]
+    nx, nl = x[0].numel(), low[0].numel()
+    assert x.is_contiguous() and low.is_contiguous() and out.is_contiguous() and out[0].numel() == nx + nl
+    assert all(t.dtype == torch.float32 for t in (x, low, out)) and low.shape[0] == B and out.shape[0] == B
+    assert z is None or (z.dtype == torch.float32 and z.is_contiguous())
+    _lib.check(_lib.lib().xd_sr_input(_p(x), _p(low), _p(z), z_step_stride, _p(out), B, nx, nl, a, c, _p(idx_dev), idx_host,
+                                      seed, _p(seed_dev), elem_offset, _stream()), "xd_sr_input")
+    _count()
+
+
 @_op("blend_frames(Tensor(a!) x, Tensor x0, Tensor mask) -> ()")
 def _blend_frames(x, x0, mask):
     """x[b, c, f] = mask[b, f] ? x[b, c, f] : x0[b, c, f] in place (x, x0 fp32 [B, C, F, H, W]; mask bool / uint8 [B, F])."""
