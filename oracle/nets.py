@@ -335,6 +335,81 @@ def sr_input(x, low_resolution_images, size, tables, s, z_cond):
     return torch.cat([x, a * low + c * z_cond], dim=1)
 
 
+# ----------------------------------------------------------------------------- EDM: DDPM++ (SongUNet)
+def _edm_gn(sd, pre, x):
+    """layers/edm.py GroupNorm: min(32, C // 4) groups, eps 1e-6 in SongUNet blocks (score_networks/edm.py:68)."""
+    C = x.shape[1]
+    return F.group_norm(x, min(32, C // 4), sd[pre + ".weight"], sd[pre + ".bias"], 1e-6)
+
+
+def _edm_block(sd, pre, x, emb, skip_scale, up=False, down=False):
+    """layers/edm.py UNetBlock.forward (:302-343) with adaptive_scale = False, resample_filter [1, 1] (up = nearest x2,
+    down = 2x2 average: Conv2d.forward :97-145 with f = [[1,1],[1,1]] / 4), resample_proj = True, one attention head."""
+    def resample(t):
+        if up:
+            return F.interpolate(t, scale_factor=2, mode="nearest")
+        if down:
+            return F.avg_pool2d(t, 2, 2)
+        return t
+    orig = x
+    x = F.conv2d(resample(F.silu(_edm_gn(sd, pre + "norm0", x))), sd[pre + "conv0.weight"], sd[pre + "conv0.bias"], padding=1)
+    params = _lin(sd, pre + "affine", emb)[:, :, None, None]
+    x = F.silu(_edm_gn(sd, pre + "norm1", x + params))
+    x = F.conv2d(x, sd[pre + "conv1.weight"], sd[pre + "conv1.bias"], padding=1)
+    if pre + "skip.weight" in sd:
+        orig = F.conv2d(resample(orig), sd[pre + "skip.weight"], sd[pre + "skip.bias"])
+    x = (x + orig) * skip_scale
+    if pre + "qkv.weight" in sd:
+        B, C = x.shape[:2]
+        qkv = F.conv2d(_edm_gn(sd, pre + "norm2", x), sd[pre + "qkv.weight"], sd[pre + "qkv.bias"])
+        q, k, v = qkv.reshape(B, C, 3, -1).unbind(2)                        # one head: channel c of q = output channel 3c
+        w = torch.einsum("ncq,nck->nqk", q, k / math.sqrt(C)).softmax(dim=2)
+        a = torch.einsum("nqk,nck->ncq", w, v)
+        x = (F.conv2d(a.reshape(x.shape), sd[pre + "proj.weight"], sd[pre + "proj.bias"]) + x) * skip_scale
+    return x
+
+
+def songunet_forward(sd, p, x, noise_labels, prefix="model."):
+    """score_networks/edm.py SongUNet.forward (:183-238), DDPM++ configuration (positional embedding, standard encoder /
+    decoder).  ``noise_labels`` (n,) fp32 with n = 1 or B."""
+    nc = p["model_channels"] * p.get("channel_mult_noise", 1)
+    freqs = torch.arange(0, nc // 2, dtype=torch.float32) / (nc // 2 - 1)
+    freqs = (1 / 10000) ** freqs
+    e = noise_labels.float().ger(freqs)
+    emb = torch.cat([e.cos(), e.sin()], dim=1)
+    emb = emb.reshape(emb.shape[0], 2, -1).flip(1).reshape(*emb.shape)              # swap sin / cos
+    emb = F.silu(_lin(sd, prefix + "map_layer0", emb))
+    emb = F.silu(_lin(sd, prefix + "map_layer1", emb))
+    s = math.sqrt(0.5)
+    names = {"enc": [], "dec": []}
+    for k in sd:                                                                    # ModuleDict order = state-dict order
+        if k.startswith(prefix + "enc.") or k.startswith(prefix + "dec."):
+            part, name = k[len(prefix):].split(".")[:2]
+            if name not in names[part]:
+                names[part].append(name)
+    skips = []
+    for name in names["enc"]:
+        pre = f"{prefix}enc.{name}."
+        if name.endswith("_conv"):
+            x = F.conv2d(x, sd[pre + "weight"], sd[pre + "bias"], padding=1)
+        else:
+            x = _edm_block(sd, pre, x, emb, s, down=name.endswith("_down"))
+        skips.append(x)
+    out = None
+    for name in names["dec"]:
+        pre = f"{prefix}dec.{name}."
+        if name.endswith("aux_norm"):
+            out = _edm_gn(sd, pre[:-1], x)
+        elif name.endswith("aux_conv"):
+            out = F.conv2d(F.silu(out), sd[pre + "weight"], sd[pre + "bias"], padding=1)
+        else:
+            cin = sd[pre + "norm0.weight"].shape[0]
+            if x.shape[1] != cin:
+                x = torch.cat([x, skips.pop()], dim=1)
+            x = _edm_block(sd, pre, x, emb, s, up=name.endswith("_up"))
+    return out
+
+
 # ----------------------------------------------------------------------------- DiT
 def _ln(x):
     return F.layer_norm(x, x.shape[-1:], None, None, 1e-6)

@@ -12,7 +12,7 @@ import hashlib
 
 import torch
 
-_KEEP = ("pos_embed",)          # deterministic tables: keep the constructor's value
+_KEEP = ("pos_embed", "resample_filter")          # deterministic tables: keep the constructor's value
 
 
 def _seed(key: str, seed: int) -> int:

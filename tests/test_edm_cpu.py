@@ -39,3 +39,31 @@ def test_product_time_steps_and_scalars_match_oracle():
         s = sigma.to(torch.float32).reshape(-1, 1, 1, 1)
         want = (0.25 / (s ** 2 + 0.25), s * 0.5 / (s ** 2 + 0.25).sqrt(), 1 / (0.25 + s ** 2).sqrt(), s.log() / 4)
         assert net.precond_scalars(sigma) == tuple(float(w) for w in want)
+
+
+def _net_fx():
+    return torch.load(os.path.join(GOLDEN, "edm_net.pt"), weights_only=False)
+
+
+def test_oracle_songunet_and_precond_match_reference():
+    """The oracle's DDPM++ network (oracle.nets.songunet_forward) + EDMPrecond against the real reference
+    (tests/golden/make_edm_net.py): raw output, denoiser at four noise levels, and a 4-step Heun run."""
+    from oracle import nets
+    from oracle.weights import synth_state_dict
+    fx = _net_fx()
+    sd = synth_state_dict(fx["manifest"], seed=0)
+    p = fx["config"]["diffusion"]["score_network"]["params"]["model"]["params"]
+    raw = lambda x, c: nets.songunet_forward(sd, p, x, c)
+    with torch.no_grad():
+        r = fx["raw"]
+        f = raw(r["x"], r["c_noise"])
+        assert float((f - r["F"]).norm() / r["F"].norm()) < 1e-5
+        for rec in fx["denoise"]:
+            d = osamplers.edm_precond(raw, rec["x"], torch.tensor(rec["sigma"]))
+            assert float((d - rec["D"]).norm() / rec["D"].norm()) < 1e-5, rec["sigma"]
+        sm = fx["sampler"]
+        trace = []
+        osamplers.edm_sample(raw, sm["latents"], num_steps=sm["num_steps"], noise=[torch.zeros_like(sm["latents"], dtype=torch.float64)] * 4,
+                             trace=trace)
+        for a, b in zip(trace, sm["states"]):
+            assert float((a - b).norm() / b.norm()) < 1e-5

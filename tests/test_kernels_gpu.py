@@ -299,6 +299,21 @@ def test_attention_query_blocks_on_tensor_cores(ops, Tq, Tk, B, H):
     assert rel_l2(out, ref) < 4e-3, rel_l2(out, ref)
 
 
+@pytest.mark.parametrize("T,B", [(256, 3), (64, 5), (100, 2)])
+def test_attention_wide_single_head(ops, T, B):
+    """Head dim 256, one head (the attention of the EDM DDPM++ network, layers/edm.py UNetBlock): the mma.sync flash kernel
+    against fp32 softmax attention on the same bf16 operands, [Q | K | V]-major rows like the network produces them."""
+    g = torch.Generator().manual_seed(500 + T)
+    C = 256
+    qkv = bf(torch.randn(B, T, 3 * C, generator=g))
+    q, k, v = (qkv[:, :, i * C:(i + 1) * C].float() for i in range(3))
+    ref = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), -1) @ v                  # B, T, C
+    d = qkv.to(DEV).view(B, T, 3, 1, C)
+    qd, kd, vd = (d[:, :, i].permute(0, 2, 1, 3) for i in range(3))                    # [B, 1, T, C] views
+    out = ops.attention(qd, kd, vd, 1 / math.sqrt(C))
+    assert rel_l2(out[:, 0], ref) < 4e-3, rel_l2(out[:, 0], ref)
+
+
 def test_attention_relative_position_scrambled(ops):
     """TemporalSelfAttention core incl. the reference's raw reshape (oracle.nets.relpos_attention)."""
     g = torch.Generator().manual_seed(21)

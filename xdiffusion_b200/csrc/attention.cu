@@ -545,6 +545,133 @@ __global__ void __launch_bounds__(KT > 5 ? 32 : 64) attention16xn_mma_kernel(con
     }
 }
 
+// ---- wide heads: head dim = 64 * DCH (the single-head attention of the EDM DDPM++ network: d = C = 256, T = 256 or 64).
+// One CTA = 64 query rows of one (batch, head), four warps of 16 rows; keys / values stream through shared memory in blocks
+// of 64 with the online-softmax recurrence; S = Q K^T and O += P V on mma.sync m16n8k16 (the S accumulators are re-used as
+// the A operand of P V, as in the kernels above).  Shared-memory tiles: [DCH][64 rows][64 columns] bf16, 128-byte rows with
+// 16-byte chunk c of row r at c ^ (r & 7) (conflict-free ldmatrix).
+template <int DCH>
+__global__ void __launch_bounds__(128) attention_wide_kernel(const AttnParams p) {
+    pdl_prologue();
+    extern __shared__ __align__(128) uint8_t smw[];
+    constexpr int TILE = 64 * 128;                        // bytes of one [64 x 64] tile
+    uint8_t* sQ = smw;
+    uint8_t* sK = sQ + DCH * TILE;
+    uint8_t* sV = sK + DCH * TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqb = (p.Tq + 63) >> 6;
+    const long long bh = blockIdx.x / nqb;
+    const int q0 = (int)(blockIdx.x - bh * nqb) * 64;
+    const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+    const bf16* qp = p.q + b * p.q_bs + h * p.q_hs;
+    const bf16* kp = p.k + b * p.k_bs + h * p.k_hs;
+    const bf16* vp = p.v + b * p.v_bs + h * p.v_hs;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    // [64 rows x 64 * DCH columns] from global rows r0.. (rows >= limit are zero) into the tiled layout
+    auto stage = [&](uint8_t* dst, const bf16* src, long long rs, int r0, int limit) {
+        for (int i = threadIdx.x; i < 64 * 8 * DCH; i += 128) {
+            const int row = i / (8 * DCH), cc = i % (8 * DCH), t = cc >> 3, c = cc & 7;
+            const uint4 v = r0 + row < limit ? *reinterpret_cast<const uint4*>(src + (long long)(r0 + row) * rs + cc * 8) : zero;
+            *reinterpret_cast<uint4*>(dst + t * TILE + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+        }
+    };
+    stage(sQ, qp, p.q_rs, q0, p.Tq);
+    const uint32_t aQ = (uint32_t)__cvta_generic_to_shared(sQ) + warp * 16 * 128, aK = (uint32_t)__cvta_generic_to_shared(sK),
+                   aV = (uint32_t)__cvta_generic_to_shared(sV);
+    float o[8 * DCH][4];
+#pragma unroll
+    for (int nt = 0; nt < 8 * DCH; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+    const float c = p.scale * 1.4426950408889634f;
+    for (int k0 = 0; k0 < p.Tk; k0 += 64) {
+        __syncthreads();                                  // everyone is done with the previous key / value block
+        stage(sK, kp, p.k_rs, k0, p.Tk);
+        stage(sV, vp, p.v_rs, k0, p.Tk);
+        __syncthreads();
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < DCH; ++t) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0, a1, a2, a3;
+                {
+                    const int row = (lane & 7) + ((lane >> 3) & 1) * 8, cc = 2 * ks + (lane >> 4);
+                    ldsm_x4(aQ + t * TILE + row * 128 + ((cc ^ (row & 7)) << 4), a0, a1, a2, a3);
+                }
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) {          // 16 keys = two 8-key n-tiles per ldmatrix.x4
+                    uint32_t b0, b1, b2, b3;
+                    const int row = kt * 16 + (lane & 7) + (lane >> 4) * 8, cc = 2 * ks + ((lane >> 3) & 1);
+                    ldsm_x4(aK + t * TILE + row * 128 + ((cc ^ (row & 7)) << 4), b0, b1, b2, b3);
+                    mma_bf16_16816(s[2 * kt], a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(s[2 * kt + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+        }
+        // mask keys >= Tk; block maxima of rows r = lane / 4 (elements 0, 1) and r + 8 (elements 2, 3)
+        float bm_lo = -INFINITY, bm_hi = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = k0 + nt * 8 + (lane & 3) * 2 + (j & 1);
+                if (key >= p.Tk) s[nt][j] = -INFINITY;
+                if (j < 2) bm_lo = fmaxf(bm_lo, s[nt][j]); else bm_hi = fmaxf(bm_hi, s[nt][j]);
+            }
+        bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+        bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+        const float n_lo = fmaxf(m_lo, bm_lo), n_hi = fmaxf(m_hi, bm_hi);
+        const float f_lo = exp2f((m_lo - n_lo) * c), f_hi = exp2f((m_hi - n_hi) * c);      // (exp2(-inf) = 0 on the first block)
+        m_lo = n_lo; m_hi = n_hi;
+        float r_lo = 0.f, r_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f((s[nt][0] - n_lo) * c); s[nt][1] = exp2f((s[nt][1] - n_lo) * c);
+            s[nt][2] = exp2f((s[nt][2] - n_hi) * c); s[nt][3] = exp2f((s[nt][3] - n_hi) * c);
+            r_lo += s[nt][0] + s[nt][1];
+            r_hi += s[nt][2] + s[nt][3];
+        }
+        l_lo = l_lo * f_lo + r_lo;                        // (per-lane partial sums; reduced over the quad at the end)
+        l_hi = l_hi * f_hi + r_hi;
+#pragma unroll
+        for (int nt = 0; nt < 8 * DCH; ++nt) { o[nt][0] *= f_lo; o[nt][1] *= f_lo; o[nt][2] *= f_hi; o[nt][3] *= f_hi; }
+        // O += P V: four k-steps of 16 keys; V^T fragments via ldmatrix.trans, two 8-wide n-tiles of d per instruction
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t pa0 = f2_to_bf2(s[2 * kt][0], s[2 * kt][1]), pa1 = f2_to_bf2(s[2 * kt][2], s[2 * kt][3]);
+            const uint32_t pa2 = f2_to_bf2(s[2 * kt + 1][0], s[2 * kt + 1][1]), pa3 = f2_to_bf2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+            for (int t = 0; t < DCH; ++t) {
+#pragma unroll
+                for (int nt = 0; nt < 8; nt += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, cc = nt + (lane >> 4);
+                    ldsm_x4_trans(aV + t * TILE + row * 128 + ((cc ^ (row & 7)) << 4), b0, b1, b2, b3);
+                    mma_bf16_16816(o[t * 8 + nt], pa0, pa1, pa2, pa3, b0, b1);
+                    mma_bf16_16816(o[t * 8 + nt + 1], pa0, pa1, pa2, pa3, b2, b3);
+                }
+            }
+        }
+    }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+    const int r_lo_g = q0 + warp * 16 + (lane >> 2), r_hi_g = r_lo_g + 8;
+    bf16* op = p.o + b * p.o_bs + h * p.o_hs;
+#pragma unroll
+    for (int nt = 0; nt < 8 * DCH; ++nt) {
+        const int col = nt * 8 + (lane & 3) * 2;
+        if (r_lo_g < p.Tq) *reinterpret_cast<uint32_t*>(op + (long long)r_lo_g * p.o_rs + col) = f2_to_bf2(o[nt][0] * i_lo, o[nt][1] * i_lo);
+        if (r_hi_g < p.Tq) *reinterpret_cast<uint32_t*>(op + (long long)r_hi_g * p.o_rs + col) = f2_to_bf2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+    }
+}
+
 }  // namespace
 
 int xd_attention_tc256_try(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k,
@@ -558,8 +685,9 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
                                  long long o_rs, int B, int H, int Tq, int Tk, int head_dim, float scale,
                                  const float* relk, int scramble, long long o_cs, int qkv_dtype, int heads_per_group,
                                  long long o_gs, void* stream) {
-    XD_CHECK_ARG(q && k && v && o && head_dim == D && B > 0 && H > 0 && Tq > 0 && Tk > 0);
+    XD_CHECK_ARG(q && k && v && o && (head_dim == D || head_dim == 4 * D) && B > 0 && H > 0 && Tq > 0 && Tk > 0);
     const int in_f32 = qkv_dtype == XD_F32;
+    XD_CHECK_ARG(head_dim == D || (!in_f32 && !relk && !scramble));
     XD_CHECK_ARG(!in_f32 || (Tq == 16 && Tk == 16));            // fp32 q/k/v: SIMT T = 16 kernel only
     XD_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && q_hs % 8 == 0 && k_hs % 8 == 0 && v_hs % 8 == 0 &&
                  q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0);
@@ -569,6 +697,24 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
     XD_CHECK_ARG(H % heads_per_group == 0 && (heads_per_group == H || relk || scramble));
     AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, q_bs, q_hs, q_rs, k_bs, k_hs, k_rs,
                  v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, B, H, Tq, Tk, scale, relk, scramble, o_cs, in_f32, heads_per_group, o_gs};
+    if (head_dim == 4 * D) {                                      // wide single head (EDM DDPM++ network), mma.sync flash kernel
+        XD_CHECK_ARG(o_rs % 2 == 0 && o_hs % 2 == 0 && o_bs % 2 == 0);
+        const size_t smem = 3 * 4 * 64 * 128;
+        static bool configured_w = false;
+        if (!configured_w) {
+            if (cudaFuncSetAttribute(attention_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed (attention_wide)");
+                return XD_ERR_CUDA;
+            }
+            configured_w = true;
+        }
+        const long long blocks = (long long)B * H * ((Tq + 63) / 64);
+        if (xd_launch(attention_wide_kernel<4>, (unsigned)blocks, 128, smem, (cudaStream_t)stream, p) != cudaSuccess) {
+            xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+            return XD_ERR_CUDA;
+        }
+        return XD_OK;
+    }
     if (Tq == 256 && Tk == 256 && !relk && !scramble) {           // tcgen05 path (csrc/attention_tc.cu)
         const int rc = xd_attention_tc256_try(q, q_bs, q_hs, q_rs, k, k_bs, k_hs, k_rs, v, v_bs, v_hs, v_rs, o, o_bs,
                                               o_hs, o_rs, B, H, scale, (cudaStream_t)stream);
