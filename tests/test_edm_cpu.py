@@ -67,3 +67,17 @@ def test_oracle_songunet_and_precond_match_reference():
                              trace=trace)
         for a, b in zip(trace, sm["states"]):
             assert float((a - b).norm() / b.norm()) < 1e-5
+
+
+def test_product_songunet_state_dict_matches_reference_manifest():
+    """The product's DDPM++ network built from the reference's own configs/image/mnist/edm.yaml has exactly the reference's
+    state_dict keys and shapes (incl. the ``resample_filter`` buffers), and the reference's values in those buffers."""
+    from xdiffusion_b200.diffusion.edm import GaussianDiffusion_EDM
+    from xdiffusion_b200.utils import DotConfig
+    fx = _net_fx()
+    m = GaussianDiffusion_EDM(DotConfig(fx["config"]))
+    sd = m._score_network.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == fx["manifest"]
+    for k, v in sd.items():
+        if k.endswith("resample_filter"):
+            assert torch.equal(v, torch.full((1, 1, 2, 2), 0.25))
