@@ -95,6 +95,28 @@ int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int
                        const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
                        long long out_ld, int force_bn, void* stream);
 
+/* GroupNorm statistics from the producer.  The `_qstats` variants compute exactly what xd_gemm_bf16_tc / xd_conv3x3_bf16_tc
+ * compute and, when the launch takes the unsplit bf16 TMA-epilogue path without activation (*emitted = 1), also write per
+ * block of 32 output rows and per quad of 4 output columns the fp32 (sum, sum of squares) of the stored values:
+ *   qstats[(m / 32) * qstats_ld + (n / 4) * 2 + {0, 1}]        (M % 32 == 0, N % 4 == 0, fixed summation order).
+ * *emitted = 0 (host int; split-K, narrow tiles, fp32 out): nothing was written, run the stand-alone GroupNorm.
+ * xd_groupnorm_apply_quads is the GroupNorm (+ scale/shift, + SiLU) of torch.nn.GroupNorm(32, C) over a tensor whose
+ * producers all emitted their quads (a concat buffer: each producer its own channel slice): one streaming pass, the
+ * `x.float().mean / var` reduction of the reference (layers/resnet.py:126-128,151-153) never re-reads x. */
+int xd_gemm_bf16_tc_qstats(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                           long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                           int gate_rows, long long gate_ld, const void* residual, int res_dtype, long long res_ld,
+                           void* out, int out_dtype, long long out_ld, int force_bn, float* qstats, long long qstats_ld,
+                           int* emitted, void* stream);
+int xd_conv3x3_bf16_tc_qstats(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                              long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                              const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                              long long out_ld, int force_bn, float* qstats, long long qstats_ld, int* emitted,
+                              void* stream);
+int xd_groupnorm_apply_quads(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* qstats,
+                             long long qstats_ld, const float* gamma, const float* beta, const float* scale_shift,
+                             long long ss_ld, int ss_div, float eps, int silu, void* out, long long ldo, void* stream);
+
 /* CUDA-core twins with the identical contract (on-device cross-check; K not a multiple of 64). */
 int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
                       long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,

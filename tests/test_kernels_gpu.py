@@ -197,6 +197,106 @@ def test_conv3x3_strided_concat_slot(ops):
     assert float(outw[..., Co:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("nimg,H,C,Co,Cs,c0,wide,splitk", [
+    (4, 32, 128, 128, 0, 0, 128, False), (2, 32, 128, 128, 128, 128, 384, False), (4, 16, 256, 256, 0, 256, 512, False),
+    (8, 16, 128, 256, 128, 0, 256, False), (16, 8, 256, 256, 0, 0, 256, False), (2, 8, 256, 256, 0, 0, 256, True),
+    (16, 32, 128, 128, 0, 0, 128, True), (64, 16, 256, 256, 0, 256, 512, True)])
+def test_conv3x3_quad_stats_and_groupnorm_from_them(ops, nimg, H, C, Co, Cs, c0, wide, splitk):
+    """GroupNorm statistics from the producer (include/xdb200.h: xd_conv3x3_bf16_tc_qstats + xd_groupnorm_apply_quads): the
+    conv writes its slice of a concat buffer and emits per-(32 rows, 4 channels) sums; they equal the sums of the stored
+    tensor (to the bf16 rounding of the stored values), and the GroupNorm computed from them equals the stand-alone
+    GroupNorm and the fp32 torch reference.  Where the launch cannot emit (split-K at few tiles) the helper says so and
+    the GroupNorm falls back."""
+    g = torch.Generator().manual_seed(nimg + H + C + Co + c0)
+    x = bf(torch.randn(nimg, H, H, C, generator=g)).to(DEV)
+    w = bf(torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    xs = ws = None
+    if Cs:
+        xs = bf(torch.randn(nimg, H, H, Cs, generator=g)).to(DEV)
+        ws = bf(torch.randn(Co, Cs, 1, 1, generator=g) / math.sqrt(Cs))
+    bias = torch.randn(Co, generator=g).to(DEV)
+    buf = bf(torch.randn(nimg, H, H, wide, generator=g)).to(DEV)                 # the other slices: someone else's data
+    gamma, beta = (1 + 0.1 * torch.randn(wide, generator=g)).to(DEV), (0.1 * torch.randn(wide, generator=g)).to(DEV)
+    ss = (torch.randn(nimg, 2 * wide, generator=g) * 0.3).to(DEV)
+    wp = _pack_conv(w, ws).to(DEV)
+    ops.set_split_k(splitk)
+    try:
+        _quad_stats_case(ops, x, wp, bias, xs, buf, c0, Co, wide, gamma, beta, ss, nimg, H, expect=not (splitk and nimg == 2))
+    finally:
+        ops.set_split_k(True)
+
+
+def _quad_stats_case(ops, x, wp, bias, xs, buf, c0, Co, wide, gamma, beta, ss, nimg, H, expect):
+    with ops.quad_stats():
+        out = ops.conv3x3(x, wp, bias, xs=xs, out=buf[..., c0:c0 + Co], qstats=True)
+        book = ops._qs_book[buf.untyped_storage().data_ptr()]
+        emitted = (c0, c0 + Co) in book["cover"]
+        rows = nimg * H * H
+        assert emitted == expect, (emitted, rows)        # (2 images of 8 x 8 with split-K on: one tile, long K -> split -> none)
+        if emitted:
+            q = book["table"][:, c0 // 4:(c0 + Co) // 4].cpu()
+            o = out.float().cpu().reshape(rows // 32, 32, Co // 4, 4)
+            assert float((q[..., 0] - o.sum((1, 3))).abs().max()) < 0.15                   # 128 values of |x| ~ 1, bf16-rounded
+            assert rel_l2(q[..., 1], (o * o).sum((1, 3))) < 3e-3
+        # the other slices of the concat buffer come from a producer without statistics: full-width GroupNorm must not use them
+        assert ops._qs_lookup(buf.view(nimg, H * H, wide)) is None or (c0 == 0 and Co == wide)
+        sl = buf[..., c0:c0 + Co]
+        view = sl.as_strided((nimg, H * H, Co), (H * H * wide, wide, 1), sl.storage_offset())
+        assert (ops._qs_lookup(view) is not None) == emitted
+        n0 = ops.LAUNCHES
+        got = ops.groupnorm(view, gamma[:Co], beta[:Co], scale_shift=ss[:, :2 * Co], silu=True)
+        assert ops.LAUNCHES - n0 == 1
+    alone = ops.groupnorm(view, gamma[:Co], beta[:Co], scale_shift=ss[:, :2 * Co], silu=True)     # outside the scope
+    ref = F.group_norm(view.float().cpu().permute(0, 2, 1), 32, gamma[:Co].cpu(), beta[:Co].cpu(), 1e-5)
+    ref = F.silu(ref * (1 + ss[:, :Co, None].cpu()) + ss[:, Co:2 * Co, None].cpu())
+    assert rel_l2(got.permute(0, 2, 1), ref) < 3e-3, rel_l2(got.permute(0, 2, 1), ref)
+    assert rel_l2(got, alone) < 3e-3
+    # conv result itself unchanged by the statistics epilogue
+    plain = ops.conv3x3(x, wp, bias, xs=xs)
+    assert torch.equal(plain, out)
+
+
+def test_quad_stats_concat_of_two_producers_and_invalidation(ops):
+    """A concat buffer whose two slices come from two contractions (a conv and a 1x1 projection with residual): GroupNorm over
+    the full width uses the merged statistics (group boundaries straddle the seam: 384 channels = 32 groups of 12); a later
+    write into the buffer by an op without statistics drops them."""
+    g = torch.Generator().manual_seed(77)
+    nimg, H, Ca, Cb = 4, 16, 256, 128
+    buf = torch.zeros(nimg, H, H, Ca + Cb, dtype=torch.bfloat16, device=DEV)
+    x = bf(torch.randn(nimg, H, H, Ca, generator=g)).to(DEV)
+    w = _pack_conv(bf(torch.randn(Ca, Ca, 3, 3, generator=g) / math.sqrt(9 * Ca))).to(DEV)
+    a = bf(torch.randn(nimg * H * H, 128, generator=g)).to(DEV)
+    wl = bf(torch.randn(Cb, 128, generator=g) / math.sqrt(128)).to(DEV)
+    res = bf(torch.randn(nimg * H * H, Cb, generator=g)).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(Ca + Cb, generator=g)).to(DEV), (0.1 * torch.randn(Ca + Cb, generator=g)).to(DEV)
+    full = buf.view(nimg, H * H, Ca + Cb)
+    ops.set_split_k(False)                      # (4 images: the conv would otherwise be split over K and emit nothing)
+    try:
+        _two_producers_case(ops, buf, x, w, a, wl, res, gamma, beta, full, nimg, H, Ca, Cb, g)
+    finally:
+        ops.set_split_k(True)
+
+
+def _two_producers_case(ops, buf, x, w, a, wl, res, gamma, beta, full, nimg, H, Ca, Cb, g):
+    with ops.quad_stats():
+        ops.conv3x3(x, w, out=buf[..., :Ca], qstats=True)
+        assert ops._qs_lookup(full) is None                                        # second slice not produced yet
+        right = buf[..., Ca:]
+        ops.linear(a, wl, residual=res, out=right.as_strided((nimg * H * H, Cb), (Ca + Cb, 1), right.storage_offset()), qstats=True)
+        assert ops._qs_lookup(full) is not None
+        got = ops.groupnorm(full, gamma, beta, silu=True)
+        torch.ops.xdb200.avgpool2x2(bf(torch.randn(nimg, 2 * H, 2 * H, Cb, generator=g)).to(DEV), right)    # foreign writer
+        assert ops._qs_lookup(full) is None and ops._qs_lookup(buf[..., :Ca].as_strided((nimg, H * H, Ca), (H * H * (Ca + Cb), Ca + Cb, 1))) is not None
+    with ops.quad_stats():                                                          # (buf was overwritten above: fresh pass)
+        ops.conv3x3(x, w, out=buf[..., :Ca], qstats=True)
+        ops.linear(a, wl, residual=res, out=right.as_strided((nimg * H * H, Cb), (Ca + Cb, 1), right.storage_offset()), qstats=True)
+        n0 = ops.LAUNCHES
+        got = ops.groupnorm(full, gamma, beta, silu=True)
+        assert ops.LAUNCHES - n0 == 1
+    ref = F.silu(F.group_norm(full.float().cpu().permute(0, 2, 1), 32, gamma.cpu(), beta.cpu(), 1e-5))
+    assert rel_l2(got.permute(0, 2, 1), ref) < 3e-3, rel_l2(got.permute(0, 2, 1), ref)
+
+
 def test_conv_in_out(ops):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(3, 1, 32, 32, generator=g)

@@ -64,6 +64,11 @@ struct TcParams {
     int ln_rows_per_mod;
     float ln_eps;
     long long* prof;    // XDB200_PROF=1: per-CTA cycle counters (16 slots per CTA), nullptr otherwise
+    // QS kernels: the epilogue also emits, per 32-row block and per group of 4 output columns ("quad"), the sum and the sum
+    // of squares of the values it stores: qstats[(m / 32) * qstats_ld + (n / 4) * 2 + {0, 1}].  The GroupNorm that consumes
+    // the output then needs no statistics pass of its own (norm.cu: gn_apply_quads_kernel).
+    float* qstats;
+    long long qstats_ld;
     int ksplit, kb_per_split, ws_rows;   // split-K: item = (tile, split); split s covers k-blocks [s * kb_per_split, ...) and
                                          // stores its fp32 partial tile at rows s * ws_rows + m of the workspace (out)
     int ng, tpg;        // work items: every m-tile is split into ng groups of tpg consecutive n-tiles
@@ -126,7 +131,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // 256 x BN tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one
 // M = 256 MMA that reads both CTAs' shared memory and writes both CTAs' TMEM -- half the shared-memory
 // and L2 operand traffic per FLOP, which is what bounds the 1-CTA kernel (see profiles/README.md).
-template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false>
+template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false, bool QS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmRes,
@@ -588,6 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     } else {
                         const uint32_t rowa = wb + lane * 64;
                         uint4 bq[8], rs[4];
+                        float qa[16];                            // QS: this row's 8 quad sums and 8 quad sums of squares
 #pragma unroll
                         for (int j = 0; j < 8; ++j) bq[j] = ptx::lds128(bias_a + (ci * 32 + 4 * j) * 4);
 #pragma unroll
@@ -617,9 +623,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 t = bf2_to_f2(rs[j].w); v[6] += t.x; v[7] += t.y;
                             }
                             rs[j] = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]), f2_to_bf2(v[6], v[7]));
+                            if constexpr (QS) {
+                                qa[2 * j] = (v[0] + v[1]) + (v[2] + v[3]);
+                                qa[2 * j + 1] = (v[4] + v[5]) + (v[6] + v[7]);
+                                qa[8 + 2 * j] = fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3]);
+                                qa[9 + 2 * j] = fmaf(v[4], v[4], v[5] * v[5]) + fmaf(v[6], v[6], v[7] * v[7]);
+                            }
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) ptx::sts128(rowa + ((j ^ ((lane >> 1) & 3)) << 4), rs[j]);
+                        if constexpr (QS) {
+                            // Sum the 16 per-row values over the warp's 32 rows with a transposing butterfly (16 + 8 + 4 + 2 + 1
+                            // = 31 shuffles; fixed order, no atomics): afterwards lane L holds value (L >> 1) & 15, i.e.
+                            // kind (sum / sum of squares) = L >> 4, quad = (L >> 1) & 7.
+#pragma unroll
+                            for (int w = 8; w >= 1; w >>= 1) {
+                                const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+                                for (int i = 0; i < w; ++i) {
+                                    const float send = up ? qa[i] : qa[i + w], keep = up ? qa[i + w] : qa[i];
+                                    qa[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+                                }
+                            }
+                            qa[0] += __shfl_xor_sync(0xffffffffu, qa[0], 1);
+                            const int quad = (lane >> 1) & 7;
+                            if (!(lane & 1) && m0 < p.M && nc + 4 * quad < p.N)
+                                p.qstats[(long long)(m0 >> 5) * p.qstats_ld + ((nc >> 2) + quad) * 2 + (lane >> 4)] = qa[0];
+                        }
                     }
                     if (prof) { const long long t = clock64(); seg[2] += t - tA; tA = t; }     // residual wait + math + STS
                     ptx::fence_proxy_async();
@@ -881,11 +911,11 @@ int setup_epilogue(TcParams* p, CUtensorMap* tres, CUtensorMap* tout) {
     return XD_OK;
 }
 
-template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false>
+template <int BN, int ACT, int CG, bool AS, int EPI, bool LNA = false, bool QS = false>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& tr,
            const CUtensorMap& to, const TcParams& p, cudaStream_t st) {
     static bool configured = false;
-    auto kernel = gemm_tc_kernel<BN, ACT, CG, AS, EPI, LNA>;
+    auto kernel = gemm_tc_kernel<BN, ACT, CG, AS, EPI, LNA, QS>;
     if (!configured) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, AS>::SMEM) != cudaSuccess) {
             xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute(max dynamic smem) failed");
@@ -1008,7 +1038,7 @@ void set_items(TcParams* p, const TileChoice& t) {
 }
 
 int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
-             cudaStream_t st) {
+             cudaStream_t st, int* qs_emitted = nullptr) {
     set_items(&p, t);
     // Split-K: long contractions over few tiles (the 8x8 / 4x4 UNet convs: 16-32 tiles, K = 2304-9216) are bound by
     // the per-CTA TMA -> MMA round trip (~370 ns per k-block), not by the tensor pipe: S CTAs share a tile's K range,
@@ -1057,6 +1087,18 @@ int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, 
         return XD_ERR_ARG;
     }
     const int epi = p.tma_epi ? (p.epi.out_dtype == XD_F32 ? EPI_TMA_F32 : EPI_TMA_BF16) : EPI_LEGACY;
+    // Quad statistics for the consuming GroupNorm: only from the unsplit bf16 TMA epilogue without activation (every
+    // conv3x3 / 1x1 projection that feeds a GroupNorm at the resolutions where the statistics pass matters); otherwise the
+    // caller is told that nothing was written and runs the stand-alone GroupNorm.
+    const bool qs = p.qstats && S == 1 && epi == EPI_TMA_BF16 && p.epi.act == XD_ACT_NONE && !t.as && t.bn >= 128 &&
+                    p.M % 32 == 0 && p.N % 4 == 0;
+    if (qs_emitted) *qs_emitted = qs ? 1 : 0;
+    if (!qs) p.qstats = nullptr;
+#define XD_TC_QS(BN_, CG_)                                                                                                 \
+    if (qs && t.bn == BN_ && t.cg == CG_)                                                                                  \
+        return launch<BN_, XD_ACT_NONE, CG_, false, EPI_TMA_BF16, false, true>(a0, a1, b, tr, to, p, st);
+    XD_TC_QS(128, 1) XD_TC_QS(192, 1) XD_TC_QS(256, 1) XD_TC_QS(128, 2) XD_TC_QS(192, 2) XD_TC_QS(256, 2)
+#undef XD_TC_QS
 #define XD_TC_ACT(BN_, CG_, AS_, EPI_)                                                                     \
     switch (p.epi.act) {                                                                                   \
         case XD_ACT_NONE: return finish(launch<BN_, XD_ACT_NONE, CG_, AS_, EPI_>(a0, a1, b, tr, to, p, st));       \
@@ -1090,11 +1132,11 @@ int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, 
 // ---------------------------------------------------------------------------------------------
 // C ABI (declared in include/xdb200.h)
 // ---------------------------------------------------------------------------------------------
-extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
-                               long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
-                               int gate_rows, long long gate_ld, const void* residual, int res_dtype,
-                               long long res_ld, void* out, int out_dtype, long long out_ld, int force_bn,
-                               void* stream) {
+static int gemm_impl(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                     long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                     int gate_rows, long long gate_ld, const void* residual, int res_dtype,
+                     long long res_ld, void* out, int out_dtype, long long out_ld, int force_bn,
+                     float* qstats, long long qstats_ld, int* qs_emitted, void* stream) {
     XD_CHECK_ARG(A && Wt && out && M > 0 && N > 0 && K > 0);
     XD_CHECK_ARG(K % BK == 0 && K2 % BK == 0 && (A2 != nullptr) == (K2 > 0));
     XD_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda2 % 8 == 0 && aligned16(A) && aligned16(Wt) && aligned16(A2));
@@ -1113,13 +1155,33 @@ extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, lon
     ta1 = ta0;
     if (A2 && (rc = tmap_rows(&ta1, A2, M, K2, lda2, BM))) return rc;
     if ((rc = tmap_weights(&tb, Wt, N, K + K2, ldw, t.bn / t.cg))) return rc;
-    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream);
+    p.qstats = qstats; p.qstats_ld = qstats_ld;
+    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream, qs_emitted);
 }
 
-extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
-                                  long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
-                                  const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
-                                  long long out_ld, int force_bn, void* stream) {
+extern "C" int xd_gemm_bf16_tc(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                               long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                               int gate_rows, long long gate_ld, const void* residual, int res_dtype,
+                               long long res_ld, void* out, int out_dtype, long long out_ld, int force_bn,
+                               void* stream) {
+    return gemm_impl(A, lda, A2, lda2, K2, Wt, ldw, M, N, K, bias, act, gate, gate_rows, gate_ld, residual, res_dtype, res_ld,
+                     out, out_dtype, out_ld, force_bn, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int xd_gemm_bf16_tc_qstats(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
+                                      long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,
+                                      int gate_rows, long long gate_ld, const void* residual, int res_dtype,
+                                      long long res_ld, void* out, int out_dtype, long long out_ld, int force_bn,
+                                      float* qstats, long long qstats_ld, int* emitted, void* stream) {
+    XD_CHECK_ARG(qstats && emitted && qstats_ld >= N / 4 * 2);
+    return gemm_impl(A, lda, A2, lda2, K2, Wt, ldw, M, N, K, bias, act, gate, gate_rows, gate_ld, residual, res_dtype, res_ld,
+                     out, out_dtype, out_ld, force_bn, qstats, qstats_ld, emitted, stream);
+}
+
+static int conv_impl(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                     long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                     const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                     long long out_ld, int force_bn, float* qstats, long long qstats_ld, int* qs_emitted, void* stream) {
     XD_CHECK_ARG(X && Wp && out && nimg > 0 && H > 0 && W > 0 && Cout > 0);
     XD_CHECK_ARG(C % BK == 0 && Cs % BK == 0 && (Xs != nullptr) == (Cs > 0));
     XD_CHECK_ARG(ldx % 8 == 0 && lds % 8 == 0 && aligned16(X) && aligned16(Xs) && aligned16(Wp));
@@ -1141,7 +1203,26 @@ extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H,
     if (Xs && (rc = tmap_nhwc(&ta1, Xs, nimg, H, W, Cs, lds))) return rc;
     const long long ktot = 9LL * C + Cs;
     if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, t.bn / t.cg))) return rc;
-    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream);
+    p.qstats = qstats; p.qstats_ld = qstats_ld;
+    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream, qs_emitted);
+}
+
+extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                                  long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                                  const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                                  long long out_ld, int force_bn, void* stream) {
+    return conv_impl(X, ldx, nimg, H, W, C, Xs, lds, Cs, Wp, Cout, bias, act, residual, res_dtype, res_ld, out, out_dtype,
+                     out_ld, force_bn, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int xd_conv3x3_bf16_tc_qstats(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
+                                         long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
+                                         const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
+                                         long long out_ld, int force_bn, float* qstats, long long qstats_ld, int* emitted,
+                                         void* stream) {
+    XD_CHECK_ARG(qstats && emitted && qstats_ld >= Cout / 4 * 2);
+    return conv_impl(X, ldx, nimg, H, W, C, Xs, lds, Cs, Wp, Cout, bias, act, residual, res_dtype, res_ld, out, out_dtype,
+                     out_ld, force_bn, qstats, qstats_ld, emitted, stream);
 }
 
 // LayerNorm(no affine) + modulate fused into the A operand of the GEMM:

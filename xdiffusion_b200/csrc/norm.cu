@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -325,6 +326,92 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 }
 
 // ----------------------------------------------------------------------------- LayerNorm + modulate
+// GroupNorm whose statistics come from the PRODUCER: the contraction that wrote x also emitted, per block of 32 rows and per
+// quad of 4 channels, the sum and the sum of squares of what it stored (gemm_tc.cu, QS kernels).  What is left is one
+// streaming pass: fold the sample's P / 32 partial rows in a fixed order (two stages: NPART contiguous ranges, then the
+// ranges), group them, and apply y = x * A[c] + B[c] (+ SiLU) with the coefficients of the thread's 8 channels in registers.
+// blockDim.x = the largest multiple of V = C / 8 that is <= 256, so a thread always works on the same vector column.
+__global__ void __launch_bounds__(256)
+gn_apply_quads_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, const float* __restrict__ qstats,
+                      long long qld, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ ss, long long ss_ld, int ss_div, float eps, int silu,
+                      bf16* __restrict__ out, long long ldo) {
+    pdl_prologue();
+    extern __shared__ float sm[];               // [2][C] coefficients | [2][nq] quad sums | [NPARTS][2][nq] partial ranges
+    const int nq = C >> 2, nb = P >> 5;
+    float* coef = sm;
+    float* qsum = sm + 2 * C;
+    float* part = qsum + 2 * nq;
+    const int sample = blockIdx.y;
+    const int nparts = min(max((int)blockDim.x / nq, 1), nb);
+    const int per = (nb + nparts - 1) / nparts;
+    for (int u = threadIdx.x; u < nparts * nq; u += blockDim.x) {
+        const int pt = u / nq, q = u - pt * nq;
+        const int b0 = pt * per, b1 = min(nb, b0 + per);
+        const float2* src = reinterpret_cast<const float2*>(qstats + ((long long)sample * nb + b0) * qld) + q;
+        float s = 0.f, sq = 0.f;
+        for (int b = b0; b < b1; ++b, src += qld / 2) {
+            const float2 v = __ldg(src);
+            s += v.x; sq += v.y;
+        }
+        part[(pt * 2) * nq + q] = s;
+        part[(pt * 2 + 1) * nq + q] = sq;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        float s = 0.f, sq = 0.f;
+        for (int pt = 0; pt < nparts; ++pt) { s += part[(pt * 2) * nq + q]; sq += part[(pt * 2 + 1) * nq + q]; }
+        qsum[q] = s; qsum[nq + q] = sq;
+    }
+    __syncthreads();
+    const int cpg = C / G, qpg = cpg >> 2;
+    const float inv_cnt = 1.0f / ((float)P * (float)cpg);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float sum = 0.f, sq = 0.f;
+        for (int q = g * qpg; q < (g + 1) * qpg; ++q) { sum += qsum[q]; sq += qsum[nq + q]; }
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        float a = rstd * gamma[c], b = beta[c] - mean * rstd * gamma[c];
+        if (ss) {
+            const float* row = ss + (long long)(sample / ss_div) * ss_ld;
+            const float sc = 1.0f + row[c], sh = row[C + c];
+            a *= sc; b = b * sc + sh;
+        }
+        coef[c] = a; coef[C + c] = b;
+    }
+    __syncthreads();
+    const int V = C >> 3;
+    const int j = threadIdx.x % V, r0 = threadIdx.x / V, rstep = blockDim.x / V;
+    float ca[8], cb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ca[k] = coef[j * 8 + k]; cb[k] = coef[C + j * 8 + k]; }
+    const int slabs = gridDim.x;
+    const int rows = (P + slabs - 1) / slabs;
+    const int p0 = blockIdx.x * rows, p1 = min(P, p0 + rows);
+    const bf16* xb = x + ((long long)sample * P) * ld + j * 8;
+    bf16* ob = out + ((long long)sample * P) * ldo + j * 8;
+    for (int r = p0 + r0; r < p1; r += 4 * rstep) {          // four rows in flight per thread
+        bf16x8 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r + i * rstep < p1) v[i] = *reinterpret_cast<const bf16x8*>(xb + (long long)(r + i * rstep) * ld);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r + i * rstep >= p1) break;
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float y = fmaf(f[k], ca[k], cb[k]);
+                f[k] = silu ? silu_fast(y) : y;
+            }
+            *reinterpret_cast<bf16x8*>(ob + (long long)(r + i * rstep) * ldo) = pack8(f);
+        }
+    }
+}
+
 template <int NV>   // D = NV * 128
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, long long ld, int M, const float* __restrict__ shift,
@@ -400,6 +487,27 @@ extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int
     xd_launch(gn_apply_kernel, dim3(slabs, nsamples), 256, 2 * C * sizeof(float), (cudaStream_t)stream, 
         (const bf16*)x, ld, P, C, groups, stats, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu,
         inner, xd_groupnorm_slabs(nsamples, P, C), split, (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+// GroupNorm from the quad statistics of the producing contraction (xd_conv3x3_bf16_tc_qstats / xd_gemm_bf16_tc_qstats):
+// qstats[(row / 32) * qstats_ld + (c / 4) * 2 + {0, 1}] for the rows / channels of x; sample s = rows [s * P, (s + 1) * P).
+extern "C" int xd_groupnorm_apply_quads(const void* x, long long ld, int nsamples, int P, int C, int groups,
+                                        const float* qstats, long long qstats_ld, const float* gamma, const float* beta,
+                                        const float* scale_shift, long long ss_ld, int ss_div, float eps, int silu,
+                                        void* out, long long ldo, void* stream) {
+    XD_CHECK_ARG(x && qstats && gamma && beta && out && nsamples > 0 && P > 0 && P % 32 == 0 && ld % 8 == 0 && ldo % 8 == 0);
+    XD_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0 && qstats_ld % 2 == 0);
+    const int V = C / 8, nq = C / 4, nb = P / 32;
+    const int threads = 256 / V * V;
+    const int nparts = std::min(std::max(threads / nq, 1), nb);
+    const size_t smem = (2 * (size_t)C + 2 * nq + 2 * (size_t)nparts * nq) * sizeof(float);
+    XD_CHECK_ARG(smem <= 48 * 1024);
+    int slabs = (4 * 148 + nsamples - 1) / nsamples;
+    slabs = std::max(1, std::min(slabs, P / 32));
+    xd_launch(gn_apply_quads_kernel, dim3(slabs, nsamples), threads, smem, (cudaStream_t)stream, (const bf16*)x, ld, P, C,
+              groups, qstats, qstats_ld, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

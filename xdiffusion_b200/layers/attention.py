@@ -240,7 +240,7 @@ class SpatialCrossAttention(ContextBlock, Packed):
             out = torch.empty((nimg, H, W, C), device=x.device, dtype=torch.bfloat16)
         x2 = x.as_strided((nimg * T, C), (x.stride(2), 1))
         o2 = out.as_strided((nimg * T, C), (out.stride(2), 1))
-        ops.linear(a2, wp, self._proj_out.bias, residual=x2, out=o2)
+        ops.linear(a2, wp, self._proj_out.bias, residual=x2, out=o2, qstats=True)
         return out
 
 
@@ -317,5 +317,5 @@ class TemporalSelfAttention(ContextBlock, Packed):
         if out is None:
             out = torch.empty((nimg, H, W, C), device=x.device, dtype=torch.bfloat16)
         o2 = out.as_strided((nimg * HW, C), (out.stride(2), 1))
-        ops.linear(a, wp, self._proj_out.bias, residual=rows, out=o2)
+        ops.linear(a, wp, self._proj_out.bias, residual=rows, out=o2, qstats=True)
         return out

@@ -130,9 +130,10 @@ class UNetBlock(torch.nn.Module, Packed):
         """x bf16 NHWC view [n, H, W, Cin]; emb_bias fp32 [Cout] = conv0.bias + affine(emb) (one row for the batch)."""
         pk = self._packs()
         h = ops.groupnorm(_as_samples(x, samples), self.norm0.weight, self.norm0.bias, eps=self.norm0.eps, silu=True).view(x.shape)
-        h = ops.conv3x3(_resample(h, self.up, self.down), pk["w0"], emb_bias)
+        h = ops.conv3x3(_resample(h, self.up, self.down), pk["w0"], emb_bias, qstats=True)
         h = ops.groupnorm(_as_samples(h, samples), self.norm1.weight, self.norm1.bias, eps=self.norm1.eps, silu=True).view(h.shape)
-        y = ops.conv3x3(h, pk["w1"], pk["b1"], xs=_resample(x, self.up, self.down), out=None if self.num_heads else out)
+        y = ops.conv3x3(h, pk["w1"], pk["b1"], xs=_resample(x, self.up, self.down), out=None if self.num_heads else out,
+                        qstats=True)
         if not self.num_heads:
             return y
         n, H, W, C = y.shape
@@ -143,6 +144,6 @@ class UNetBlock(torch.nn.Module, Packed):
         a = ops.attention(q, k, v, 1 / math.sqrt(C))                               # [n, 1, T, C] view of [n, T, 1, C]
         if out is None:
             out = torch.empty_like(y)
-        ops.linear(a.permute(0, 2, 1, 3).reshape(n * H * W, C), pk["wproj"], pk["bproj"], a2=_rows(y), out=_rows(out))
+        ops.linear(a.permute(0, 2, 1, 3).reshape(n * H * W, C), pk["wproj"], pk["bproj"], a2=_rows(y), out=_rows(out), qstats=True)
         return out
 

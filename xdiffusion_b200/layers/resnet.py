@@ -63,12 +63,12 @@ class ResnetBlockBigGAN(ContextBlock, Packed):
             (c2.bias + skip.bias).detach().float() if has_skip else None))
         g1, g2 = self.in_layers[0], self.out_layers[0]
         h = ops.groupnorm(_as_samples(x, samples), g1.weight, g1.bias, eps=g1.eps, silu=True).view(x.shape)
-        h = ops.conv3x3(h, w1, c1.bias)
+        h = ops.conv3x3(h, w1, c1.bias, qstats=True)
         h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps,
                           silu=True).view(h.shape)
         if has_skip:
-            return ops.conv3x3(h, w2, b2, xs=x, out=out)
-        return ops.conv3x3(h, w2, c2.bias, residual=x, out=out)
+            return ops.conv3x3(h, w2, b2, xs=x, out=out, qstats=True)
+        return ops.conv3x3(h, w2, c2.bias, residual=x, out=out, qstats=True)
 
 
 class Downsample(torch.nn.Module):
@@ -134,9 +134,9 @@ class ResnetBlockEfficient(ContextBlock, Packed):
         w1, w2, b2 = self.packed("w", (c1.weight, c2.weight, c2.bias, skip.weight, skip.bias), lambda: (
             pack_conv3x3(c1.weight), pack_conv3x3(c2.weight * s, skip.weight * s), ((c2.bias + skip.bias) * s).detach().float()))
         h = ops.groupnorm(_as_samples(x, samples), g1.weight, g1.bias, eps=g1.eps, silu=True).view(x.shape)
-        h = ops.conv3x3(h, w1, c1.bias)
+        h = ops.conv3x3(h, w1, c1.bias, qstats=True)
         h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, eps=g2.eps, silu=True).view(h.shape)
-        return ops.conv3x3(h, w2, b2, xs=x, out=out)
+        return ops.conv3x3(h, w2, b2, xs=x, out=out, qstats=True)
 
 
 class _EfficientStage(ContextBlock, Packed):

@@ -6,6 +6,7 @@ one with CPU tensors raises (there is no CPU or eager-PyTorch fallback).  The fu
 at the bottom allocate outputs with torch's caching allocator, which keeps the whole forward
 capturable in a CUDA graph.
 """
+import ctypes
 import os
 
 import torch
@@ -86,15 +87,136 @@ _defs = []
 _SKIP = set(filter(None, os.environ.get("XDB200_SKIP", "").split(",")))
 
 
+# ------------------------------------------------------------------------------------ GroupNorm statistics from the producer
+# Inside ``with quad_stats():`` (one network forward) the conv3x3 / linear helpers ask the tensor-core kernels to emit, next
+# to their bf16 output, the per-(32 rows, 4 channels) sums the GroupNorm that consumes the output needs
+# (xd_*_bf16_tc_qstats); ``groupnorm`` then runs the one-pass xd_groupnorm_apply_quads when every channel of its input is
+# covered.  The book is keyed by the output's storage (a concat buffer collects the slices of several producers) and keeps
+# that storage alive for the duration of the forward, so an address is never re-used under a stale entry; any other op of
+# this module that writes into a registered storage drops the entry (``_op`` below).
+QUAD_STATS = os.environ.get("XDB200_GN_QSTATS", "1") == "1"
+_qs_book = None
+
+
+class quad_stats:
+    def __enter__(self):
+        global _qs_book
+        self._prev, _qs_book = _qs_book, ({} if QUAD_STATS and MATMUL_BACKEND == "tc" else None)
+        return self
+
+    def __exit__(self, *exc):
+        global _qs_book
+        _qs_book = self._prev
+
+
+def _qs_geometry(t):
+    """(rows, ld, c0, C) of a bf16 [.., C] view whose rows are uniformly strided and start in row 0 of its storage."""
+    if t.dim() == 4:
+        n, H, W, C = t.shape
+        if not (t.stride(3) == 1 and t.stride(1) == W * t.stride(2) and t.stride(0) == H * t.stride(1)):
+            return None
+        rows, ld = n * H * W, t.stride(2)
+    elif t.dim() == 3:
+        n, P, C = t.shape
+        if not (t.stride(2) == 1 and t.stride(0) == P * t.stride(1)):
+            return None
+        rows, ld = n * P, t.stride(1)
+    elif t.dim() == 2:
+        rows, C = t.shape
+        if t.stride(1) != 1:
+            return None
+        ld = t.stride(0)
+    else:
+        return None
+    c0 = t.storage_offset()
+    if t.dtype != torch.bfloat16 or c0 + C > ld or rows % 32 or ld % 4 or c0 % 4 or C % 4:
+        return None
+    return rows, ld, c0, C
+
+
+def _qs_slot(out):
+    """The quad-statistics view for ``out`` (allocating the storage's table on first use), or None."""
+    if _qs_book is None:
+        return None
+    g = _qs_geometry(out)
+    if g is None:
+        return None
+    rows, ld, c0, C = g
+    key = out.untyped_storage().data_ptr()
+    e = _qs_book.get(key)
+    if e is None or e["rows"] != rows or e["ld"] != ld:
+        e = {"rows": rows, "ld": ld, "cover": [], "keep": out,
+             "table": torch.empty((rows // 32, ld // 4, 2), device=out.device, dtype=torch.float32)}
+        _qs_book[key] = e
+    return e, e["table"][:, c0 // 4:(c0 + C) // 4], (c0, c0 + C)
+
+
+def _qs_written(t, emitted_range=None):
+    """``t`` was (re)written: forget the statistics of the channels it covers, then record the new ones if emitted."""
+    if _qs_book is None or t is None:
+        return
+    e = _qs_book.get(t.untyped_storage().data_ptr())
+    if e is None:
+        return
+    g = _qs_geometry(t)
+    if g is None or g[0] != e["rows"] or g[1] != e["ld"]:
+        e["cover"] = []
+    else:
+        lo, hi = g[2], g[2] + g[3]
+        e["cover"] = [(a, b) for a, b in e["cover"] if b <= lo or a >= hi]
+    if emitted_range is not None:
+        e["cover"].append(emitted_range)
+
+
+def _qs_lookup(x):
+    """Quad-statistics view covering every channel of the GroupNorm input ``x`` [ns, P, C], or None."""
+    if _qs_book is None:
+        return None
+    e = _qs_book.get(x.untyped_storage().data_ptr())
+    g = _qs_geometry(x)
+    if e is None or g is None or g[0] != e["rows"] or g[1] != e["ld"]:
+        return None
+    lo, hi = g[2], g[2] + g[3]
+    pos = lo
+    for a, b in sorted(e["cover"]):
+        if a <= pos < b:
+            pos = b
+    if pos < hi:
+        return None
+    return e["table"][:, lo // 4:hi // 4]
+
+
 def _op(schema):
     def deco(fn):
         name = schema.split("(", 1)[0]
+        args = schema.split("(", 1)[1].rsplit(")", 1)[0]
+        mutated = [i for i, a in enumerate(_split_args(args)) if "!" in a]
+
+        def run(*a):
+            r = fn(*a)
+            if _qs_book is not None and not name.endswith("_qs"):
+                for i in mutated:
+                    _qs_written(a[i])
+            return r
         if name in _SKIP:
             _defs.append((schema, lambda *a, **k: None))
         else:
-            _defs.append((schema, fn))
+            _defs.append((schema, run))
         return fn
     return deco
+
+
+def _split_args(args):
+    out, depth, cur = [], 0, ""
+    for ch in args:
+        depth += ch == "("
+        depth -= ch == ")"
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    return out + [cur]
 
 
 # ------------------------------------------------------------------------------------ contractions
@@ -192,6 +314,69 @@ def _conv3x3(x, xs, wp, bias, act, residual, out, force_bn):
         _lib.check(_lib.lib().xd_conv3x3_bf16_tc(*args, force_bn, _stream()), "xd_conv3x3_bf16_tc")
     else:
         _lib.check(_lib.lib().xd_conv3x3_bf16_simt(*args, _stream()), "xd_conv3x3_bf16_simt")
+    _count()
+
+
+@_op("gemm_qs(Tensor a, Tensor? a2, Tensor w, Tensor? bias, int act, Tensor? gate, int gate_rows, "
+     "Tensor? residual, Tensor(a!) out, int force_bn, Tensor(b!) qstats) -> int")
+def _gemm_qs(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn, qstats):
+    """gemm + quad statistics of ``out`` (see quad_stats above); returns 1 when the statistics were written."""
+    _cuda(a, a2, w, bias, gate, residual, out, qstats)
+    _ensure_workspace(a)
+    M, K = a.shape
+    K2 = 0 if a2 is None else a2.shape[1]
+    N = w.shape[0]
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K + K2 and K % 64 == 0 and K2 % 64 == 0
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1 and out.shape == (M, N)
+    assert qstats.dtype == torch.float32 and qstats.shape == (M // 32, N // 4, 2) and qstats.stride(2) == 1 and qstats.stride(1) == 2
+    emitted = ctypes.c_int(0)
+    _lib.check(_lib.lib().xd_gemm_bf16_tc_qstats(
+        _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K2, _p(w), w.stride(0), M, N, K,
+        _p(bias), act, _p(gate), gate_rows, 0 if gate is None else gate.stride(0), _p(residual),
+        0 if residual is None else _dt(residual), 0 if residual is None else residual.stride(0),
+        _p(out), _dt(out), out.stride(0), force_bn, _p(qstats), qstats.stride(0), ctypes.addressof(emitted), _stream()),
+        "xd_gemm_bf16_tc_qstats")
+    _count()
+    return emitted.value
+
+
+@_op("conv3x3_qs(Tensor x, Tensor? xs, Tensor wp, Tensor? bias, int act, Tensor? residual, Tensor(a!) out, "
+     "int force_bn, Tensor(b!) qstats) -> int")
+def _conv3x3_qs(x, xs, wp, bias, act, residual, out, force_bn, qstats):
+    _cuda(x, xs, wp, bias, residual, out, qstats)
+    _ensure_workspace(x)
+    nimg, H, W, C = x.shape
+    Cs = 0 if xs is None else xs.shape[3]
+    Cout = wp.shape[0]
+    assert wp.shape[1] == 9 * C + Cs and wp.is_contiguous()
+    for t in (x, xs, out, residual):
+        if t is not None:
+            assert t.stride(3) == 1 and t.stride(1) == W * t.stride(2) and t.stride(0) == H * t.stride(1)
+    assert qstats.dtype == torch.float32 and qstats.shape == (nimg * H * W // 32, Cout // 4, 2)
+    assert qstats.stride(2) == 1 and qstats.stride(1) == 2
+    emitted = ctypes.c_int(0)
+    _lib.check(_lib.lib().xd_conv3x3_bf16_tc_qstats(
+        _p(x), x.stride(2), nimg, H, W, C, _p(xs), 0 if xs is None else xs.stride(2), Cs, _p(wp), Cout,
+        _p(bias), act, _p(residual), 0 if residual is None else _dt(residual),
+        0 if residual is None else residual.stride(2), _p(out), _dt(out), out.stride(2), force_bn,
+        _p(qstats), qstats.stride(0), ctypes.addressof(emitted), _stream()), "xd_conv3x3_bf16_tc_qstats")
+    _count()
+    return emitted.value
+
+
+@_op("groupnorm_quads(Tensor x, Tensor qstats, Tensor gamma, Tensor beta, Tensor? scale_shift, int ss_div, float eps, "
+     "int silu, int nsamples, Tensor(a!) out) -> ()")
+def _groupnorm_quads(x, qstats, gamma, beta, scale_shift, ss_div, eps, silu, nsamples, out):
+    """x [rows, C] bf16 view of nsamples samples of P consecutive rows; qstats [rows / 32, C / 4, 2] from the producers."""
+    _cuda(x, qstats, gamma, beta, scale_shift, out)
+    rows, C = x.shape
+    P = rows // nsamples
+    assert x.stride(1) == 1 and out.stride(1) == 1 and nsamples * P == rows and qstats.shape == (rows // 32, C // 4, 2)
+    assert qstats.stride(2) == 1 and qstats.stride(1) == 2
+    _lib.check(_lib.lib().xd_groupnorm_apply_quads(
+        _p(x), x.stride(0), nsamples, P, C, 32, _p(qstats), qstats.stride(0), _p(gamma), _p(beta), _p(scale_shift),
+        0 if scale_shift is None else scale_shift.stride(0), ss_div, eps, silu, _p(out), out.stride(0), _stream()),
+        "xd_groupnorm_apply_quads")
     _count()
 
 
@@ -507,10 +692,15 @@ _ops = torch.ops.xdb200
 
 # ------------------------------------------------------------------------------------ functional helpers
 def linear(a, w, bias=None, act=ACT_NONE, out_dtype=torch.bfloat16, gate=None, gate_rows=1, residual=None,
-           out=None, a2=None, force_bn=0):
-    """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K(+K2)]."""
+           out=None, a2=None, force_bn=0, qstats=False):
+    """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K(+K2)].  ``qstats``: a GroupNorm consumes ``out`` (quad_stats)."""
     if out is None:
         out = torch.empty((a.shape[0], w.shape[0]), device=a.device, dtype=out_dtype)
+    slot = _qs_slot(out) if qstats and act == ACT_NONE and a.shape[1] % 64 == 0 and (a2 is None or a2.shape[1] % 64 == 0) else None
+    if slot is not None:
+        emitted = _ops.gemm_qs(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn, slot[1])
+        _qs_written(out, slot[2] if emitted else None)
+        return out
     _ops.gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn)
     return out
 
@@ -535,9 +725,14 @@ def ln_linear(x, shift, scale, rows_per_mod, w, bias=None, act=ACT_NONE, eps=1e-
     return linear(a, w, bias, act=act, out=out)
 
 
-def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, force_bn=0):
+def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, force_bn=0, qstats=False):
     if out is None:
         out = torch.empty(x.shape[:3] + (wp.shape[0],), device=x.device, dtype=torch.bfloat16)
+    slot = _qs_slot(out) if qstats and act == ACT_NONE else None
+    if slot is not None:
+        emitted = _ops.conv3x3_qs(x, xs, wp, bias, act, residual, out, force_bn, slot[1])
+        _qs_written(out, slot[2] if emitted else None)
+        return out
     _ops.conv3x3(x, xs, wp, bias, act, residual, out, force_bn)
     return out
 
@@ -552,6 +747,10 @@ def groupnorm(x, gamma, beta, scale_shift=None, ss_div=1, eps=1e-5, silu=False, 
     assert out.stride(2) == 1 and out.stride(0) == P * out.stride(1)
     x2 = x.as_strided((ns * P, C), (x.stride(1), 1))
     o2 = out.as_strided((ns * P, C), (out.stride(1), 1))
+    q = _qs_lookup(x) if inner == 1 and C % 128 == 0 and P % 32 == 0 else None
+    if q is not None:                      # statistics came with the input: one streaming pass
+        _ops.groupnorm_quads(x2, q, gamma, beta, scale_shift, ss_div, eps, int(silu), ns, o2)
+        return out
     stats = torch.empty(ns * 64 * _lib.lib().xd_groupnorm_slabs(ns, P, C), device=x.device, dtype=torch.float32)
     _ops.groupnorm(x2, gamma, beta, scale_shift, ss_div, eps, int(silu), inner, ns, 0, stats, o2)
     return out

@@ -148,6 +148,10 @@ class SongUNet(torch.nn.Module, Packed):
         return lambda b: row[offs[id(b)][0]: offs[id(b)][0] + offs[id(b)][1]]
 
     def forward(self, x, noise_labels, class_labels=None, augment_labels=None):
+        with ops.quad_stats():
+            return self._forward(x, noise_labels)
+
+    def _forward(self, x, noise_labels):
         if noise_labels.numel() != 1:
             raise NotImplementedError("one noise level per batch (the sampling path); got %d" % noise_labels.numel())
         B, _, H, W = x.shape

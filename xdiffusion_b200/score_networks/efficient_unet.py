@@ -89,6 +89,10 @@ class Unet(torch.nn.Module, Packed):
         return self.packed("emb_all", tuple(w for w, _ in lins) + tuple(b for _, b in lins), build)
 
     def forward(self, x, context: Dict):
+        with ops.quad_stats():
+            return self._forward(x, context)
+
+    def _forward(self, x, context: Dict):
         context = context.copy()
         for ct in self._context_transformers:
             context = ct(context, device=x.device)

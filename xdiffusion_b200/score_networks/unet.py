@@ -165,6 +165,10 @@ class Unet(torch.nn.Module, Packed):
         return h
 
     def forward(self, x, context: Dict):
+        with ops.quad_stats():                         # GroupNorm statistics ride along with the producing convs (ops.py)
+            return self._forward(x, context)
+
+    def _forward(self, x, context: Dict):
         context = context.copy()
         context["x"] = x
         for ct in self._context_transformers:
