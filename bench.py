@@ -289,10 +289,10 @@ def conv_roofline(model, batch, device):
     from xdiffusion_b200 import ops
     seen, real = {}, ops.conv3x3
 
-    def spy(x, wp, bias=None, act=ops.ACT_NONE, residual=None, xs=None, out=None, force_bn=0):
-        key = (tuple(x.shape), 0 if xs is None else xs.shape[3], wp.shape[0], residual is not None)
+    def spy(x, wp, bias=None, act=ops.ACT_NONE, residual=None, xs=None, out=None, force_bn=0, qstats=False):
+        key = (tuple(x.shape), 0 if xs is None else xs.shape[3], wp.shape[0], residual is not None, bool(qstats))
         seen[key] = seen.get(key, 0) + 1
-        return real(x, wp, bias, act=act, residual=residual, xs=xs, out=out, force_bn=force_bn)
+        return real(x, wp, bias, act=act, residual=residual, xs=xs, out=out, force_bn=force_bn, qstats=qstats)
 
     ops.conv3x3 = spy
     try:
@@ -301,7 +301,7 @@ def conv_roofline(model, batch, device):
     finally:
         ops.conv3x3 = real
     tot_flop, tot_ms, per = 0.0, 0.0, {}
-    for (shape, cs, cout, has_res), count in sorted(seen.items()):
+    for (shape, cs, cout, has_res, qs), count in sorted(seen.items()):
         nimg, H, W, C = shape
         K = 9 * C + cs
         xin = torch.randn(shape, device=device).bfloat16()
@@ -310,7 +310,8 @@ def conv_roofline(model, batch, device):
         bias = torch.randn(cout, device=device)
         res = torch.randn(nimg, H, W, cout, device=device).bfloat16() if has_res else None
         out = torch.empty(nimg, H, W, cout, device=device, dtype=torch.bfloat16)
-        t = _time_in_graph(lambda: real(xin, wp, bias, residual=res, xs=xs, out=out))
+        with ops.quad_stats():          # as the network launches it: GroupNorm statistics emitted by the epilogue (ops.py)
+            t = _time_in_graph(lambda: real(xin, wp, bias, residual=res, xs=xs, out=out, qstats=qs))
         flop = 2.0 * nimg * H * W * cout * K
         per[f"{H}x{W} {C}{'+' + str(cs) if cs else ''}->{cout}{' +res' if has_res else ''}"] = {
             "count": count, "us": round(t * 1e3, 2), "tflops": round(flop / t / 1e9, 1)}

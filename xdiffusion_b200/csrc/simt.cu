@@ -182,6 +182,106 @@ conv3x3_out_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, i
     }
 }
 
+// ---- the shapes the score networks actually use: one image channel in / out.  The thread's 8 output (input) channels are
+// fixed for the whole kernel, so its 72 weights live in registers instead of 18 shared-memory loads per pixel; a CTA walks
+// a band of image rows (32-bit index arithmetic; the 3 x 3 neighbourhood of a band stays in L1).
+__global__ void __launch_bounds__(256)
+conv3x3_in1_kernel(const float* __restrict__ x, int nimg, int H, int W, const float* __restrict__ w /*[Cout][1][3][3]*/,
+                   const float* __restrict__ bias, int Cout, bf16* __restrict__ out, long long ldo, int band) {
+    pdl_prologue();
+    const int cg = Cout >> 3;                                // threads per pixel
+    const int g = threadIdx.x % cg, slot = threadIdx.x / cg, slots = blockDim.x / cg;
+    float wr[9][8], br[8];
+    {
+        float flat[72];                                      // w[(g * 8 + j) * 9 + tap]: 72 consecutive floats, 18 x 16 bytes
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(w + g * 72) + i);
+            flat[4 * i] = t.x; flat[4 * i + 1] = t.y; flat[4 * i + 2] = t.z; flat[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            br[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) wr[tap][j] = flat[j * 9 + tap];
+        }
+    }
+    const int bands = (H + band - 1) / band;
+    const int img = blockIdx.x / bands, y0 = (blockIdx.x - img * bands) * band, y1 = min(H, y0 + band);
+    const float* xp = x + (long long)img * H * W;
+    bf16* op = out + (long long)img * H * W * ldo + g * 8;
+    for (int pix = y0 * W + slot; pix < y1 * W; pix += slots) {
+        const int hh = pix / W, ww = pix - hh * W;
+        float xv[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+            const bool ok = y >= 0 && y < H && xx >= 0 && xx < W;
+            const float t = __ldg(xp + min(max(y, 0), H - 1) * W + min(max(xx, 0), W - 1));
+            xv[tap] = ok ? t : 0.f;
+        }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[tap], wr[tap][j], acc[j]);
+        *reinterpret_cast<bf16x8*>(op + (long long)pix * ldo) = pack8(acc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+conv3x3_out1_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
+                    const float* __restrict__ w /*[1][C][3][3]*/, const float* __restrict__ bias, float* __restrict__ out,
+                    int band) {
+    pdl_prologue();
+    const int lpp = C >> 3;                                  // lanes per pixel (a power of two <= 32)
+    const int g = threadIdx.x % lpp, slot = threadIdx.x / lpp, slots = blockDim.x / lpp;
+    float wr[9][8];
+    {
+        float flat[72];                                      // w[(g * 8 + j) * 9 + tap]: 72 consecutive floats, 18 x 16 bytes
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(w + g * 72) + i);
+            flat[4 * i] = t.x; flat[4 * i + 1] = t.y; flat[4 * i + 2] = t.z; flat[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[tap][j] = flat[j * 9 + tap];
+    }
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    const int bands = (H + band - 1) / band;
+    const int img = blockIdx.x / bands, y0 = (blockIdx.x - img * bands) * band, y1 = min(H, y0 + band);
+    const bf16* xp = X + (long long)img * H * W * ldx + g * 8;
+    float* op = out + (long long)img * H * W;
+    const int n = (y1 - y0) * W;
+    for (int i = slot; i < (n + slots - 1) / slots * slots; i += slots) {      // whole warps stay in the loop together
+        const bool live = i < n;
+        const int pix = y0 * W + (live ? i : n - 1);
+        const int hh = pix / W, ww = pix - hh * W;
+        bf16x8 xt[9];                                        // all nine taps in flight (clamped address, masked value)
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = min(max(hh + tap / 3 - 1, 0), H - 1), xx = min(max(ww + tap % 3 - 1, 0), W - 1);
+            xt[tap] = *reinterpret_cast<const bf16x8*>(xp + (long long)(y * W + xx) * ldx);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+            if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
+            float f[8];
+            unpack8(xt[tap], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wr[tap][j], acc);
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0 && live) op[pix] = acc + b0;
+    }
+}
+
 }  // namespace
 
 extern "C" int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
@@ -214,6 +314,14 @@ extern "C" int xd_conv3x3_bf16_simt(const void* X, long long ldx, int nimg, int 
 extern "C" int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, int W, const float* w,
                                       const float* bias, int Cout, void* out, long long ldo, void* stream) {
     XD_CHECK_ARG(x && w && out && Cout % 8 == 0 && ldo % 8 == 0);
+    if (Cin == 1 && 256 % (Cout / 8) == 0 && (long long)H * W < (1LL << 30) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {       // register-weight kernel, one band of rows per CTA
+        int band = H;
+        while (band > 1 && (long long)nimg * ((H + band - 1) / band) < 2 * 148) band = (band + 1) / 2;
+        const unsigned grid = (unsigned)(nimg * ((H + band - 1) / band));
+        xd_launch(conv3x3_in1_kernel, grid, 256, 0, (cudaStream_t)stream, x, nimg, H, W, w, bias, Cout, (bf16*)out, ldo, band);
+        XD_CHECK_LAUNCH();
+        return XD_OK;
+    }
     const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
     XD_CHECK_ARG(smem <= 48 * 1024);
     const long long total = (long long)nimg * H * W * (Cout / 8);
@@ -228,6 +336,14 @@ extern "C" int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, i
     XD_CHECK_ARG(X && w && out && C % 8 == 0 && ldx % 8 == 0);
     const int lpp = C / 8;
     XD_CHECK_ARG(lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0);
+    if (Cout == 1 && (long long)H * W * ldx < (1LL << 31) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {                          // register-weight kernel, one band of rows per CTA
+        int band = H;
+        while (band > 2 && (long long)nimg * ((H + band - 1) / band) < 2 * 148) band = (band + 1) / 2;
+        const unsigned grid = (unsigned)(nimg * ((H + band - 1) / band));
+        xd_launch(conv3x3_out1_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)X, ldx, nimg, H, W, C, w, bias, out, band);
+        XD_CHECK_LAUNCH();
+        return XD_OK;
+    }
     const size_t smem = (size_t)Cout * 9 * C * sizeof(float);
     XD_CHECK_ARG(smem <= 48 * 1024);
     const long long threads = (long long)nimg * H * W * lpp;
