@@ -96,6 +96,27 @@ o64 = torch.randn_like(x64)
 targets.append(("sampler step (clamp)", lambda: torch.ops.xdb200.sampler_step(
     0, 0, 0, x64, o64, None, 0, x64, coefs, None, 500, 0, 0, 0.0, 0.0, 3, None, 0)))
 
+# ---- second half of round 2 ("r2b ..."): GroupNorm statistics from the producer, first / last conv, wide attention ------------
+for (hw, c, co) in [(32, 128, 128), (16, 256, 256)]:
+    x, wp, bias = bf(64, hw, hw, c), bf(co, 9 * c) * (9 * c) ** -0.5, torch.randn(co, device=dev)
+    res = bf(64, hw, hw, co)
+    out = torch.empty(64, hw, hw, co, device=dev, dtype=torch.bfloat16)
+    q = torch.empty(64 * hw * hw // 32, co // 4, 2, device=dev)
+    targets.append((f"r2b conv+quad stats {hw}x{hw} {c}->{co}", lambda x=x, wp=wp, bias=bias, res=res, out=out, q=q:
+                    torch.ops.xdb200.conv3x3_qs(x, None, wp, bias, 0, res, out, 0, q)))
+    gamma, beta = torch.randn(co, device=dev), torch.randn(co, device=dev)
+    y = torch.empty_like(out)
+    targets.append((f"r2b groupnorm from quads {hw}x{hw}x{co}", lambda out=out, q=q, gamma=gamma, beta=beta, y=y, co=co:
+                    torch.ops.xdb200.groupnorm_quads(out.view(-1, co), q, gamma, beta, None, 1, 1e-5, 1, 64, y.view(-1, co))))
+x1, w_in, b_in = torch.randn(64, 1, 32, 32, device=dev), torch.randn(128, 1, 3, 3, device=dev), torch.randn(128, device=dev)
+o_in = torch.empty(64, 32, 32, 128, device=dev, dtype=torch.bfloat16)
+targets.append(("r2b conv3x3_in 1->128", lambda: torch.ops.xdb200.conv3x3_in(x1, w_in, b_in, o_in)))
+h_out, w_out, o_out = bf(64, 32, 32, 128), torch.randn(1, 128, 3, 3, device=dev), torch.empty(64, 1, 32, 32, device=dev)
+targets.append(("r2b conv3x3_out 128->1", lambda: torch.ops.xdb200.conv3x3_out(h_out, w_out, None, o_out)))
+qkvw = bf(64, 256, 3, 1, 256)                                       # EDM DDPM++ attention: one 256-wide head, T = 256
+qw, kw, vw = (qkvw[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+targets.append(("r2b attention wide head (EDM, d=256, T=256)", lambda: ops.attention(qw, kw, vw, 1 / 16)))
+
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 targets = [(n, f) for n, f in targets if only in n]
 for name, fn in targets:
