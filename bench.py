@@ -338,12 +338,12 @@ class Runner:
             self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(self, fn):
+    def timed(self, fn, steps=None):
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(self.local) as clk:
             e0.record()
-            for k in range(self.args.steps):
+            for k in range(steps or self.args.steps):
                 fn(k)
             e1.record()
             self.barrier()
@@ -354,7 +354,7 @@ class Runner:
             ms = float(t)
         return ms, clk.summary()
 
-    def run_workload(self, workload, global_batch, model=None, with_e2e=True):
+    def run_workload(self, workload, global_batch, model=None, with_e2e=True, steps=None, warmup=None):
         """value / e2e of one workload with its GLOBAL batch sharded over the ranks."""
         from xdiffusion_b200 import ops
         from xdiffusion_b200.dist import gather_rows, shard_bounds
@@ -392,12 +392,13 @@ class Runner:
             ops.LAUNCHES = 0
             lp._step()                                 # one eager step = the kernels one graph replay launches
             launches_per_timestep = ops.LAUNCHES
-        for w in range(max(args.warmup - 1, 0)):
+        steps = steps or args.steps
+        for w in range(max((args.warmup if warmup is None else warmup) - 1, 0)):
             loop(x_dev, cls_dev, 1 + w)
-        ms, clocks = self.timed(lambda k: loop(x_dev, cls_dev, 100 + k))
-        rec = {"value": B * args.steps / (ms / 1e3), "unit": UNIT[workload], "ms_per_step": ms / args.steps,
-               "ms_per_timestep": ms / args.steps / n_steps, "launches_per_timestep": launches_per_timestep,
-               "gpu_launches": ((launches_per_timestep or 0) * n_steps + 2) * args.steps, "clocks": clocks,
+        ms, clocks = self.timed(lambda k: loop(x_dev, cls_dev, 100 + k), steps)
+        rec = {"value": B * steps / (ms / 1e3), "unit": UNIT[workload], "ms_per_step": ms / steps, "steps": steps,
+               "ms_per_timestep": ms / steps / n_steps, "launches_per_timestep": launches_per_timestep,
+               "gpu_launches": ((launches_per_timestep or 0) * n_steps + 2) * steps, "clocks": clocks,
                "config": workload_config(workload, B, world, n_steps)}
         rec["step_tensor_frac_of_sustained"] = (rec["value"] / world * FLOP_PER_SAMPLE_STEP[workload] * n_steps
                                                 / (measured_peaks()[1] * 1e12))
@@ -410,11 +411,37 @@ class Runner:
                     out_host.copy_(full, non_blocking=True)
 
             e2e_step(0)
-            ms_e2e, _ = self.timed(e2e_step)
+            ms_e2e, _ = self.timed(e2e_step, steps)
             per_rank_h2d = x_host.numel() * 4 + cls_host.numel() * 8
-            rec["e2e"] = {"value": B * args.steps / (ms_e2e / 1e3), "unit": UNIT[workload],
+            rec["e2e"] = {"value": B * steps / (ms_e2e / 1e3), "unit": UNIT[workload],
                           "h2d_bytes_per_step": per_rank_h2d * world, "d2h_bytes_per_step": B * x_host[0].numel() * 4}
         return rec, model
+
+    def run_edm(self, global_batch=1024, reps=2):
+        """EDM (configs/image/mnist/edm.yaml: DDPM++ network, 18 Heun steps = 35 network evaluations) through
+        GaussianDiffusion_EDM.sample(), batch sharded over the ranks; the loop is host-driven (no graph)."""
+        from xdiffusion_b200.diffusion.edm import GaussianDiffusion_EDM
+        from xdiffusion_b200.dist import shard_bounds
+        from xdiffusion_b200.utils import DotConfig
+        cfg = torch.load(os.path.join(ROOT, "tests", "golden", "edm_net.pt"), weights_only=False)["config"]
+        torch.manual_seed(0)
+        m = GaussianDiffusion_EDM(DotConfig(cfg))
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for name, p in m.named_parameters():              # the reference initialises these to ~1e-5: re-draw
+                if name.endswith(("conv1.weight", "proj.weight", "aux_conv.weight")):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        m = m.to(self.device).eval()
+        lo, hi = shard_bounds(global_batch, self.world, self.rank)
+        x = torch.randn(global_batch, 1, 32, 32, generator=g)[lo:hi].to(self.device)
+        m.sample(num_samples=hi - lo, initial_noise=x)
+        ms, clocks = self.timed(lambda k: m.sample(num_samples=hi - lo, initial_noise=x), reps)
+        value = global_batch * reps / (ms / 1e3)
+        return {"value": value, "unit": "images/s", "ms_per_step": ms / reps, "steps": reps, "network_evaluations": 35,
+                "ms_per_evaluation": ms / reps / 35, "clocks": clocks,
+                "step_tensor_frac_of_sustained": value / self.world * 35 * 42.357e9 / (measured_peaks()[1] * 1e12),
+                "config": {"workload": "EDM DDPM++ (configs/image/mnist/edm.yaml), 18-step Heun sampler", "global_batch": global_batch,
+                           "per_gpu_batch": hi - lo}}
 
     def run(self):
         args, world, rank = self.args, self.world, self.rank
@@ -429,6 +456,19 @@ class Runner:
                 wrec, _ = self.run_workload("dit", gb * world, model=model, with_e2e=False)
                 extra["weak_scaling"] = {"value": wrec["value"], "unit": wrec["unit"], "global_batch": gb * world,
                                          "per_gpu_batch": gb, "ms_per_step": wrec["ms_per_step"]}
+            # the other configurations of SURVEY.md section 8: one timed loop each (device-timed, no e2e leg); a failure
+            # here must not cost the main line
+            others = {}
+            for name, wl in (("rf_c3", "rf"), ("pixart_c4", "pixart"), ("video_c5", "video"), ("edm_ddpmpp", None)):
+                try:
+                    if wl is None:
+                        others[name] = self.run_edm()
+                    else:
+                        others[name] = self.run_workload(wl, GLOBAL_BATCH[wl], with_e2e=False, steps=1, warmup=1)[0]
+                except Exception as exc:  # noqa: BLE001
+                    others[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.empty_cache()
+            extra["other_workloads"] = others
         self.barrier()
         if rank != 0:
             if world > 1:
@@ -478,6 +518,7 @@ class Runner:
                                 "kernel": "gemm_tc_kernel, implicit-GEMM conv3x3: every distinct launch of one UNet forward"}
             line["gpu_launches"] += urec["gpu_launches"]
             line["workloads"] = {"unet_c1": urec}
+            line["workloads"].update(extra.pop("other_workloads", {}))
             line.update(extra)
         if world == 1 and not args.no_cpu and main in ("dit", "unet"):
             line["cpu_baseline"] = cpu_baseline_record(main, gb)
