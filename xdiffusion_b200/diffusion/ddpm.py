@@ -11,12 +11,18 @@ Training (``forward`` / ``loss_on_batch``) is out of scope.
 from enum import Enum
 from typing import Callable, Dict, List, Optional, Tuple, Union
 
+import os
+
 import torch
 
 from .. import ops
 from ..samplers.base import ReverseProcessSampler
 from ..utils import (DotConfig, get_obj_from_str, instantiate_from_config, normalize_to_neg_one_to_one,
                      unnormalize_to_zero_to_one)
+
+
+# Classifier-free guidance as one forward over [conditional | unconditional] rows instead of two forwards (0 = two forwards)
+CFG_BATCHED = os.environ.get("XDB200_CFG_BATCHED", "1") == "1"
 
 
 class PredictionType(Enum):
@@ -289,17 +295,41 @@ class _DeviceLoop:
         self.cfg = cfg
         self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tabs = model._time_tables(N, dev)
-        t = self.tabs["timestep"]
-        self.timestep = torch.empty(B, dtype=t.dtype, device=dev)
-        self.logsnr_t = torch.empty(B, dtype=torch.float32, device=dev) if "logsnr_t" in self.tabs else None
-        self.logsnr_s = torch.empty(B, dtype=torch.float32, device=dev) if "logsnr_s" in self.tabs else None
-        self.x = torch.empty(shape, dtype=torch.float32, device=dev)
         self.context = self._static(context, dev)
         self.uncond = self._static(uncond_context, dev) if uncond_context is not None else None
+        # classifier-free guidance as ONE forward over [conditional | unconditional] rows (samples are independent): half
+        # the launches, and row counts at which the fused half-block kernels pay (samplers/base.py: _score)
+        self.both = self._merge(B) if self.uncond is not None and CFG_BATCHED and self._can_batch() else None
+        self.nrows = 2 * B if self.both is not None else B
+        t = self.tabs["timestep"]
+        self.timestep = torch.empty(self.nrows, dtype=t.dtype, device=dev)
+        self.logsnr_t = torch.empty(self.nrows, dtype=torch.float32, device=dev) if "logsnr_t" in self.tabs else None
+        self.logsnr_s = torch.empty(self.nrows, dtype=torch.float32, device=dev) if "logsnr_s" in self.tabs else None
+        self.x = torch.empty(shape, dtype=torch.float32, device=dev)
         self.noise = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # Philox key, read by the step kernel
         self.graph = None
         self._precompute()
+
+    def _can_batch(self):
+        from ..context import IgnoreInputPreprocessor
+        return (isinstance(self.model._input_preprocessor, IgnoreInputPreprocessor)
+                and "video_mask" not in self.context and "x0" not in self.context)
+
+    def _merge(self, B):
+        """Static [conditional | unconditional] conditioning, or None when the two dicts do not line up row for row."""
+        if set(self.context) != set(self.uncond):
+            return None
+        out = {}
+        for k, v in self.context.items():
+            u = self.uncond[k]
+            if torch.is_tensor(v) and torch.is_tensor(u) and v.shape == u.shape and v.dim() > 0 and v.shape[0] == B:
+                out[k] = torch.cat([v, u], 0)
+            elif not torch.is_tensor(v) and not torch.is_tensor(u) and v == u:
+                out[k] = v
+            else:
+                return None
+        return out
 
     @staticmethod
     def _static(ctx, dev):
@@ -318,6 +348,12 @@ class _DeviceLoop:
                     static[k].copy_(v)
                 else:
                     static[k] = v
+        if self.both is not None:
+            B = self.shape[0]
+            for k, v in self.both.items():
+                if torch.is_tensor(v) and k in self.context and torch.is_tensor(self.context[k]):
+                    v[:B].copy_(self.context[k])
+                    v[B:].copy_(self.uncond[k])
         self._precompute()
 
     def _precompute(self):
@@ -325,7 +361,7 @@ class _DeviceLoop:
         in place, so that graph replays read the new values."""
         net = self.model._score_network
         pre = self.model._input_preprocessor
-        for ctx in (self.context, self.uncond):
+        for ctx in ((self.both,) if self.both is not None else (self.context, self.uncond)):
             if ctx is None:
                 continue
             if hasattr(pre, "precompute"):
@@ -338,17 +374,18 @@ class _DeviceLoop:
         ti, tf = (t, None) if t.dtype == torch.int64 else (None, t)
         oi, of = (self.timestep, None) if t.dtype == torch.int64 else (None, self.timestep)
         torch.ops.xdb200.schedule_advance(self.idx, set_to, ti, tf, self.tabs.get("logsnr_t"), oi, of, self.logsnr_t,
-                                          self.shape[0])
+                                          self.nrows)
         if self.logsnr_s is not None:
             torch.ops.xdb200.schedule_advance(self.idx, -2, None, self.tabs["logsnr_s"], None, None, self.logsnr_s,
-                                              None, self.shape[0])
+                                              None, self.nrows)
 
-    def _ctx(self, base):
+    def _ctx(self, base, rows=None):
+        rows = self.shape[0] if rows is None else rows
         c = dict(base)
-        c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep, self.idx, self.N
+        c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep[:rows], self.idx, self.N
         c["row_offset"] = self.row_offset
         if self.logsnr_t is not None:
-            c["logsnr_t"], c["logsnr_s"] = self.logsnr_t, self.logsnr_s
+            c["logsnr_t"], c["logsnr_s"] = self.logsnr_t[:rows], self.logsnr_s[:rows]
         return c
 
     def _step(self):
@@ -357,6 +394,8 @@ class _DeviceLoop:
         if self.noise is not None:
             c["noise"] = self.noise
         u = self._ctx(self.uncond) if self.uncond is not None else None
+        if self.both is not None:
+            c["_cfg_both"] = self._ctx(self.both, self.nrows)
         mask = self.context.get("video_mask")
         if mask is not None:
             torch.ops.xdb200.blend_frames(self.x, self.context["x0"], mask)

@@ -84,15 +84,23 @@ class LastChannelCrossAttention(torch.nn.Module, Packed):
         B, L, C = y_bf16.shape
         return ops.linear(y_bf16.reshape(B * L, C), wkv).view(B, L, 2, self.heads, self.dim_head)
 
-    def forward(self, x_bf16, tokens: int, kv, **epilogue):
-        wq, wo = self.packed("w", (self.to_q.weight, self.to_out.weight),
-                             lambda: (bf16_weight(self.to_q.weight), bf16_weight(self.to_out.weight)))
+    def weights(self):
+        """(to_q, to_out) as bf16 [N, K] GEMM operands."""
+        return self.packed("w", (self.to_q.weight, self.to_out.weight),
+                           lambda: (bf16_weight(self.to_q.weight), bf16_weight(self.to_out.weight)))
+
+    def attend(self, x_bf16, tokens: int, kv):
+        """softmax(q k^T / sqrt(d)) v WITHOUT the output projection: bf16 [B*T, H*d]."""
+        wq, _ = self.weights()
         M, D = x_bf16.shape
         B, H, d = M // tokens, self.heads, self.dim_head
         q = ops.linear(x_bf16, wq).view(B, tokens, H, d).permute(0, 2, 1, 3)
         k, v = kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3)
-        a = ops.attention(q, k, v, self.scale)
-        return ops.linear(a.permute(0, 2, 1, 3).reshape(M, H * d), wo, self.to_out.bias, **epilogue)
+        return ops.attention(q, k, v, self.scale).permute(0, 2, 1, 3).reshape(M, H * d)
+
+    def forward(self, x_bf16, tokens: int, kv, **epilogue):
+        _, wo = self.weights()
+        return ops.linear(self.attend(x_bf16, tokens, kv), wo, self.to_out.bias, **epilogue)
 
 
 class QKVAttention(torch.nn.Module):

@@ -24,10 +24,19 @@ class ReverseProcessSampler:
         the intended computation is implemented.)"""
         if diffusion_model.is_learned_sigma():
             raise NotImplementedError("learned-sigma score networks are outside the covered hot path")
-        xin = diffusion_model.process_input(x=x, context=context)
-        o = diffusion_model.predict_score(xin, context=context)
         cfg = classifier_free_guidance if classifier_free_guidance is not None \
             else diffusion_model.classifier_free_guidance()
+        both = context.get("_cfg_both")
+        if cfg >= 0.0 and unconditional_context is not None and both is not None:
+            # the sampling loop prepared [conditional | unconditional] conditioning for 2B rows (diffusion/ddpm.py,
+            # _DeviceLoop._merge; identity input preprocessing only): one forward, rows B.. are the unconditional scores
+            B = x.shape[0]
+            o2 = diffusion_model.predict_score(torch.cat([x, x], 0), context=both)
+            out = torch.empty_like(x)
+            torch.ops.xdb200.cfg_combine(o2[:B], o2[B:], float(cfg), out)
+            return out
+        xin = diffusion_model.process_input(x=x, context=context)
+        o = diffusion_model.predict_score(xin, context=context)
         if cfg >= 0.0 and unconditional_context is not None:
             ou = diffusion_model.predict_score(
                 diffusion_model.process_input(x=x, context=unconditional_context), context=unconditional_context)

@@ -6,6 +6,7 @@ projections and the ContextProjection of the text embeddings do not depend on th
 reference recomputes them every step (pixart.py:237-239,264-265); the sampling loop computes them once per
 conditioning (``precompute_context``) and reuses them for every timestep (identical values, ~43% fewer FLOPs).
 """
+import os
 from typing import Dict
 
 import torch
@@ -15,7 +16,14 @@ from ..layers.attention import LastChannelCrossAttention, MultiHeadSelfAttention
 from ..layers.embedding import ContextProjection, PatchEmbed
 from ..layers.mlp import Mlp
 from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
+from . import dit as _dit
 from .dit import build_conditioning, run_custom_initializers
+
+# Token rows from which a block runs on the fused DiT half-block kernels (csrc/dit_block.cu): LayerNorm + modulate + qkv +
+# self-attention in one kernel, the cross-attention output projection + LayerNorm + modulate + fc1 + GELU + fc2 + gated
+# residual in the other (the kernel's first stage is a 384 x 384 projection with a gated residual: here the cross-attention
+# `to_out` with gate 1).  Per block 6 launches instead of 12; below the threshold one kernel per operator.
+FUSED_MIN_ROWS = int(os.environ.get("XDB200_PIXART_FUSED_MIN_ROWS", "12288"))
 
 
 class PixArtAlphaBlock(torch.nn.Module):
@@ -134,14 +142,42 @@ class PixArtAlpha(torch.nn.Module, Packed):
         h = self.x_embedder(x, self.pos_embed[0])                         # fp32 [B*T, D]
         silu_t = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
         torch.ops.xdb200.act_cast(t, ops.ACT_SILU, silu_t)
-        w_t = self.packed("t_block", (self.t_block[1].weight,), lambda: bf16_weight(self.t_block[1].weight))
-        t0 = ops.linear(silu_t, w_t, self.t_block[1].bias, out_dtype=torch.float32)            # [B, 6D]
-        tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.stack(
-            [b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float().contiguous())
-        mod = torch.empty((depth, B, 6 * D), device=x.device, dtype=torch.float32)
+        # adaLN-single: mod[n] = scale_shift_table[n] + t_block(t), six [B, D] slices per block.  A seventh slice of exact
+        # ones rides along (zero weight rows, bias 1, zero table entries): the gate of the ungated cross-attention residual
+        # for the fused kernel, at the same row pitch as the other slices and without a launch of its own.
+        w_t, b_t = self.packed("t_block", (self.t_block[1].weight, self.t_block[1].bias), lambda: (
+            torch.cat([bf16_weight(self.t_block[1].weight), torch.zeros((D, D), device=x.device, dtype=torch.bfloat16)], 0),
+            torch.cat([self.t_block[1].bias.detach().float(), torch.ones(D, device=x.device)], 0)))
+        t0 = ops.linear(silu_t, w_t, b_t, out_dtype=torch.float32)                            # [B, 7D]
+        tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.cat(
+            [torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float(),
+             torch.zeros((depth, D), device=x.device)], 1).contiguous())
+        mod = torch.empty((depth, B, 7 * D), device=x.device, dtype=torch.float32)
         torch.ops.xdb200.add_table(t0, tables, mod)                       # table + t0 for all blocks
+        fused = (_dit.FUSED_BLOCK and kvs is not None and D == 384 and T == 16 and self.num_heads * 64 == D
+                 and ops.MATMUL_BACKEND == "tc" and self.blocks[0].mlp.act == ops.ACT_GELU
+                 and self.blocks[0].mlp.fc1.out_features == 4 * D)
+        if ops.BATCH_DEPENDENT_PATHS and B * T < FUSED_MIN_ROWS:
+            fused = False                                 # (never when bit-exact batch independence is requested)
+        if fused:
+            stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32)       # (mean, rstd) of h, block n -> n + 1
         for n, blk in enumerate(self.blocks):
-            s1, sc1, g1, s2, sc2, g2 = (mod[n, :, i * D:(i + 1) * D] for i in range(6))
+            s1, sc1, g1, s2, sc2, g2, one = (mod[n, :, i * D:(i + 1) * D] for i in range(7))
+            if fused:
+                wh, bh = blk.attn.head_packed()
+                o = torch.empty((B * T, D), device=x.device, dtype=torch.bfloat16)
+                torch.ops.xdb200.dit_attn(h, stats if n > 0 else None, s1, sc1, T, 1e-6, wh, bh, self.num_heads,
+                                          blk.attn.scale, o)
+                _, wp = blk.attn.weights()
+                ops.linear(o, wp, blk.attn.proj.bias, gate=g1, gate_rows=T, residual=h, out=h)
+                hb = torch.empty((B * T, D), device=x.device, dtype=torch.bfloat16)
+                torch.ops.xdb200.act_cast(h, ops.ACT_NONE, hb)
+                a = blk.cross_attn.attend(hb, T, kvs[n])
+                _, wo = blk.cross_attn.weights()
+                w1, w2 = blk.mlp.weights()
+                torch.ops.xdb200.dit_proj_mlp(a, wo, blk.cross_attn.to_out.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias,
+                                              h, h, one, s2, sc2, g2, T, 1e-6, stats, 1)
+                continue
             a = ops.layernorm_modulate(h, s1, sc1, T)
             blk.attn(a, T, gate=g1, gate_rows=T, residual=h, out=h)
             if kvs is not None:
