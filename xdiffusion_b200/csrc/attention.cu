@@ -88,10 +88,24 @@ constexpr int PAIR_LD = 2 * T16 * RS16 + 4;  // +16 B: the two pairs of a warp h
 __global__ void __launch_bounds__(ROWS)
 attention16_kernel(const AttnParams p) {
     pdl_prologue();
-    extern __shared__ float smem[];             // [8][2][16][64] (+pad)
+    extern __shared__ float smem[];             // [8][2][16][64] (+pad) | [hpg][31][64] (+pad) relative-position tables
     const int tid = threadIdx.x;
     const int pl = tid >> 4, row = tid & 15;
-    const long long bh = (long long)blockIdx.x * 8 + pl;
+    // The relative-position key tables (hpg x 31 rows of 64 floats) are staged once per CTA: read straight from global
+    // memory every thread of a warp touched a different table row per load (32 cache lines per request) and the kernel
+    // spent most of its time there (232 us at 8 clips x 32 x 32 pixels x 2 heads).  A CTA then walks groups of 8 problems.
+    float* sR = smem + 8 * PAIR_LD;
+    if (p.relk) {
+        const int n4 = p.hpg * (2 * T16 - 1) * (D / 4);
+        for (int i = tid; i < n4; i += ROWS) {
+            const int r = i >> 4, c4 = i & 15;
+            *reinterpret_cast<float4*>(sR + r * RS16 + c4 * 4) = __ldg(reinterpret_cast<const float4*>(p.relk) + i);
+        }
+    }
+    const long long ngroups = ((long long)p.B * p.H + 7) / 8;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    if (grp != blockIdx.x) __syncthreads();     // the previous group's keys / values are no longer needed
+    const long long bh = grp * 8 + pl;
     const bool active = bh < (long long)p.B * p.H;
     const int b = active ? (int)(bh / p.H) : 0, h = active ? (int)(bh % p.H) : 0;
     float* sK = smem + pl * PAIR_LD;
@@ -140,7 +154,7 @@ attention16_kernel(const AttnParams p) {
     for (int j = 0; j < T16; ++j) {
         float acc = dot64(q, reinterpret_cast<const float4*>(sK + j * RS16));
         if (p.relk)
-            acc += dot64_ldg(q, reinterpret_cast<const float4*>(p.relk + ((long long)(h % p.hpg) * (2 * T16 - 1) + (j - row + T16 - 1)) * D));
+            acc += dot64(q, reinterpret_cast<const float4*>(sR + ((h % p.hpg) * (2 * T16 - 1) + (j - row + T16 - 1)) * RS16));
         s[j] = acc;
         mx = fmaxf(mx, acc);
     }
@@ -161,6 +175,7 @@ attention16_kernel(const AttnParams p) {
         }
     }
     if (active) store_row(p, b, h, row, o, 1.0f / l);
+    }
 }
 
 
@@ -743,12 +758,16 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
     }
     if (Tq == T16 && Tk == T16) {
         static bool configured16 = false;
-        const size_t smem16 = (size_t)8 * PAIR_LD * sizeof(float);
+        XD_CHECK_ARG(!relk || heads_per_group <= 8);
+        const size_t smem16 = ((size_t)8 * PAIR_LD + (relk ? (size_t)heads_per_group * (2 * T16 - 1) * RS16 : 0)) * sizeof(float);
         if (!configured16) {
-            cudaFuncSetAttribute(attention16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            cudaFuncSetAttribute(attention16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(((size_t)8 * PAIR_LD + (size_t)8 * (2 * T16 - 1) * RS16) * sizeof(float)));
             configured16 = true;
         }
-        const long long nb = ((long long)B * H + 7) / 8;
+        // with tables: a CTA stages them once and walks several groups of 8 problems (two CTAs per SM); without: one group
+        const long long groups = ((long long)B * H + 7) / 8;
+        const long long nb = relk ? std::min<long long>(groups, 2 * 148) : groups;
         xd_launch(attention16_kernel, (unsigned)nb, ROWS, smem16, (cudaStream_t)stream, p);
         XD_CHECK_LAUNCH();
         return XD_OK;
