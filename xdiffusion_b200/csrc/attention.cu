@@ -298,6 +298,182 @@ attention16_mma_kernel(const AttnParams p) {
     }
 }
 
+// ---- Tq == Tk == 16 with relative-position keys, fp32 q / k / v, scrambled store (the temporal attention of the video UNet):
+// one WARP per (clip, pixel, head) on mma.sync m16n8k16.  The logits are NOT scaled in the reference, so bf16 operand
+// rounding would be amplified by the softmax: every fp32 operand is split into bf16 hi + lo and each product is three MMAs
+// (hi.hi + hi.lo + lo.hi, error ~2^-17), the same scheme as the split-precision qkv projection that feeds this kernel.
+//   S = Q K^T (16 x 16),  R = Q E^T (16 x 31, E = this head's relative-position table),  logit[i][j] = S[i][j] + R[i][j - i + 15]
+//   (R goes through a 2 KB shared-memory scratch for the diagonal gather),  exact softmax,  O = P V,
+//   store a[b, h, row, d] as element (h * 16 + row) * 64 + d of the (C, L) view: frame d % 16, channel h * 64 + row * 4 + d / 16,
+//   i.e. one contiguous 128-byte row of 64 channels per frame.
+// Replaces the thread-per-row CUDA-core kernel (attention16_kernel), which was shared-memory bound.
+constexpr int WRP = 4;                                   // warps (problems in flight) per CTA
+constexpr int RP_WARP_BYTES = 6 * 2048 + 2176;           // Q, K, V as hi / lo tiles + the R scratch ([16][33] floats, padded to 128 B)
+__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, int row, int c4, float4 x) {
+    const bf16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+    const int off = row * 128 + (((c4 >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8;
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(f2_to_bf2(x.x, x.y), f2_to_bf2(x.z, x.w));
+    *reinterpret_cast<uint2*>(lo + off) = make_uint2(
+        f2_to_bf2(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1)), f2_to_bf2(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3)));
+}
+__global__ void __launch_bounds__(32 * WRP)
+attention16_relpos_mma_kernel(const AttnParams p) {
+    pdl_prologue();
+    extern __shared__ __align__(128) uint8_t smr[];      // [WRP][RP_WARP_BYTES] | [hpg][hi, lo][32 rows x 128 B]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sE = smr + WRP * RP_WARP_BYTES;
+    for (int i = threadIdx.x; i < p.hpg * 32 * 16; i += 32 * WRP) {
+        const int t = i >> 9, r = (i >> 4) & 31, c4 = i & 15;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < 2 * T16 - 1) x = __ldg(reinterpret_cast<const float4*>(p.relk + ((long long)t * (2 * T16 - 1) + r) * D) + c4);
+        split_store(sE + t * 8192, sE + t * 8192 + 4096, r, c4, x);
+    }
+    __syncthreads();
+    uint8_t* sQh = smr + warp * RP_WARP_BYTES;
+    uint8_t *sQl = sQh + 2048, *sKh = sQh + 4096, *sKl = sQh + 6144, *sVh = sQh + 8192, *sVl = sQh + 10240;
+    float* sR = reinterpret_cast<float*>(sQh + 12288);
+    const uint32_t aQh = (uint32_t)__cvta_generic_to_shared(sQh), aQl = aQh + 2048, aKh = aQh + 4096, aKl = aQh + 6144,
+                   aVh = aQh + 8192, aVl = aQh + 10240, aE = (uint32_t)__cvta_generic_to_shared(sE);
+    const long long total = (long long)p.B * p.H;
+    for (long long bh = (long long)blockIdx.x * WRP + warp; bh < total; bh += (long long)gridDim.x * WRP) {
+        const int b = (int)(bh / p.H), h = (int)(bh % p.H);
+        const int g = h / p.hpg, hh = h - g * p.hpg;
+        const float* qp = (const float*)p.q + b * p.q_bs + h * p.q_hs;
+        const float* kp = (const float*)p.k + b * p.k_bs + h * p.k_hs;
+        const float* vp = (const float*)p.v + b * p.v_bs + h * p.v_hs;
+        {   // 16 rows x 16 float4 per tensor: 8 per lane, all 24 loads in flight
+            float4 rq[8], rk[8], rv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, row = idx >> 4, c4 = idx & 15;
+                rq[i] = *reinterpret_cast<const float4*>(qp + (long long)row * p.q_rs + c4 * 4);
+                rk[i] = *reinterpret_cast<const float4*>(kp + (long long)row * p.k_rs + c4 * 4);
+                rv[i] = *reinterpret_cast<const float4*>(vp + (long long)row * p.v_rs + c4 * 4);
+            }
+            __syncwarp();                                 // the previous problem's tiles are no longer read
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, row = idx >> 4, c4 = idx & 15;
+                rq[i].x *= p.scale; rq[i].y *= p.scale; rq[i].z *= p.scale; rq[i].w *= p.scale;
+                split_store(sQh, sQl, row, c4, rq[i]);
+                split_store(sKh, sKl, row, c4, rk[i]);
+                split_store(sVh, sVl, row, c4, rv[i]);
+            }
+        }
+        __syncwarp();
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, r[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[nt][j] = 0.f;
+        const uint32_t aEh = aE + hh * 8192, aEl = aEh + 4096;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ah[4], al[4], bh4[4], bl4[4];
+            {
+                const int row = (lane & 7) + ((lane >> 3) & 1) * 8, c = 2 * ks + (lane >> 4);
+                const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+                ldsm_x4(aQh + off, ah[0], ah[1], ah[2], ah[3]);
+                ldsm_x4(aQl + off, al[0], al[1], al[2], al[3]);
+            }
+            const int brow = (lane & 7) + (lane >> 4) * 8, bc = 2 * ks + ((lane >> 3) & 1);
+            {
+                const uint32_t off = brow * 128 + ((bc ^ (brow & 7)) << 4);
+                ldsm_x4(aKh + off, bh4[0], bh4[1], bh4[2], bh4[3]);
+                ldsm_x4(aKl + off, bl4[0], bl4[1], bl4[2], bl4[3]);
+            }
+            mma_bf16_16816(s0, ah[0], ah[1], ah[2], ah[3], bh4[0], bh4[1]);
+            mma_bf16_16816(s1, ah[0], ah[1], ah[2], ah[3], bh4[2], bh4[3]);
+            mma_bf16_16816(s0, ah[0], ah[1], ah[2], ah[3], bl4[0], bl4[1]);
+            mma_bf16_16816(s1, ah[0], ah[1], ah[2], ah[3], bl4[2], bl4[3]);
+            mma_bf16_16816(s0, al[0], al[1], al[2], al[3], bh4[0], bh4[1]);
+            mma_bf16_16816(s1, al[0], al[1], al[2], al[3], bh4[2], bh4[3]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {       // table rows 16 * half .. 16 * half + 15
+                const int er = brow + 16 * half;
+                const uint32_t off = er * 128 + ((bc ^ (er & 7)) << 4);
+                ldsm_x4(aEh + off, bh4[0], bh4[1], bh4[2], bh4[3]);
+                ldsm_x4(aEl + off, bl4[0], bl4[1], bl4[2], bl4[3]);
+                mma_bf16_16816(r[2 * half], ah[0], ah[1], ah[2], ah[3], bh4[0], bh4[1]);
+                mma_bf16_16816(r[2 * half + 1], ah[0], ah[1], ah[2], ah[3], bh4[2], bh4[3]);
+                mma_bf16_16816(r[2 * half], ah[0], ah[1], ah[2], ah[3], bl4[0], bl4[1]);
+                mma_bf16_16816(r[2 * half + 1], ah[0], ah[1], ah[2], ah[3], bl4[2], bl4[3]);
+                mma_bf16_16816(r[2 * half], al[0], al[1], al[2], al[3], bh4[0], bh4[1]);
+                mma_bf16_16816(r[2 * half + 1], al[0], al[1], al[2], al[3], bh4[2], bh4[3]);
+            }
+        }
+        // R -> scratch [16][33]; logit[i][j] += R[i][j - i + 15]
+        const int i_lo = lane >> 2, i_hi = i_lo + 8, jc = (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            sR[i_lo * 33 + nt * 8 + jc] = r[nt][0]; sR[i_lo * 33 + nt * 8 + jc + 1] = r[nt][1];
+            sR[i_hi * 33 + nt * 8 + jc] = r[nt][2]; sR[i_hi * 33 + nt * 8 + jc + 1] = r[nt][3];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            s0[e] += sR[i_lo * 33 + (jc + e) - i_lo + 15];          s1[e] += sR[i_lo * 33 + (8 + jc + e) - i_lo + 15];
+            s0[2 + e] += sR[i_hi * 33 + (jc + e) - i_hi + 15];      s1[2 + e] += sR[i_hi * 33 + (8 + jc + e) - i_hi + 15];
+        }
+        // exact softmax over the 16 keys of rows i_lo (elements 0, 1) and i_hi (2, 3); a row lives in one quad
+        float m_lo = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])), m_hi = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+        s0[0] = __expf(s0[0] - m_lo); s0[1] = __expf(s0[1] - m_lo); s1[0] = __expf(s1[0] - m_lo); s1[1] = __expf(s1[1] - m_lo);
+        s0[2] = __expf(s0[2] - m_hi); s0[3] = __expf(s0[3] - m_hi); s1[2] = __expf(s1[2] - m_hi); s1[3] = __expf(s1[3] - m_hi);
+        float l_lo = s0[0] + s0[1] + s1[0] + s1[1], l_hi = s0[2] + s0[3] + s1[2] + s1[3];
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+        // P = hi + lo as the A operand of the second contraction (accumulator fragments are already in A layout)
+        uint32_t pah[4], pal[4];
+        {
+            const float pv[8] = {s0[0], s0[1], s0[2], s0[3], s1[0], s1[1], s1[2], s1[3]};
+            float lo8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lo8[i] = pv[i] - __bfloat162float(__float2bfloat16_rn(pv[i]));
+            pah[0] = f2_to_bf2(pv[0], pv[1]); pah[1] = f2_to_bf2(pv[2], pv[3]); pah[2] = f2_to_bf2(pv[4], pv[5]); pah[3] = f2_to_bf2(pv[6], pv[7]);
+            pal[0] = f2_to_bf2(lo8[0], lo8[1]); pal[1] = f2_to_bf2(lo8[2], lo8[3]); pal[2] = f2_to_bf2(lo8[4], lo8[5]); pal[3] = f2_to_bf2(lo8[6], lo8[7]);
+        }
+        float o[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt += 2) {
+            uint32_t vh[4], vl[4];
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8, cc = nt + (lane >> 4);
+            const uint32_t off = row * 128 + ((cc ^ (row & 7)) << 4);
+            ldsm_x4_trans(aVh + off, vh[0], vh[1], vh[2], vh[3]);
+            ldsm_x4_trans(aVl + off, vl[0], vl[1], vl[2], vl[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { o[nt][j] = 0.f; o[nt + 1][j] = 0.f; }
+            mma_bf16_16816(o[nt], pah[0], pah[1], pah[2], pah[3], vh[0], vh[1]);
+            mma_bf16_16816(o[nt + 1], pah[0], pah[1], pah[2], pah[3], vh[2], vh[3]);
+            mma_bf16_16816(o[nt], pah[0], pah[1], pah[2], pah[3], vl[0], vl[1]);
+            mma_bf16_16816(o[nt + 1], pah[0], pah[1], pah[2], pah[3], vl[2], vl[3]);
+            mma_bf16_16816(o[nt], pal[0], pal[1], pal[2], pal[3], vh[0], vh[1]);
+            mma_bf16_16816(o[nt + 1], pal[0], pal[1], pal[2], pal[3], vh[2], vh[3]);
+        }
+        const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+        __syncwarp();                                     // everyone is done with the Q tiles: the hi tile becomes the output tile
+        // out_tile[frame = d % 16][channel = row * 4 + d / 16] (bf16, 128 bytes per frame)
+        bf16* st = reinterpret_cast<bf16*>(sQh);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = (nt & 1) * 8 + jc + e, qd = nt >> 1;
+                st[f * 64 + i_lo * 4 + qd] = __float2bfloat16_rn(o[nt][e] * inv_lo);
+                st[f * 64 + i_hi * 4 + qd] = __float2bfloat16_rn(o[nt][2 + e] * inv_hi);
+            }
+        }
+        __syncwarp();
+        bf16* ob = p.o + b * p.o_bs + g * p.o_gs + hh * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, f = idx >> 3, ch = idx & 7;
+            *reinterpret_cast<uint4*>(ob + (long long)f * p.o_rs + ch * 8) = *reinterpret_cast<const uint4*>(st + f * 64 + ch * 8);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(ROWS)
 attention_kernel(const AttnParams p) {
     pdl_prologue();
@@ -754,6 +930,25 @@ extern "C" int xd_attention_bf16(const void* q, long long q_bs, long long q_hs, 
             xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
             return XD_ERR_CUDA;
         }
+        return XD_OK;
+    }
+    if (Tq == T16 && Tk == T16 && relk && scramble && in_f32 && o_cs == 1 && heads_per_group <= 8 && o_rs % 8 == 0 &&
+        o_bs % 8 == 0 && o_gs % 8 == 0 && q_rs % 4 == 0 && q_hs % 4 == 0 && q_bs % 4 == 0 && getenv("XDB200_RELPOS_SIMT") == nullptr) {
+        // temporal attention of the video UNet: split-precision mma.sync kernel, one warp per (clip, pixel, head)
+        static bool configured_rp = false;
+        const size_t smem = (size_t)WRP * RP_WARP_BYTES + (size_t)heads_per_group * 8192;
+        if (!configured_rp) {
+            if (cudaFuncSetAttribute(attention16_relpos_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)WRP * RP_WARP_BYTES + 8 * 8192)) != cudaSuccess) {
+                xd_set_error(__FILE__, __LINE__, "cudaFuncSetAttribute failed (attention16_relpos_mma)");
+                return XD_ERR_CUDA;
+            }
+            configured_rp = true;
+        }
+        const long long warps = (long long)B * H;
+        const long long nb = std::min<long long>((warps + WRP - 1) / WRP, 3 * 148);
+        xd_launch(attention16_relpos_mma_kernel, (unsigned)nb, 32 * WRP, smem, (cudaStream_t)stream, p);
+        XD_CHECK_LAUNCH();
         return XD_OK;
     }
     if (Tq == T16 && Tk == T16) {
