@@ -117,6 +117,17 @@ int xd_groupnorm_apply_quads(const void* x, long long ld, int nsamples, int P, i
                              long long qstats_ld, const float* gamma, const float* beta, const float* scale_shift,
                              long long ss_ld, int ss_div, float eps, int silu, void* out, long long ldo, void* stream);
 
+/* out = GroupNorm(32 groups)(conv3x3(X) + bias) [* (1 + scale) + shift] [-> SiLU]: the first convolution of a residual block and the
+ * normalisation that consumes it (layers/resnet.py:129 + 151-153,193-197) in the cheapest way the shape allows.  Few output
+ * tiles and a long contraction (the 8x8 / 4x4 levels): the contraction is split over K and the reduce pass normalises -- one
+ * CTA per sample, the un-normalised activation never reaches memory.  Unsplit: quad statistics from the epilogue + one
+ * streaming pass.  Otherwise: conv, then xd_groupnorm_fused / stats + apply.  tmp: bf16 [nimg*H*W, Cout] scratch; scratch:
+ * fp32, max(nimg*H*W / 32 * Cout / 2, nsamples * 64 * xd_groupnorm_slabs(nsamples, P, Cout)) elements. */
+int xd_conv3x3_groupnorm_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Wp, int Cout,
+                                 const float* bias, int nsamples, const float* gamma, const float* beta,
+                                 const float* scale_shift, long long ss_ld, int ss_div, float eps, int silu, void* tmp,
+                                 float* scratch, void* out, long long out_ld, void* stream);
+
 /* CUDA-core twins with the identical contract (on-device cross-check; K not a multiple of 64). */
 int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
                       long long ldw, int M, int N, int K, const float* bias, int act, const float* gate,

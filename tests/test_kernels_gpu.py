@@ -297,6 +297,32 @@ def _two_producers_case(ops, buf, x, w, a, wl, res, gamma, beta, full, nimg, H, 
     assert rel_l2(got.permute(0, 2, 1), ref) < 3e-3, rel_l2(got.permute(0, 2, 1), ref)
 
 
+@pytest.mark.parametrize("nimg,H,C,Co,samples,route", [(64, 8, 256, 256, 64, "split"), (64, 4, 256, 256, 64, "split"),
+                                                       (16, 8, 512, 256, 16, "split"), (32, 8, 128, 128, 2, "split"),
+                                                       (64, 16, 256, 256, 64, "quads"), (16, 32, 128, 128, 16, "quads"),
+                                                       (2, 8, 256, 256, 2, "any"), (64, 4, 256, 512, 64, "any")])
+def test_conv3x3_groupnorm_all_routes(ops, nimg, H, C, Co, samples, route):
+    """xd_conv3x3_groupnorm_bf16_tc: GroupNorm32(conv3x3(x) + bias) * (1 + scale) + shift -> SiLU against fp32 torch, on the
+    route the shape selects (split-K reduce that normalises / epilogue statistics / conv then GroupNorm); `samples` < nimg =
+    several images share statistics (the frames of a clip)."""
+    g = torch.Generator().manual_seed(nimg + H + C + Co)
+    x = bf(torch.randn(nimg, C, H, H, generator=g))
+    w = bf(torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(Co, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(Co, generator=g), 0.1 * torch.randn(Co, generator=g)
+    ss = torch.randn(samples, 2 * Co, generator=g) * 0.3
+    conv = F.conv2d(x.float(), w.float(), bias, padding=1)                                 # [nimg, Co, H, H]
+    per = nimg // samples
+    cs = conv.view(samples, per, Co, H * H).permute(0, 2, 1, 3).reshape(samples, Co, per * H * H)
+    ref = F.group_norm(cs, 32, gamma, beta, 1e-5) * (1 + ss[:, :Co, None]) + ss[:, Co:, None]
+    ref = F.silu(ref).view(samples, Co, per, H, H).permute(0, 2, 1, 3, 4).reshape(nimg, Co, H, H)
+    n0 = ops.LAUNCHES
+    out = ops.conv3x3_groupnorm(x.permute(0, 2, 3, 1).contiguous().to(DEV), _pack_conv(w).to(DEV), bias.to(DEV), samples,
+                                gamma.to(DEV), beta.to(DEV), scale_shift=ss.to(DEV))
+    assert ops.LAUNCHES - n0 == 2
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 4e-3, (route, rel_l2(out.permute(0, 3, 1, 2), ref))
+
+
 def test_conv_in_out(ops):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(3, 1, 32, 32, generator=g)

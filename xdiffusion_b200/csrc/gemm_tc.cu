@@ -976,6 +976,90 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     return XD_OK;
 }
 
+// Split-K second pass fused with the GroupNorm (+ scale / shift, + SiLU) that consumes the contraction's output (the first conv
+// of a resblock at the low resolutions: 8 x 8 and 4 x 4 pixels per sample): one CTA per sample sums the fp32 partial tiles in
+// split order, keeps its <= 64 values per thread in registers, reduces the 32 groups in a fixed order (two adjacent lanes x
+// four row slots per group), normalises and stores bf16 -- the un-normalised activation never exists in memory and the
+// stand-alone GroupNorm launch disappears.  C / 4 divides 256, so a thread always works on the same four channels.
+constexpr int GN_MAX_V4 = 16;                            // float4 per thread: P * C <= 16384
+struct GnFuse {
+    int nsamples, P;
+    const float *gamma, *beta, *ss;
+    long long ss_ld;
+    int ss_div, silu;
+    float eps;
+    void* out;
+    long long out_ld;
+    int done;                                            // set by dispatch(): the fused kernel ran
+};
+__global__ void __launch_bounds__(256)
+splitk_reduce_gn_kernel(const float* __restrict__ ws, int S, long long split_stride, int P, int N, const float* __restrict__ bias,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
+                        long long ss_ld, int ss_div, float eps, int silu, bf16* __restrict__ out, long long out_ld) {
+    pdl_prologue();
+    __shared__ float2 part[8][32];
+    const int n4 = N >> 2, sample = blockIdx.x;
+    const int col4 = threadIdx.x % n4, slot = threadIdx.x / n4, slots = 256 / n4;
+    const int c = col4 * 4, cpg = N / 32;
+    const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[GN_MAX_V4];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < GN_MAX_V4; ++i) {
+        const int r = slot + i * slots;
+        if (r < P) {
+            const float* src = ws + ((long long)sample * P + r) * N + c;
+            float4 t = *reinterpret_cast<const float4*>(src);
+            for (int sidx = 1; sidx < S; ++sidx) {
+                const float4 u = *reinterpret_cast<const float4*>(src + sidx * split_stride);
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+            v[i] = t;
+            sum += (t.x + t.y) + (t.z + t.w);
+            sq += fmaf(t.x, t.x, t.y * t.y) + fmaf(t.z, t.z, t.w * t.w);
+        }
+    }
+    // group = cpg / 4 adjacent column quads (1, 2, 4 lanes) x `slots` row slots
+    const int qpg = cpg >> 2;
+    for (int o = 1; o < qpg; o <<= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    const int g = col4 / qpg;
+    if (col4 % qpg == 0) part[slot][g] = make_float2(sum, sq);
+    __syncthreads();
+    float gs = 0.f, gq = 0.f;
+    for (int k = 0; k < slots; ++k) { gs += part[k][g].x; gq += part[k][g].y; }
+    const float inv_cnt = 1.0f / ((float)P * (float)cpg);
+    const float mean = gs * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(gq * inv_cnt - mean * mean, 0.f) + eps);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float a[4] = {rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w};
+    float bb[4] = {be.x - mean * a[0], be.y - mean * a[1], be.z - mean * a[2], be.w - mean * a[3]};
+    if (ss) {
+        const float* row = ss + (long long)(sample / ss_div) * ss_ld;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(row + c)), sh = __ldg(reinterpret_cast<const float4*>(row + N + c));
+        const float s4[4] = {1.0f + sc.x, 1.0f + sc.y, 1.0f + sc.z, 1.0f + sc.w}, h4[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] *= s4[k]; bb[k] = bb[k] * s4[k] + h4[k]; }
+    }
+#pragma unroll
+    for (int i = 0; i < GN_MAX_V4; ++i) {
+        const int r = slot + i * slots;
+        if (r < P) {
+            float y[4] = {fmaf(v[i].x, a[0], bb[0]), fmaf(v[i].y, a[1], bb[1]), fmaf(v[i].z, a[2], bb[2]), fmaf(v[i].w, a[3], bb[3])};
+            if (silu) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float hh = 0.5f * y[k];
+                    float t;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hh));
+                    y[k] = fmaf(hh, t, hh);
+                }
+            }
+            *reinterpret_cast<uint2*>(out + ((long long)sample * P + r) * out_ld + c) = make_uint2(f2_to_bf2(y[0], y[1]), f2_to_bf2(y[2], y[3]));
+        }
+    }
+}
+
 struct TileChoice {
     int bn, cg, as;
 };
@@ -1038,7 +1122,7 @@ void set_items(TcParams* p, const TileChoice& t) {
 }
 
 int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
-             cudaStream_t st, int* qs_emitted = nullptr) {
+             cudaStream_t st, int* qs_emitted = nullptr, GnFuse* gnf = nullptr) {
     set_items(&p, t);
     // Split-K: long contractions over few tiles (the 8x8 / 4x4 UNet convs: 16-32 tiles, K = 2304-9216) are bound by
     // the per-CTA TMA -> MMA round trip (~370 ns per k-block), not by the tensor pipe: S CTAs share a tile's K range,
@@ -1074,6 +1158,17 @@ int dispatch(const TileChoice& t, const CUtensorMap& a0, const CUtensorMap& a1, 
     }
     auto finish = [&](int rc) -> int {
         if (rc != XD_OK || S == 1) return rc;
+        if (gnf && !e_final.gate && !e_final.residual && e_final.act == XD_ACT_NONE && p.N % 128 == 0 && 256 % (p.N / 4) == 0 &&
+            (long long)gnf->P * p.N <= 1024LL * GN_MAX_V4 && (long long)gnf->nsamples * gnf->P == p.M && gnf->out_ld % 4 == 0) {
+            if (xd_launch(splitk_reduce_gn_kernel, dim3((unsigned)gnf->nsamples), dim3(256), 0, st, (const float*)g_ws, S,
+                          (long long)p.ws_rows * p.N, gnf->P, p.N, e_final.bias, gnf->gamma, gnf->beta, gnf->ss, gnf->ss_ld,
+                          gnf->ss_div > 0 ? gnf->ss_div : 1, gnf->eps, gnf->silu, (bf16*)gnf->out, gnf->out_ld) != cudaSuccess) {
+                xd_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+                return XD_ERR_CUDA;
+            }
+            gnf->done = 1;
+            return XD_OK;
+        }
         const long long n4 = (long long)p.M * (p.N / 4);
         if (xd_launch(splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, (const float*)g_ws, S,
                       (long long)p.ws_rows * p.N, p.M, p.N, e_final) != cudaSuccess) {
@@ -1181,7 +1276,8 @@ extern "C" int xd_gemm_bf16_tc_qstats(const void* A, long long lda, const void* 
 static int conv_impl(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,
                      long long lds, int Cs, const void* Wp, int Cout, const float* bias, int act,
                      const void* residual, int res_dtype, long long res_ld, void* out, int out_dtype,
-                     long long out_ld, int force_bn, float* qstats, long long qstats_ld, int* qs_emitted, void* stream) {
+                     long long out_ld, int force_bn, float* qstats, long long qstats_ld, int* qs_emitted, void* stream,
+                     GnFuse* gnf = nullptr) {
     XD_CHECK_ARG(X && Wp && out && nimg > 0 && H > 0 && W > 0 && Cout > 0);
     XD_CHECK_ARG(C % BK == 0 && Cs % BK == 0 && (Xs != nullptr) == (Cs > 0));
     XD_CHECK_ARG(ldx % 8 == 0 && lds % 8 == 0 && aligned16(X) && aligned16(Xs) && aligned16(Wp));
@@ -1204,7 +1300,50 @@ static int conv_impl(const void* X, long long ldx, int nimg, int H, int W, int C
     const long long ktot = 9LL * C + Cs;
     if ((rc = tmap_weights(&tb, Wp, Cout, ktot, ktot, t.bn / t.cg))) return rc;
     p.qstats = qstats; p.qstats_ld = qstats_ld;
-    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream, qs_emitted);
+    return dispatch(t, ta0, ta1, tb, p, (cudaStream_t)stream, qs_emitted, gnf);
+}
+
+extern "C" int xd_groupnorm_apply_quads(const void* x, long long ld, int nsamples, int P, int C, int groups,
+                                        const float* qstats, long long qstats_ld, const float* gamma, const float* beta,
+                                        const float* scale_shift, long long ss_ld, int ss_div, float eps, int silu,
+                                        void* out, long long ldo, void* stream);
+extern "C" int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int P, int C, int groups, const float* gamma,
+                                  const float* beta, const float* scale_shift, long long ss_ld, int ss_div, float eps,
+                                  int silu, void* out, long long ldo, void* stream);
+extern "C" int xd_groupnorm_stats(const void* x, long long ld, int nsamples, int P, int C, int groups, int inner,
+                                  float* stats, void* stream);
+extern "C" int xd_groupnorm_apply(const void* x, long long ld, int nsamples, int P, int C, int groups,
+                                  const float* stats, const float* gamma, const float* beta, const float* scale_shift,
+                                  long long ss_ld, int ss_div, float eps, int silu, int inner, int split, void* out,
+                                  long long ldo, void* stream);
+extern "C" int xd_groupnorm_slabs(int nsamples, int P, int C);
+
+// out = GroupNorm32(conv3x3(X) + bias) [* (1 + scale) + shift] [SiLU], the cheapest way the shape allows:
+//   split-K contraction (few output tiles, long K)  -> the reduce pass normalises (splitk_reduce_gn_kernel), 2 launches;
+//   unsplit bf16 TMA epilogue                        -> quad statistics from the epilogue + one streaming pass, 2 launches;
+//   otherwise                                        -> conv, then the single-pass cluster GroupNorm (or statistics + apply).
+// tmp: bf16 [nimg * H * W, Cout] scratch for the un-normalised activation (unused by the first path); scratch: fp32,
+// max(M / 32 * Cout / 4 * 2, nsamples * 64 * xd_groupnorm_slabs(nsamples, P, Cout)) elements.
+extern "C" int xd_conv3x3_groupnorm_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Wp,
+                                            int Cout, const float* bias, int nsamples, const float* gamma, const float* beta,
+                                            const float* scale_shift, long long ss_ld, int ss_div, float eps, int silu,
+                                            void* tmp, float* scratch, void* out, long long out_ld, void* stream) {
+    XD_CHECK_ARG(tmp && scratch && out && gamma && beta && nsamples > 0 && ((long long)nimg * H * W) % nsamples == 0);
+    const int M = nimg * H * W, P = M / nsamples;
+    GnFuse gnf{nsamples, P, gamma, beta, scale_shift, ss_ld, ss_div, silu, eps, out, out_ld, 0};
+    int emitted = 0;
+    const bool want_q = M % 32 == 0 && P % 32 == 0 && Cout % 128 == 0;
+    int rc = conv_impl(X, ldx, nimg, H, W, C, nullptr, 0, 0, Wp, Cout, bias, XD_ACT_NONE, nullptr, 0, 0, tmp, XD_BF16, Cout, 0,
+                       want_q ? scratch : nullptr, want_q ? Cout / 4 * 2 : 0, &emitted, stream, &gnf);
+    if (rc != XD_OK || gnf.done) return rc;
+    if (emitted)
+        return xd_groupnorm_apply_quads(tmp, Cout, nsamples, P, Cout, 32, scratch, Cout / 4 * 2, gamma, beta, scale_shift, ss_ld,
+                                        ss_div, eps, silu, out, out_ld, stream);
+    rc = xd_groupnorm_fused(tmp, Cout, nsamples, P, Cout, 32, gamma, beta, scale_shift, ss_ld, ss_div, eps, silu, out, out_ld, stream);
+    if (rc != -1) return rc;
+    if ((rc = xd_groupnorm_stats(tmp, Cout, nsamples, P, Cout, 32, 1, scratch, stream))) return rc;
+    return xd_groupnorm_apply(tmp, Cout, nsamples, P, Cout, 32, scratch, gamma, beta, scale_shift, ss_ld, ss_div, eps, silu, 1, 0,
+                              out, out_ld, stream);
 }
 
 extern "C" int xd_conv3x3_bf16_tc(const void* X, long long ldx, int nimg, int H, int W, int C, const void* Xs,

@@ -1,11 +1,18 @@
 """BigGAN-style residual block, Downsample, Upsample on the xdb200 kernels (NHWC bf16).
 Parameter names / constructor arguments follow the reference (layers/resnet.py:83-201,440-502)."""
+import os
 from typing import Dict
 
 import torch
 
 from .. import ops
 from .utils import ContextBlock, Packed, pack_conv3x3, zero_module
+
+
+# First conv of a resblock + its GroupNorm as one library call (xd_conv3x3_groupnorm_bf16_tc: at the 8x8 / 4x4 levels the
+# split-K reduce pass normalises).  Measured neutral on the UNet step (37.4 vs 36.9 img/s: one CTA per sample sums the partial
+# tiles more slowly than the wide reduce kernel + the 5 us cluster GroupNorm it replaces), so it is an opt-in.
+CONV_GN_FUSED = os.environ.get("XDB200_CONV_GN", "0") == "1"
 
 
 def _as_samples(x, samples):
@@ -63,9 +70,14 @@ class ResnetBlockBigGAN(ContextBlock, Packed):
             (c2.bias + skip.bias).detach().float() if has_skip else None))
         g1, g2 = self.in_layers[0], self.out_layers[0]
         h = ops.groupnorm(_as_samples(x, samples), g1.weight, g1.bias, eps=g1.eps, silu=True).view(x.shape)
-        h = ops.conv3x3(h, w1, c1.bias, qstats=True)
-        h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps,
-                          silu=True).view(h.shape)
+        if ops.MATMUL_BACKEND == "tc" and CONV_GN_FUSED and self.out_channels % 128 == 0:
+            # first conv + the GroupNorm that consumes it as one library call (split-K reduce that normalises at the low
+            # resolutions, statistics from the conv epilogue at the high ones: include/xdb200.h)
+            h = ops.conv3x3_groupnorm(h, w1, c1.bias, samples, g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps)
+        else:
+            h = ops.conv3x3(h, w1, c1.bias, qstats=True)
+            h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps,
+                              silu=True).view(h.shape)
         if has_skip:
             return ops.conv3x3(h, w2, b2, xs=x, out=out, qstats=True)
         return ops.conv3x3(h, w2, c2.bias, residual=x, out=out, qstats=True)

@@ -364,6 +364,25 @@ def _conv3x3_qs(x, xs, wp, bias, act, residual, out, force_bn, qstats):
     return emitted.value
 
 
+@_op("conv3x3_groupnorm(Tensor x, Tensor wp, Tensor? bias, int nsamples, Tensor gamma, Tensor beta, Tensor? scale_shift, "
+     "int ss_div, float eps, int silu, Tensor(a!) tmp, Tensor(b!) scratch, Tensor(c!) out) -> ()")
+def _conv3x3_groupnorm(x, wp, bias, nsamples, gamma, beta, scale_shift, ss_div, eps, silu, tmp, scratch, out):
+    """out = GroupNorm32(conv3x3(x) + bias) [*(1 + scale) + shift] [SiLU]; see include/xdb200.h for the three routes."""
+    _cuda(x, wp, bias, gamma, beta, scale_shift, tmp, scratch, out)
+    _ensure_workspace(x)
+    nimg, H, W, C = x.shape
+    Cout = wp.shape[0]
+    assert wp.shape[1] == 9 * C and wp.is_contiguous() and tmp.is_contiguous() and scratch.is_contiguous()
+    assert tmp.dtype == torch.bfloat16 and tmp.numel() == nimg * H * W * Cout and scratch.dtype == torch.float32
+    for t in (x, out):
+        assert t.stride(3) == 1 and t.stride(1) == W * t.stride(2) and t.stride(0) == H * t.stride(1)
+    _lib.check(_lib.lib().xd_conv3x3_groupnorm_bf16_tc(
+        _p(x), x.stride(2), nimg, H, W, C, _p(wp), Cout, _p(bias), nsamples, _p(gamma), _p(beta), _p(scale_shift),
+        0 if scale_shift is None else scale_shift.stride(0), ss_div, eps, silu, _p(tmp), _p(scratch), _p(out), out.stride(2),
+        _stream()), "xd_conv3x3_groupnorm_bf16_tc")
+    _count(2)
+
+
 @_op("groupnorm_quads(Tensor x, Tensor qstats, Tensor gamma, Tensor beta, Tensor? scale_shift, int ss_div, float eps, "
      "int silu, int nsamples, Tensor(a!) out) -> ()")
 def _groupnorm_quads(x, qstats, gamma, beta, scale_shift, ss_div, eps, silu, nsamples, out):
@@ -734,6 +753,18 @@ def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, fo
         _qs_written(out, slot[2] if emitted else None)
         return out
     _ops.conv3x3(x, xs, wp, bias, act, residual, out, force_bn)
+    return out
+
+
+def conv3x3_groupnorm(x, wp, bias, samples, gamma, beta, scale_shift=None, eps=1e-5, silu=True):
+    """GroupNorm32(conv3x3(x) + bias) [modulated] [SiLU] -> bf16 NHWC; x bf16 NHWC view, ``samples`` statistics units."""
+    nimg, H, W, _ = x.shape
+    co, M = wp.shape[0], nimg * H * W
+    out = torch.empty((nimg, H, W, co), device=x.device, dtype=torch.bfloat16)
+    tmp = torch.empty((M, co), device=x.device, dtype=torch.bfloat16)
+    need = max(M // 32 * (co // 2), samples * 64 * _lib.lib().xd_groupnorm_slabs(samples, M // samples, co))
+    scratch = torch.empty(max(need, 1), device=x.device, dtype=torch.float32)
+    _ops.conv3x3_groupnorm(x, wp, bias, samples, gamma, beta, scale_shift, 1, eps, int(silu), tmp, scratch, out)
     return out
 
 
