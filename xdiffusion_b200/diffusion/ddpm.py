@@ -325,7 +325,13 @@ class _DeviceLoop:
             u = self.uncond[k]
             if torch.is_tensor(v) and torch.is_tensor(u) and v.shape == u.shape and v.dim() > 0 and v.shape[0] == B:
                 out[k] = torch.cat([v, u], 0)
-            elif not torch.is_tensor(v) and not torch.is_tensor(u) and v == u:
+            elif not torch.is_tensor(v) and not torch.is_tensor(u):
+                try:
+                    same = bool(v == u)
+                except Exception:  # noqa: BLE001  (e.g. array-valued entries: keep the two-forward path)
+                    same = False
+                if not same:
+                    return None
                 out[k] = v
             else:
                 return None
