@@ -60,7 +60,8 @@ class ResnetBlockBigGAN(ContextBlock, Packed):
         return self.emb_layers[1].weight, self.emb_layers[1].bias
 
     def forward(self, x, scale_shift, samples, out=None):
-        """x bf16 NHWC [nimg,H,W,Cin] (may be a concat buffer); scale_shift fp32 [samples, 2*Cout] view;
+        """x bf16 NHWC [nimg,H,W,Cin] (may be a concat buffer); scale_shift fp32 [samples, 2*Cout] view (or a callable
+        returning it, resolved after the first convolution has been launched);
         ``samples`` = number of GroupNorm statistics units (B; frames of a clip share statistics)."""
         c1, c2, skip = self.in_layers[2], self.out_layers[3], self.skip_connection
         has_skip = not isinstance(skip, torch.nn.Identity)
@@ -70,12 +71,17 @@ class ResnetBlockBigGAN(ContextBlock, Packed):
             (c2.bias + skip.bias).detach().float() if has_skip else None))
         g1, g2 = self.in_layers[0], self.out_layers[0]
         h = ops.groupnorm(_as_samples(x, samples), g1.weight, g1.bias, eps=g1.eps, silu=True).view(x.shape)
+        late = callable(scale_shift)             # conditioning branch on a side stream: join as late as possible
+        if late and (ops.MATMUL_BACKEND == "tc" and CONV_GN_FUSED and self.out_channels % 128 == 0):
+            scale_shift, late = scale_shift(), False
         if ops.MATMUL_BACKEND == "tc" and CONV_GN_FUSED and self.out_channels % 128 == 0:
             # first conv + the GroupNorm that consumes it as one library call (split-K reduce that normalises at the low
             # resolutions, statistics from the conv epilogue at the high ones: include/xdb200.h)
             h = ops.conv3x3_groupnorm(h, w1, c1.bias, samples, g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps)
         else:
             h = ops.conv3x3(h, w1, c1.bias, qstats=True)
+            if late:
+                scale_shift = scale_shift()
             h = ops.groupnorm(_as_samples(h, samples), g2.weight, g2.bias, scale_shift=scale_shift, eps=g2.eps,
                               silu=True).view(h.shape)
         if has_skip:

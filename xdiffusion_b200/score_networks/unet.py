@@ -144,20 +144,35 @@ class Unet(torch.nn.Module, Packed):
                     torch.cat([b.detach().float() for _, b in lins], 0), offs)
         return self.packed("emb_all", params, build)
 
-    def _block_embeddings(self, temb):
-        """[scale | shift] of every resblock from ONE GEMM over SiLU(temb)."""
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            object.__setattr__(self, "_side", st)
+        return st
+
+    def _block_embeddings(self, temb, main):
+        """[scale | shift] of every resblock from ONE GEMM over SiLU(temb).  Runs on the conditioning (side) stream; the
+        accessor makes ``main`` wait for the rows the first time a block asks for them."""
         w, b, offs = self._emb_all()
         st = torch.empty(temb.shape, device=temb.device, dtype=torch.bfloat16)
         torch.ops.xdb200.act_cast(temb.contiguous(), ops.ACT_SILU, st)
         emb = ops.linear(st, w, b, out_dtype=torch.float32)
-        return lambda blk: emb[:, offs[id(blk)][0]: offs[id(blk)][0] + offs[id(blk)][1]]
+        ready = [torch.cuda.Event()]
+        ready[0].record(torch.cuda.current_stream(temb.device))
+
+        def emb_of(blk):
+            if ready:
+                main.wait_event(ready.pop())
+            return emb[:, offs[id(blk)][0]: offs[id(blk)][0] + offs[id(blk)][1]]
+        return emb_of
 
     def _run_entry(self, entry, h, emb_of, samples, frames, out, context=None):
         mods = list(entry)
         for j, layer in enumerate(mods):
             dst = out if j == len(mods) - 1 else None
             if isinstance(layer, ResnetBlockBigGAN):
-                h = layer(h, emb_of(layer), samples, out=dst)
+                h = layer(h, (lambda blk=layer: emb_of(blk)), samples, out=dst)      # resolved right before the block's second GroupNorm
             elif isinstance(layer, (Downsample, Upsample)):
                 h = layer(h, out=dst)
             else:
@@ -171,10 +186,16 @@ class Unet(torch.nn.Module, Packed):
     def _forward(self, x, context: Dict):
         context = context.copy()
         context["x"] = x
-        for ct in self._context_transformers:
-            context = ct(context, device=x.device)
-        temb = context["timestep_embedding"]
-        emb_of = self._block_embeddings(temb)
+        # The conditioning branch (timestep / text embeddings, the resblocks' [scale | shift] rows) does not depend on the
+        # activations: it runs on a side stream (a fork in the captured graph) next to the first convolution; the first block
+        # that asks for its rows joins it, and everything the branch wrote into ``context`` is ordered before that point.
+        main, side = torch.cuda.current_stream(x.device), self._side_stream(x.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for ct in self._context_transformers:
+                context = ct(context, device=x.device)
+            temb = context["timestep_embedding"]
+            emb_of = self._block_embeddings(temb, main)
         samples = x.shape[0]
         x4, frames = self._to_nhwc_in(x)
         nimg, _, H, W = x4.shape

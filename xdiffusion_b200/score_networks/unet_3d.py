@@ -53,31 +53,22 @@ class Unet(Unet2D):
             return fn(h, frames, out=out)
         return fn(h, out=out)
 
-    def _side_stream(self, device):
-        st = getattr(self, "_side", None)
-        if st is None or st.device != device:
-            st = torch.cuda.Stream(device=device)
-            object.__setattr__(self, "_side", st)
-        return st
-
-    def _block_embeddings(self, temb):
+    def _block_embeddings(self, temb, main):
         """[scale | shift] of every resblock.  The embedding Mlp stacks (2 small GEMMs per block, 44 launches of ~7 us per
-        forward) depend on the timestep embedding only, so they all run up front on a side stream (a fork in the captured
-        graph) while the main stream starts on the convolutions; a block waits for its own event just before it needs the
-        rows (blocks are visited in registration order, so the last wait also joins the side stream)."""
+        forward) depend on the timestep embedding only, so they all run up front on the conditioning (side) stream while
+        ``main`` starts on the convolutions; a block waits for its own event just before it needs the rows (blocks are
+        visited in registration order, so the last wait also joins the side stream)."""
         dev = temb.device
-        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        side = torch.cuda.current_stream(dev)
         tb = torch.empty(temb.shape, device=dev, dtype=torch.bfloat16)
         torch.ops.xdb200.act_cast(temb.contiguous(), ops.ACT_NONE, tb)
         blocks = [m for m in self.modules() if isinstance(m, ResnetBlockBigGAN3D)]
         cache, events = {}, {}
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            for blk in blocks:
-                cache[id(blk)] = blk.embedding(tb)              # kept alive until the forward returns
-                ev = torch.cuda.Event()
-                ev.record(side)
-                events[id(blk)] = ev
+        for blk in blocks:
+            cache[id(blk)] = blk.embedding(tb)                  # kept alive until the forward returns
+            ev = torch.cuda.Event()
+            ev.record(side)
+            events[id(blk)] = ev
 
         def emb_of(blk):
             ev = events.pop(id(blk), None)
