@@ -133,27 +133,35 @@ class PixArtAlpha(torch.nn.Module, Packed):
         kvs = context.get(self.KV_KEY)
         if kvs is None and "context_key" in self._config:
             kvs = self._compute_kv(context)
-        for ct in self._context_transformers:
-            if not isinstance(ct, ContextProjection):
-                context = ct(context=context, device=x.device)
-        t = context["timestep_embedding"].contiguous()                    # fp32 [B, D]
         B, D, T = x.shape[0], self.hidden_size, self.x_embedder.num_patches
         depth = len(self.blocks)
+        # Two independent branches before the first block, as in the DiT: (a) conditioning -> adaLN-single rows on a side
+        # stream (a fork / join in the captured graph), (b) patch embedding on the main stream.
+        main, side = torch.cuda.current_stream(x.device), _dit.DiT._side_stream(self, x.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for ct in self._context_transformers:
+                if not isinstance(ct, ContextProjection):
+                    context = ct(context=context, device=x.device)
+            t = context["timestep_embedding"].contiguous()                    # fp32 [B, D]
+            silu_t = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
+            torch.ops.xdb200.act_cast(t, ops.ACT_SILU, silu_t)
+            # adaLN-single: mod[n] = scale_shift_table[n] + t_block(t), six [B, D] slices per block.  A seventh slice of
+            # exact ones rides along (zero weight rows, bias 1, zero table entries): the gate of the ungated cross-attention
+            # residual for the fused kernel, at the same row pitch as the other slices and without a launch of its own.
+            w_t, b_t = self.packed("t_block", (self.t_block[1].weight, self.t_block[1].bias), lambda: (
+                torch.cat([bf16_weight(self.t_block[1].weight), torch.zeros((D, D), device=x.device, dtype=torch.bfloat16)], 0),
+                torch.cat([self.t_block[1].bias.detach().float(), torch.ones(D, device=x.device)], 0)))
+            t0 = ops.linear(silu_t, w_t, b_t, out_dtype=torch.float32)                        # [B, 7D]
+            tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.cat(
+                [torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float(),
+                 torch.zeros((depth, D), device=x.device)], 1).contiguous())
+            mod = torch.empty((depth, B, 7 * D), device=x.device, dtype=torch.float32)
+            torch.ops.xdb200.add_table(t0, tables, mod)                   # table + t0 for all blocks
+            fmod = torch.empty((2, B, D), device=x.device, dtype=torch.float32)
+            torch.ops.xdb200.add_table(t, self.final_layer.scale_shift_table.detach().float().contiguous(), fmod)
         h = self.x_embedder(x, self.pos_embed[0])                         # fp32 [B*T, D]
-        silu_t = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
-        torch.ops.xdb200.act_cast(t, ops.ACT_SILU, silu_t)
-        # adaLN-single: mod[n] = scale_shift_table[n] + t_block(t), six [B, D] slices per block.  A seventh slice of exact
-        # ones rides along (zero weight rows, bias 1, zero table entries): the gate of the ungated cross-attention residual
-        # for the fused kernel, at the same row pitch as the other slices and without a launch of its own.
-        w_t, b_t = self.packed("t_block", (self.t_block[1].weight, self.t_block[1].bias), lambda: (
-            torch.cat([bf16_weight(self.t_block[1].weight), torch.zeros((D, D), device=x.device, dtype=torch.bfloat16)], 0),
-            torch.cat([self.t_block[1].bias.detach().float(), torch.ones(D, device=x.device)], 0)))
-        t0 = ops.linear(silu_t, w_t, b_t, out_dtype=torch.float32)                            # [B, 7D]
-        tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.cat(
-            [torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float(),
-             torch.zeros((depth, D), device=x.device)], 1).contiguous())
-        mod = torch.empty((depth, B, 7 * D), device=x.device, dtype=torch.float32)
-        torch.ops.xdb200.add_table(t0, tables, mod)                       # table + t0 for all blocks
+        main.wait_stream(side)
         fused = (_dit.FUSED_BLOCK and kvs is not None and D == 384 and T == 16 and self.num_heads * 64 == D
                  and ops.MATMUL_BACKEND == "tc" and self.blocks[0].mlp.act == ops.ACT_GELU
                  and self.blocks[0].mlp.fc1.out_features == 4 * D)
@@ -186,8 +194,6 @@ class PixArtAlpha(torch.nn.Module, Packed):
                 blk.cross_attn(hb, T, kvs[n], residual=h, out=h)          # x += cross_attn(x, y): no norm, no gate
             a = ops.layernorm_modulate(h, s2, sc2, T)
             blk.mlp(a, gate=g2, gate_rows=T, residual=h, out=h)
-        fmod = torch.empty((2, B, D), device=x.device, dtype=torch.float32)
-        torch.ops.xdb200.add_table(t, self.final_layer.scale_shift_table.detach().float().contiguous(), fmod)
         a = ops.layernorm_modulate(h, fmod[0], fmod[1], T)
         w_lin = self.packed("final", (self.final_layer.linear.weight,),
                             lambda: bf16_weight(self.final_layer.linear.weight))
