@@ -185,6 +185,13 @@ int xd_groupnorm_fused(const void* x, long long ld, int nsamples, int P, int C, 
                        const float* beta, const float* scale_shift, long long ss_ld, int ss_div, float eps,
                        int silu, void* out, long long ldo, void* stream);
 
+/* GroupNorm(32 groups) over the F frames of every (clip, pixel) sample -- rows ordered (clip, frame, pixel), sample rows at
+ * stride HW -- with the split bf16 output [hi(C) | lo(C)] of xd_groupnorm_apply(split = 1): the normalisation in front of the
+ * temporal attention's split-precision qkv projection (layers/attention.py:551-600: GroupNorm on the "(b h w) c f" view), one
+ * pass, one warp per sample (a lane's C / 32 channels are one group).  Returns -1 for C other than 128 / 256 or F > 16. */
+int xd_groupnorm_frames_split(const void* x, long long ld, int B, int F, int HW, int C, const float* gamma,
+                              const float* beta, float eps, void* out, long long ldo, void* stream);
+
 /* out(bf16)[m,:] = LayerNorm(x[m,:]; no affine) * (1 + scale[r,:]) + shift[r,:], r = (m / rows_per_mod)*mod_ld.
  * (score_networks/dit.py:16-17,46-51,70-72; pixart.py:20-21,82-92) */
 int xd_layernorm_modulate(const float* x, long long ld, int M, int D, const float* shift, const float* scale,

@@ -352,6 +352,30 @@ def test_groupnorm(ops, ns, P, C):
     assert rel_l2(out.permute(0, 2, 1), ref2) < 3e-3
 
 
+@pytest.mark.parametrize("B,F,HW,C", [(2, 16, 64, 128), (3, 16, 16, 256), (1, 8, 256, 128)])
+def test_groupnorm_over_frames_split_output(ops, B, F, HW, C):
+    """xd_groupnorm_frames_split (one warp per (clip, pixel) sample) against torch GroupNorm on the reference's "(b h w) c f"
+    view; hi + lo reproduces the fp32 result to 2^-16, and the generic two-kernel path agrees."""
+    from xdiffusion_b200 import _lib
+    g = torch.Generator().manual_seed(B + F + HW + C)
+    x = bf(torch.randn(B * F * HW, C, generator=g) * 1.5 + 0.3)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    xs = x.float().view(B, F, HW, C).permute(0, 2, 3, 1).reshape(B * HW, C, F)
+    ref = F_gn(xs, gamma, beta).view(B, HW, C, F).permute(0, 3, 1, 2).reshape(B * F * HW, C)
+    out = torch.empty(B * F * HW, 2 * C, dtype=torch.bfloat16, device=DEV)
+    assert torch.ops.xdb200.groupnorm_frames_split(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, B, F, HW, out) == 1
+    got = out[:, :C].float() + out[:, C:].float()
+    assert rel_l2(got, ref) < 2e-5, rel_l2(got, ref)
+    two = torch.empty_like(out)
+    stats = torch.empty(B * HW * 64 * _lib.lib().xd_groupnorm_slabs(B * HW, F, C), device=DEV)
+    torch.ops.xdb200.groupnorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), None, 1, 1e-5, 0, HW, B * HW, 1, stats, two)
+    assert rel_l2(got, two[:, :C].float() + two[:, C:].float()) < 2e-5
+
+
+def F_gn(x, gamma, beta):
+    return F.group_norm(x, 32, gamma, beta, 1e-5)
+
+
 def test_layernorm_modulate(ops):
     g = torch.Generator().manual_seed(3)
     B, T, D = 5, 16, 384

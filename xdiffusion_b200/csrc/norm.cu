@@ -186,6 +186,74 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int P, int C, int G, c
 }
 
 
+// ----------------------------------------------------------------------------- GroupNorm over (C / 32 x F) per pixel
+// The temporal attention of the video UNet normalises every pixel of every clip over its F frames (samples (clip, pixel),
+// rows = frames, row stride HW * ld) and feeds a split-precision GEMM (out row = [hi(C) | lo(C)]).  One WARP per sample,
+// a lane owns C / 32 consecutive channels = exactly one group, so the statistics never leave the lane: one pass, one
+// launch (the generic path is xd_groupnorm_stats + xd_groupnorm_apply: two launches and a second read).
+template <int CPL>       // channels per lane: 4 (C = 128) or 8 (C = 256)
+__global__ void __launch_bounds__(256)
+gn_frames_kernel(const bf16* __restrict__ x, long long ld, int B, int F, int HW, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, bf16* __restrict__ out, long long ldo) {
+    pdl_prologue();
+    constexpr int C = 32 * CPL, MAXF = 16;
+    const int lane = threadIdx.x & 31;
+    const long long s = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= (long long)B * HW) return;
+    const long long b = s / HW, pix = s - b * HW;
+    const bf16* xp = x + (b * F * HW + pix) * ld + lane * CPL;
+    bf16* op = out + (b * F * HW + pix) * ldo + lane * CPL;
+    float v[MAXF][CPL];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) {
+        if (f < F) {
+            if constexpr (CPL == 8) {
+                unpack8(*reinterpret_cast<const bf16x8*>(xp + (long long)f * HW * ld), v[f]);
+            } else {
+                const uint2 t = *reinterpret_cast<const uint2*>(xp + (long long)f * HW * ld);
+                const float2 a = bf2_to_f2(t.x), c = bf2_to_f2(t.y);
+                v[f][0] = a.x; v[f][1] = a.y; v[f][2] = c.x; v[f][3] = c.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) {
+        if (f < F) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) { sum += v[f][k]; sq = fmaf(v[f][k], v[f][k], sq); }
+        }
+    }
+    const float inv_cnt = 1.0f / ((float)F * (float)CPL);
+    const float mean = sum * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(sq * inv_cnt - mean * mean, 0.f) + eps);
+    float a[CPL], bb[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        a[k] = rstd * __ldg(gamma + lane * CPL + k);
+        bb[k] = __ldg(beta + lane * CPL + k) - mean * a[k];
+    }
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) {
+        if (f < F) {
+            float y[CPL], lo[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                y[k] = fmaf(v[f][k], a[k], bb[k]);
+                lo[k] = y[k] - __bfloat162float(__float2bfloat16_rn(y[k]));
+            }
+            bf16* row = op + (long long)f * HW * ldo;
+            if constexpr (CPL == 8) {
+                *reinterpret_cast<bf16x8*>(row) = pack8(y);
+                *reinterpret_cast<bf16x8*>(row + C) = pack8(lo);
+            } else {
+                *reinterpret_cast<uint2*>(row) = make_uint2(f2_to_bf2(y[0], y[1]), f2_to_bf2(y[2], y[3]));
+                *reinterpret_cast<uint2*>(row + C) = make_uint2(f2_to_bf2(lo[0], lo[1]), f2_to_bf2(lo[2], lo[3]));
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- fused GroupNorm (cluster)
 // One thread-block CLUSTER per sample: each CTA keeps its slab of pixels in shared memory, the 32 group
 // statistics are reduced across the cluster through distributed shared memory, and the slab is
@@ -508,6 +576,20 @@ extern "C" int xd_groupnorm_apply_quads(const void* x, long long ld, int nsample
     slabs = std::max(1, std::min(slabs, P / 32));
     xd_launch(gn_apply_quads_kernel, dim3(slabs, nsamples), threads, smem, (cudaStream_t)stream, (const bf16*)x, ld, P, C,
               groups, qstats, qstats_ld, gamma, beta, scale_shift, ss_ld, ss_div > 0 ? ss_div : 1, eps, silu, (bf16*)out, ldo);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+// GroupNorm(32 groups) over the F frames of every (clip, pixel) sample, split bf16 output [hi(C) | lo(C)]; rows ordered
+// (clip, frame, pixel).  Returns -1 (and does nothing) for shapes the one-warp-per-sample kernel does not cover (C other than
+// 128 / 256, F > 16): the caller then uses xd_groupnorm_stats + xd_groupnorm_apply with inner = HW, split = 1.
+extern "C" int xd_groupnorm_frames_split(const void* x, long long ld, int B, int F, int HW, int C, const float* gamma,
+                                         const float* beta, float eps, void* out, long long ldo, void* stream) {
+    XD_CHECK_ARG(x && gamma && beta && out && B > 0 && F > 0 && HW > 0);
+    if ((C != 128 && C != 256) || F > 16 || ld % 8 != 0 || ldo % 8 != 0) return -1;
+    const unsigned grid = (unsigned)(((long long)B * HW + 7) / 8);
+    if (C == 128) xd_launch(gn_frames_kernel<4>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, B, F, HW, gamma, beta, eps, (bf16*)out, ldo);
+    else xd_launch(gn_frames_kernel<8>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, B, F, HW, gamma, beta, eps, (bf16*)out, ldo);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

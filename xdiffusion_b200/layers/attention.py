@@ -308,10 +308,11 @@ class TemporalSelfAttention(ContextBlock, Packed):
         # GroupNorm over (C/32 x F) for every pixel of every clip: samples (b, hw), rows = frames
         rows = x.as_strided((nimg * HW, C), (x.stride(2), 1))
         n = torch.empty((nimg * HW, 2 * C), device=x.device, dtype=torch.bfloat16)        # [hi | lo]
-        stats = torch.empty(B * HW * 64 * _lib.lib().xd_groupnorm_slabs(B * HW, F, C), device=x.device,
-                            dtype=torch.float32)
-        torch.ops.xdb200.groupnorm(rows, self._norm.weight, self._norm.bias, None, 1, self._norm.eps, 0, HW, B * HW,
-                                   1, stats, n)
+        if not torch.ops.xdb200.groupnorm_frames_split(rows, self._norm.weight, self._norm.bias, self._norm.eps, B, F, HW, n):
+            stats = torch.empty(B * HW * 64 * _lib.lib().xd_groupnorm_slabs(B * HW, F, C), device=x.device,
+                                dtype=torch.float32)
+            torch.ops.xdb200.groupnorm(rows, self._norm.weight, self._norm.bias, None, 1, self._norm.eps, 0, HW, B * HW,
+                                       1, stats, n)
         qkv = ops.linear(n, wq3, self._qkv.bias, out_dtype=torch.float32, a2=n[:, :C])    # rows (b, f, hw) x 3C
         a = torch.empty((nimg * HW, C), device=x.device, dtype=torch.bfloat16)
         # ONE launch for all clips: kernel batch = clip, kernel "head" index = (pixel, head) -- the (pixel, head) pair has a

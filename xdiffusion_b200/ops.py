@@ -463,6 +463,22 @@ def _groupnorm(x, gamma, beta, scale_shift, ss_div, eps, silu, inner, nsamples, 
     _count(3)
 
 
+@_op("groupnorm_frames_split(Tensor x, Tensor gamma, Tensor beta, float eps, int B, int F, int HW, Tensor(a!) out) -> int")
+def _groupnorm_frames_split(x, gamma, beta, eps, B, F, HW, out):
+    """x bf16 [B*F*HW, C] rows (clip, frame, pixel) -> out bf16 [B*F*HW, 2C] = [hi | lo] of the per-pixel GroupNorm over
+    frames; returns 0 when the shape is not covered by the one-pass kernel (nothing written)."""
+    _cuda(x, gamma, beta, out)
+    rows, C = x.shape
+    assert rows == B * F * HW and x.stride(1) == 1 and out.stride(1) == 1 and out.shape == (rows, 2 * C)
+    rc = _lib.lib().xd_groupnorm_frames_split(_p(x), x.stride(0), B, F, HW, C, _p(gamma), _p(beta), eps, _p(out),
+                                              out.stride(0), _stream())
+    if rc == -1:
+        return 0
+    _lib.check(rc, "xd_groupnorm_frames_split")
+    _count()
+    return 1
+
+
 @_op("layernorm_modulate(Tensor x, Tensor? shift, Tensor? scale, int rows_per_mod, float eps, Tensor(a!) out) -> ()")
 def _layernorm_modulate(x, shift, scale, rows_per_mod, eps, out):
     _cuda(x, shift, scale, out)
