@@ -4,6 +4,7 @@
 // (C_out tiny, fp32 NCHW out), which are bandwidth-bound and not GEMM-shaped.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -282,6 +283,128 @@ conv3x3_out1_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, 
     }
 }
 
+// ---- sliding-window variants (W * C / 8 <= 512 threads): a thread owns one image column and walks down the rows of its
+// band with a 3 x 3 window in registers, so an output costs 3 new loads instead of 9 clamped ones (the band kernels above
+// spend ~430 / ~250 instructions per (pixel, 8 channels), most of them on addressing: profiles/README.md).
+__global__ void __launch_bounds__(512)
+conv3x3_in1_slide_kernel(const float* __restrict__ x, int nimg, int H, int W, const float* __restrict__ w,
+                         const float* __restrict__ bias, int Cout, bf16* __restrict__ out, long long ldo, int band) {
+    pdl_prologue();
+    const int cg = Cout >> 3;
+    const int g = threadIdx.x % cg, xx = threadIdx.x / cg;
+    float wr[9][8], br[8];
+    {
+        float flat[72];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(w + g * 72) + i);
+            flat[4 * i] = t.x; flat[4 * i + 1] = t.y; flat[4 * i + 2] = t.z; flat[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            br[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) wr[tap][j] = flat[j * 9 + tap];
+        }
+    }
+    const int bands = (H + band - 1) / band;
+    const int img = blockIdx.x / bands, y0 = (blockIdx.x - img * bands) * band, y1 = min(H, y0 + band);
+    const float* xp = x + (long long)img * H * W;
+    bf16* op = out + (long long)img * H * W * ldo + g * 8;
+    const bool has_l = xx > 0, has_r = xx + 1 < W;
+    auto load_row = [&](int y, float (&r)[3]) {
+        const bool ok = y >= 0 && y < H;
+        const float* row = xp + min(max(y, 0), H - 1) * W + xx;
+        r[0] = ok && has_l ? __ldg(row - 1) : 0.f;
+        r[1] = ok ? __ldg(row) : 0.f;
+        r[2] = ok && has_r ? __ldg(row + 1) : 0.f;
+    };
+    float top[3], mid[3], bot[3];
+    load_row(y0 - 1, top);
+    load_row(y0, mid);
+    for (int y = y0; y < y1; ++y) {
+        load_row(y + 1, bot);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(top[k], wr[k][j], acc[j]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(mid[k], wr[3 + k][j], acc[j]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(bot[k], wr[6 + k][j], acc[j]);
+        *reinterpret_cast<bf16x8*>(op + (long long)(y * W + xx) * ldo) = pack8(acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
+    }
+}
+
+__global__ void __launch_bounds__(512)
+conv3x3_out1_slide_kernel(const bf16* __restrict__ X, long long ldx, int nimg, int H, int W, int C,
+                          const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int band) {
+    pdl_prologue();
+    const int lpp = C >> 3;
+    const int g = threadIdx.x % lpp, xx = threadIdx.x / lpp;
+    float wr[9][8];
+    {
+        float flat[72];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(w + g * 72) + i);
+            flat[4 * i] = t.x; flat[4 * i + 1] = t.y; flat[4 * i + 2] = t.z; flat[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[tap][j] = flat[j * 9 + tap];
+    }
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    const int bands = (H + band - 1) / band;
+    const int img = blockIdx.x / bands, y0 = (blockIdx.x - img * bands) * band, y1 = min(H, y0 + band);
+    const bf16* xp = X + (long long)img * H * W * ldx + g * 8;
+    float* op = out + (long long)img * H * W;
+    const bool has_l = xx > 0, has_r = xx + 1 < W;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    auto load_row = [&](int y, uint4 (&r)[3]) {
+        const bool ok = y >= 0 && y < H;
+        const bf16* row = xp + (long long)(min(max(y, 0), H - 1) * W + xx) * ldx;
+        r[0] = ok && has_l ? *reinterpret_cast<const uint4*>(row - ldx) : zero;
+        r[1] = ok ? *reinterpret_cast<const uint4*>(row) : zero;
+        r[2] = ok && has_r ? *reinterpret_cast<const uint4*>(row + ldx) : zero;
+    };
+    auto dot8 = [](const uint4& v, const float (&ww)[8], float acc) {
+        float2 t;
+        t = bf2_to_f2(v.x); acc = fmaf(t.x, ww[0], acc); acc = fmaf(t.y, ww[1], acc);
+        t = bf2_to_f2(v.y); acc = fmaf(t.x, ww[2], acc); acc = fmaf(t.y, ww[3], acc);
+        t = bf2_to_f2(v.z); acc = fmaf(t.x, ww[4], acc); acc = fmaf(t.y, ww[5], acc);
+        t = bf2_to_f2(v.w); acc = fmaf(t.x, ww[6], acc); acc = fmaf(t.y, ww[7], acc);
+        return acc;
+    };
+    uint4 top[3], mid[3], bot[3];
+    load_row(y0 - 1, top);
+    load_row(y0, mid);
+    for (int y = y0; y < y1; ++y) {
+        load_row(y + 1, bot);
+        float acc = 0.f;                          // same order as the band kernel: taps 0..8, 8 channels each
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = dot8(top[k], wr[k], acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = dot8(mid[k], wr[3 + k], acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = dot8(bot[k], wr[6 + k], acc);
+        for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0) op[y * W + xx] = acc + b0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
+    }
+}
+
 }  // namespace
 
 extern "C" int xd_gemm_bf16_simt(const void* A, long long lda, const void* A2, long long lda2, int K2, const void* Wt,
@@ -314,6 +437,16 @@ extern "C" int xd_conv3x3_bf16_simt(const void* X, long long ldx, int nimg, int 
 extern "C" int xd_conv3x3_in_f32_nchw(const float* x, int nimg, int Cin, int H, int W, const float* w,
                                       const float* bias, int Cout, void* out, long long ldo, void* stream) {
     XD_CHECK_ARG(x && w && out && Cout % 8 == 0 && ldo % 8 == 0);
+    static const bool slide = getenv("XDB200_CONV_SLIDE") == nullptr || atoi(getenv("XDB200_CONV_SLIDE")) != 0;
+    if (slide && Cin == 1 && W * (Cout / 8) <= 512 && (W * (Cout / 8)) % 32 == 0 && (long long)H * W < (1LL << 30) &&
+        (reinterpret_cast<uintptr_t>(w) & 15) == 0) {                                 // sliding window: thread = (column, 8 channels)
+        int band = H;
+        while (band > 4 && (long long)nimg * ((H + band - 1) / band) < 148) band = (band + 1) / 2;
+        const unsigned grid = (unsigned)(nimg * ((H + band - 1) / band));
+        xd_launch(conv3x3_in1_slide_kernel, grid, W * (Cout / 8), 0, (cudaStream_t)stream, x, nimg, H, W, w, bias, Cout, (bf16*)out, ldo, band);
+        XD_CHECK_LAUNCH();
+        return XD_OK;
+    }
     if (Cin == 1 && 256 % (Cout / 8) == 0 && (long long)H * W < (1LL << 30) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {       // register-weight kernel, one band of rows per CTA
         int band = H;
         while (band > 1 && (long long)nimg * ((H + band - 1) / band) < 2 * 148) band = (band + 1) / 2;
@@ -336,6 +469,16 @@ extern "C" int xd_conv3x3_out_f32_nchw(const void* X, long long ldx, int nimg, i
     XD_CHECK_ARG(X && w && out && C % 8 == 0 && ldx % 8 == 0);
     const int lpp = C / 8;
     XD_CHECK_ARG(lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0);
+    static const bool slide = getenv("XDB200_CONV_SLIDE") == nullptr || atoi(getenv("XDB200_CONV_SLIDE")) != 0;
+    if (slide && Cout == 1 && W * lpp <= 512 && (W * lpp) % 32 == 0 && (long long)H * W * ldx < (1LL << 31) &&
+        (reinterpret_cast<uintptr_t>(w) & 15) == 0) {                                 // sliding window: thread = (column, 8 channels)
+        int band = H;
+        while (band > 4 && (long long)nimg * ((H + band - 1) / band) < 148) band = (band + 1) / 2;
+        const unsigned grid = (unsigned)(nimg * ((H + band - 1) / band));
+        xd_launch(conv3x3_out1_slide_kernel, grid, W * lpp, 0, (cudaStream_t)stream, (const bf16*)X, ldx, nimg, H, W, C, w, bias, out, band);
+        XD_CHECK_LAUNCH();
+        return XD_OK;
+    }
     if (Cout == 1 && (long long)H * W * ldx < (1LL << 31) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {                          // register-weight kernel, one band of rows per CTA
         int band = H;
         while (band > 2 && (long long)nimg * ((H + band - 1) / band) < 2 * 148) band = (band + 1) / 2;

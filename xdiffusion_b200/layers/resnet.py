@@ -121,7 +121,7 @@ class Upsample(torch.nn.Module, Packed):
         nimg, H, W, C = x.shape
         up = out if out is not None and not self.use_conv else \
             torch.empty((nimg, H * 2, W * 2, C), device=x.device, dtype=torch.bfloat16)
-        torch.ops.xdb200.upsample2x(x, up)
+        ops.upsample2x(x, up)
         if not self.use_conv:
             return up
         w = self.packed("w", (self.conv.weight,), lambda: pack_conv3x3(self.conv.weight))

@@ -772,6 +772,23 @@ def conv3x3(x, wp, bias=None, act=ACT_NONE, residual=None, xs=None, out=None, fo
     return out
 
 
+def upsample2x(x, out):
+    """Nearest x2 over (H, W) of an NHWC view.  Inside ``quad_stats()``: an upsampled tensor has exactly four times the sums
+    of its source, so when the source's producers emitted their quad statistics the table of ``out`` is filled by replicating
+    every source block four times (only per-sample totals are ever read) and the GroupNorm over ``out`` needs no statistics
+    pass either.  Images must be whole 32-row blocks."""
+    _ops.upsample2x(x, out)
+    if _qs_book is None or (x.shape[1] * x.shape[2]) % 32:
+        return out
+    src = _qs_lookup(x)
+    slot = _qs_slot(out) if src is not None else None
+    if slot is not None:
+        e, view, rng = slot
+        view.unflatten(0, (src.shape[0], 4)).copy_(src.unsqueeze(1).expand(-1, 4, -1, -1))
+        _qs_written(out, rng)
+    return out
+
+
 def conv3x3_groupnorm(x, wp, bias, samples, gamma, beta, scale_shift=None, eps=1e-5, silu=True):
     """GroupNorm32(conv3x3(x) + bias) [modulated] [SiLU] -> bf16 NHWC; x bf16 NHWC view, ``samples`` statistics units."""
     nimg, H, W, _ = x.shape
