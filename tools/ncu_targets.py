@@ -117,6 +117,24 @@ qkvw = bf(64, 256, 3, 1, 256)                                       # EDM DDPM++
 qw, kw, vw = (qkvw[:, :, i].permute(0, 2, 1, 3) for i in range(3))
 targets.append(("r2b attention wide head (EDM, d=256, T=256)", lambda: ops.attention(qw, kw, vw, 1 / 16)))
 
+# ---- end of round 2 ("r2c ..."): temporal attention on mma.sync, per-pixel GroupNorm over frames, sliding-window first / last conv
+Bc, Fr, HWv, Cv, Hh = 8, 16, 1024, 128, 2                         # video UNet 32 x 32 level: 8 clips x 16 frames, 2 heads
+qkv_t = torch.randn(Bc * Fr * HWv, 3 * Cv, device=dev) * 0.5
+relk = torch.randn(Hh, 2 * Fr - 1, 64, device=dev) / 8
+a_t = torch.empty(Bc * Fr * HWv, Cv, device=dev, dtype=torch.bfloat16)
+C3 = 3 * Cv
+qt, kt, vt = (qkv_t.as_strided((Bc, HWv * Hh, Fr, 64), (Fr * HWv * C3, 192, HWv * C3, 1), i * 64) for i in range(3))
+ot = a_t.as_strided((Bc, HWv * Hh, Fr, 64), (Fr * HWv * Cv, 64, HWv * Cv, 1))
+targets.append(("r2c temporal rel-pos attention (split-precision mma.sync)", lambda: ops.attention(
+    qt, kt, vt, 1.0, out=ot, relk=relk, scramble=True, o_cs=1, hpg=Hh, o_gs=Cv)))
+xv = bf(Bc * Fr * HWv, Cv)
+gv, bv = torch.randn(Cv, device=dev), torch.randn(Cv, device=dev)
+nv = torch.empty(Bc * Fr * HWv, 2 * Cv, device=dev, dtype=torch.bfloat16)
+targets.append(("r2c groupnorm over frames (split output)", lambda: torch.ops.xdb200.groupnorm_frames_split(
+    xv, gv, bv, 1e-5, Bc, Fr, HWv, nv)))
+targets.append(("r2c conv3x3_in 1->128 (sliding window)", lambda: torch.ops.xdb200.conv3x3_in(x1, w_in, b_in, o_in)))
+targets.append(("r2c conv3x3_out 128->1 (sliding window)", lambda: torch.ops.xdb200.conv3x3_out(h_out, w_out, None, o_out)))
+
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 targets = [(n, f) for n, f in targets if only in n]
 for name, fn in targets:
