@@ -206,6 +206,11 @@ int xd_act_cast(const void* in, int in_dtype, void* out, int out_dtype, int act,
 /* c = table[labels] + temb (DiTCombineEmbeddngs, layers/embedding.py:371-406); silu_out = bf16 SiLU(c). */
 int xd_class_combine(const float* table, const long long* labels, const float* temb, int B, int D, float* c_out,
                      void* silu_out, void* stream);
+/* The same with temb = temb_table[*idx_dev] for every row: the timestep MLP (layers/embedding.py:325-343) depends on the
+ * timestep only, so the sampling loop evaluates it once for all N timesteps when it is built and the per-step conditioning
+ * chain shrinks to this kernel + the adaLN GEMM.  idx_dev: the loop index (int32, device). */
+int xd_class_combine_step(const float* table, const long long* labels, const float* temb_table, const int* idx_dev, int B,
+                          int D, float* c_out, void* silu_out, void* stream);
 /* PatchEmbed im2col (layers/embedding.py:455-457,502-504) and unpatchify (score_networks/dit.py:187-204). */
 int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out_bf16, void* stream);
 int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out, void* stream);

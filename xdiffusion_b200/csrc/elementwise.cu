@@ -70,6 +70,21 @@ __global__ void class_combine_kernel(const float* __restrict__ table, const long
     if (silu_out) silu_out[i] = __float2bfloat16_rn(silu_f(v));
 }
 
+// The same with the timestep embedding taken from a per-loop table: temb = temb_table[*idx] for every row (the sampling
+// loop evaluates the timestep MLP once for all N timesteps when it is built; the loop index lives on the device).
+__global__ void class_combine_step_kernel(const float* __restrict__ table, const long long* __restrict__ labels,
+                                          const float* __restrict__ temb_table, const int* __restrict__ idx, int B, int Dm,
+                                          float* c_out, bf16* silu_out) {
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Dm) return;
+    const int b = i / Dm, d = i % Dm;
+    float v = temb_table[(long long)(*idx) * Dm + d];
+    if (table) v = table[labels[b] * Dm + d] + v;
+    if (c_out) c_out[i] = v;
+    if (silu_out) silu_out[i] = __float2bfloat16_rn(silu_f(v));
+}
+
 // x fp32 NCHW -> bf16 [B*gh*gw, C*p*p], column order (c, py, px) = flattened Conv2d weight
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p, bf16* out) {
     pdl_prologue();
@@ -297,6 +312,15 @@ extern "C" int xd_class_combine(const float* table, const long long* labels, con
     XD_CHECK_ARG(temb && (c_out || silu_out) && (table == nullptr) == (labels == nullptr));
     xd_launch(class_combine_kernel, blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream, table, labels, temb, B, Dm,
                                                                                         c_out, (bf16*)silu_out);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_class_combine_step(const float* table, const long long* labels, const float* temb_table, const int* idx_dev,
+                                     int B, int Dm, float* c_out, void* silu_out, void* stream) {
+    XD_CHECK_ARG(temb_table && idx_dev && (c_out || silu_out) && (table == nullptr) == (labels == nullptr) && B > 0 && Dm > 0);
+    xd_launch(class_combine_step_kernel, blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream, table, labels, temb_table,
+              idx_dev, B, Dm, c_out, (bf16*)silu_out);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

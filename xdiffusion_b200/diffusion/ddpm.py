@@ -16,6 +16,7 @@ import os
 import torch
 
 from .. import ops
+from ..layers.embedding import TIMESTEP_TABLE_KEY
 from ..samplers.base import ReverseProcessSampler
 from ..utils import (DotConfig, get_obj_from_str, instantiate_from_config, normalize_to_neg_one_to_one,
                      unnormalize_to_zero_to_one)
@@ -23,6 +24,8 @@ from ..utils import (DotConfig, get_obj_from_str, instantiate_from_config, norma
 
 # Classifier-free guidance as one forward over [conditional | unconditional] rows instead of two forwards (0 = two forwards)
 CFG_BATCHED = os.environ.get("XDB200_CFG_BATCHED", "1") == "1"
+# The timestep MLP of a DiT evaluated once per loop for all timesteps instead of once per step (0 = per step)
+TIMESTEP_TABLE = os.environ.get("XDB200_TIMESTEP_TABLE", "1") == "1"
 
 
 class PredictionType(Enum):
@@ -306,6 +309,9 @@ class _DeviceLoop:
         self.logsnr_t = torch.empty(self.nrows, dtype=torch.float32, device=dev) if "logsnr_t" in self.tabs else None
         self.logsnr_s = torch.empty(self.nrows, dtype=torch.float32, device=dev) if "logsnr_s" in self.tabs else None
         self.x = torch.empty(shape, dtype=torch.float32, device=dev)
+        # timestep-only part of the conditioning, evaluated once for all N timesteps (score networks that offer it)
+        net = model._score_network
+        self.temb = net.timestep_table(self.tabs["timestep"]) if TIMESTEP_TABLE and hasattr(net, "timestep_table") else None
         self.noise = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # Philox key, read by the step kernel
         self.graph = None
@@ -390,6 +396,8 @@ class _DeviceLoop:
         c = dict(base)
         c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep[:rows], self.idx, self.N
         c["row_offset"] = self.row_offset
+        if self.temb is not None:
+            c[TIMESTEP_TABLE_KEY] = (self.temb[0], self.temb[1], self.idx)
         if self.logsnr_t is not None:
             c["logsnr_t"], c["logsnr_s"] = self.logsnr_t[:rows], self.logsnr_s[:rows]
         return c

@@ -82,11 +82,25 @@ class DiTTimestepEmbedding(torch.nn.Module, Packed):
         freq = self.packed("freq", (l0.weight,), lambda: torch.exp(
             -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(l0.weight.device))
         w0, w2 = self.packed("w", (l0.weight, l2.weight), lambda: (bf16_weight(l0.weight), bf16_weight(l2.weight)))
+        tab = (kwargs.get("context") or {}).get(TIMESTEP_TABLE_KEY)
+        if tab is not None and tab[0] == id(self):       # the sampling loop evaluated this MLP for all of its timesteps
+            return TimestepLookup(tab[1], tab[2], timestep.shape[0])
         if timestep.dtype not in (torch.int64, torch.float32):
             timestep = timestep.float()
         s = _sinusoid(timestep, freq, 0, 1.0, (0, 0), 1)
         h = ops.linear(s, w0, l0.bias, act=ops.ACT_SILU)
         return ops.linear(h, w2, l2.bias, out_dtype=torch.float32)
+
+
+SILU_PREFIX = "_xdb_silu_"
+TIMESTEP_TABLE_KEY = "_xdb_temb_table"      # context entry set by the sampling loop: (id(projection), table [N, D], loop index)
+
+
+class TimestepLookup:
+    """Deferred ``table[loop index]`` broadcast to ``rows`` rows: resolved by DiTCombineEmbeddngs in its one kernel."""
+
+    def __init__(self, table, idx, rows):
+        self.table, self.idx, self.rows = table, idx, rows
 
 
 class LabelLookup:
@@ -124,6 +138,16 @@ class DiTCombineEmbeddngs(torch.nn.Module):
     def forward(self, context: Dict, **kwargs):
         vals = [context[k] for k in self._source_context_keys]
         lookups = [v for v in vals if isinstance(v, LabelLookup) and not v.zero]
+        steps = [v for v in vals if isinstance(v, TimestepLookup)]
+        if len(steps) == 1 and len(lookups) <= 1 and not any(torch.is_tensor(v) for v in vals):
+            t, lk = steps[0], (lookups[0] if lookups else None)
+            c = torch.empty((t.rows, t.table.shape[1]), device=t.table.device, dtype=torch.float32)
+            silu = torch.empty(c.shape, device=c.device, dtype=torch.bfloat16)
+            torch.ops.xdb200.class_combine_step(lk.table if lk else None, lk.labels.contiguous() if lk else None, t.table, t.idx,
+                                                t.rows, c, silu)
+            context[self._output_context_key] = c
+            context[SILU_PREFIX + self._output_context_key] = silu          # bf16 SiLU(c): the input of the adaLN GEMMs
+            return context
         dense = [v for v in vals if torch.is_tensor(v)]
         if len(dense) != 1 or len(lookups) > 1:
             raise NotImplementedError("DiTCombineEmbeddngs: expected one dense embedding (+ one label lookup)")

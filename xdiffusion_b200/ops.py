@@ -528,6 +528,18 @@ def _class_combine(table, labels, temb, c_out, silu_out):
     _count()
 
 
+@_op("class_combine_step(Tensor? table, Tensor? labels, Tensor temb_table, Tensor idx, int B, Tensor(a!)? c_out, "
+     "Tensor(b!)? silu_out) -> ()")
+def _class_combine_step(table, labels, temb_table, idx, B, c_out, silu_out):
+    _cuda(table, labels, temb_table, idx, c_out, silu_out)
+    D = temb_table.shape[1]
+    assert temb_table.is_contiguous() and temb_table.dtype == torch.float32 and idx.dtype == torch.int32
+    assert labels is None or (labels.dtype == torch.int64 and labels.shape[0] == B)
+    _lib.check(_lib.lib().xd_class_combine_step(_p(table), _p(labels), _p(temb_table), _p(idx), B, D, _p(c_out),
+                                                _p(silu_out), _stream()), "xd_class_combine_step")
+    _count()
+
+
 @_op("patchify(Tensor x, int p, Tensor(a!) out) -> ()")
 def _patchify(x, p, out):
     _cuda(x, out)

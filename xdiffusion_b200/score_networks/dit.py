@@ -14,7 +14,7 @@ import torch
 
 from .. import ops
 from ..layers.attention import MultiHeadSelfAttention
-from ..layers.embedding import PatchEmbed
+from ..layers.embedding import SILU_PREFIX, TIMESTEP_TABLE_KEY, DiTTimestepEmbedding, PatchEmbed
 from ..layers.mlp import Mlp
 from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
 from ..utils import instantiate_from_config, instantiate_partial_from_config
@@ -101,6 +101,17 @@ class DiT(torch.nn.Module, Packed):
             torch.nn.init.constant_(lin.bias, 0)
         run_custom_initializers(self)
 
+    def timestep_table(self, timesteps):
+        """(id(projection), table): the timestep MLP for every timestep of a sampling loop, [N, D] fp32 (row = loop index).
+        The loop hands it back through ``context[TIMESTEP_TABLE_KEY]`` with its device-resident loop index, and the per-step
+        conditioning chain (sinusoid, two GEMMs, combine, SiLU cast: five launches) becomes one kernel in front of the
+        adaLN GEMM.  None when the conditioning head is not the plain DiT one."""
+        mods = [m for m in self._projections.values() if isinstance(m, DiTTimestepEmbedding)]
+        if len(mods) != 1 or timesteps.dtype not in (torch.int64, torch.float32):
+            return None
+        with torch.no_grad():
+            return id(mods[0]), mods[0](timesteps.contiguous()).contiguous()
+
     # ------------------------------------------------------------------ kernels
     def _side_stream(self, device):
         st = getattr(self, "_side", None)
@@ -131,8 +142,12 @@ class DiT(torch.nn.Module, Packed):
         with torch.cuda.stream(side):
             for ct in self._context_transformers:
                 context = ct(context, device=x.device)
-            c = context["timestep_embedding"]                          # fp32 [B, D]
-            torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
+            pre = context.get(SILU_PREFIX + "timestep_embedding")     # set when the loop's timestep table is in use
+            if pre is not None:
+                silu_c = pre
+            else:
+                c = context["timestep_embedding"]                      # fp32 [B, D]
+                torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
             ops.linear(silu_c, w_ada, b_ada, out=mod)
         h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
         main.wait_stream(side)
