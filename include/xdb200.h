@@ -77,6 +77,21 @@ int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats
                                long long mod_ld, int rows_per_mod, float eps, const void* Wh, const float* bias, int heads,
                                int M, int D, float sm_scale, void* out, long long ldo, void* stream);
 
+/* The two fused DiT kernels with indirect modulation rows: image i reads row mod_rows[i] (device int32 [M / rows_per_mod]) of
+ * shift / scale / gate instead of row i.  The adaLN modulation of a DiT depends on (timestep, class label) only, so a sampling
+ * loop can evaluate `adaLN_modulation(SiLU(t_emb + y_emb))` (score_networks/dit.py:42-51) once for all N x (classes + 1)
+ * pairs when it is built; per step the images then share at most classes + 1 distinct rows per block (L2-resident) and the
+ * per-step adaLN GEMM with its 113 MB of fp32 output disappears. */
+int xd_dit_ln_qkv_attn_bf16_tc_rows(const float* h, long long ldh, const float* stats, const float* shift, const float* scale,
+                                    long long mod_ld, int rows_per_mod, float eps, const void* Wh, const float* bias,
+                                    int heads, int M, int D, float sm_scale, void* out, long long ldo, const int* mod_rows,
+                                    void* stream);
+int xd_dit_proj_mlp_bf16_tc_rows(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1, const float* b1,
+                                 const void* W2, const float* b2, int hidden, const float* h_in, float* h_out, long long ldh,
+                                 int M, int D, const float* gate1, const float* shift2, const float* scale2,
+                                 const float* gate2, long long mod_ld, int rows_per_mod, float eps, float* stats_out,
+                                 int split, const int* mod_rows, void* stream);
+
 /* Scratch for split-K (fp32 partial tiles of long contractions over few output tiles, e.g. the 8x8 / 4x4 UNet convs).
  * Device pointer, 16-byte aligned, caller-owned; launches that use it must be ordered on one stream.  Optional: without
  * it every contraction runs unsplit. */
@@ -208,9 +223,10 @@ int xd_class_combine(const float* table, const long long* labels, const float* t
                      void* silu_out, void* stream);
 /* The same with temb = temb_table[*idx_dev] for every row: the timestep MLP (layers/embedding.py:325-343) depends on the
  * timestep only, so the sampling loop evaluates it once for all N timesteps when it is built and the per-step conditioning
- * chain shrinks to this kernel + the adaLN GEMM.  idx_dev: the loop index (int32, device). */
+ * chain shrinks to this kernel + the adaLN GEMM.  idx_dev: the loop index (int32, device).  rows_out (optional, int32 [B]):
+ * labels[b] * n_steps + *idx_dev, the row of image b in a (label, step) modulation table (xd_dit_*_rows). */
 int xd_class_combine_step(const float* table, const long long* labels, const float* temb_table, const int* idx_dev, int B,
-                          int D, float* c_out, void* silu_out, void* stream);
+                          int D, float* c_out, void* silu_out, int* rows_out, int n_steps, void* stream);
 /* PatchEmbed im2col (layers/embedding.py:455-457,502-504) and unpatchify (score_networks/dit.py:187-204). */
 int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out_bf16, void* stream);
 int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out, void* stream);

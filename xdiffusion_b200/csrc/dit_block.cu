@@ -61,6 +61,7 @@ struct MlpParams {
     long long ldh;
     long long* prof;            // -DXDB200_INSTRUMENT + XDB200_DIT_PROF=<device pointer>: 64 clock64() stamps per CTA
     const uint8_t *wp, *w1, *w2;   // the three weight matrices (bytes), for the L2 prefetch at kernel entry
+    const int* mod_rows;        // optional: modulation row of image i is mod_rows[i] (rows of a per-loop table) instead of i
 };
 
 // Every CTA pulls its share of a weight matrix into L2 (4 KB pieces, round-robin over the grid).  Issued before
@@ -358,7 +359,8 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         const int row = q * 32 + lane;                  // row inside this CTA's 128
         const int m0w = m0 + q * 32;
         const int gm = min(m0 + row, p.M - 1);
-        const long long mod_off = (long long)(gm / p.rows_per_mod) * p.mod_ld;
+        const int img = gm / p.rows_per_mod;
+        const long long mod_off = (long long)(p.mod_rows ? __ldg(p.mod_rows + img) : img) * p.mod_ld;
         // residual boxes of this warp (4 KB each, 1 KB aligned): two in the hidden buffers (idle until the first GELU), three
         // in the panel -- the very area this warp's LayerNorm pass fills afterwards (rows 32q.., k-blocks 3 grp..), idle between
         // the last proj MMA and that pass -- and, for the final pass (nothing else is live then), one in the weight ring
@@ -532,7 +534,8 @@ dit_mlp_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ 
         if (warp >= 2) {
             const int gm = m0 + row;
             const bool live = gm < p.M;
-            const long long mod_off = (long long)(min(gm, p.M - 1) / p.rows_per_mod) * p.mod_ld;
+            const int img = min(gm, p.M - 1) / p.rows_per_mod;
+            const long long mod_off = (long long)(p.mod_rows ? __ldg(p.mod_rows + img) : img) * p.mod_ld;
             float* hrow = p.h_out + (long long)min(gm, p.M - 1) * p.ldh + grp_id * W;
             const float* gp = p.gate2 + mod_off + grp_id * W;
             const float* bp2 = p.b2 + grp_id * W;
@@ -638,6 +641,7 @@ struct AttnFParams {
     const float* bias;          // packed like the weights: [heads][q(64) | k(64) | v(64)]
     bf16* out;
     float eps, sm_scale;
+    const int* mod_rows;        // optional indirection of the modulation rows (see MlpParams)
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -894,7 +898,7 @@ dit_attn_kernel(const __grid_constant__ CUtensorMap tmW, const AttnFParams p) {
                         cur_mod = mod_row;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            const long long off = (long long)mod_row * p.mod_ld + (i * 32 + lane) * 4;
+                            const long long off = (long long)(p.mod_rows ? __ldg(p.mod_rows + mod_row) : mod_row) * p.mod_ld + (i * 32 + lane) * 4;
                             sc[i] = __ldg(reinterpret_cast<const float4*>(p.scale + off));
                             sh[i] = __ldg(reinterpret_cast<const float4*>(p.shift + off));
                         }
@@ -1023,11 +1027,11 @@ int launch_mlp(const CUtensorMap& tO, const CUtensorMap& tWp, const CUtensorMap&
 }
 }  // namespace
 
-extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
-                                       const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
-                                       float* h_out, long long ldh, int M, int D, const float* gate1, const float* shift2,
-                                       const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
-                                       float eps, float* stats_out, int split, void* stream) {
+static int dit_proj_mlp_impl(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
+                             const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
+                             float* h_out, long long ldh, int M, int D, const float* gate1, const float* shift2,
+                             const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
+                             float eps, float* stats_out, int split, const int* g_mod_rows, void* stream) {
     XD_CHECK_ARG(O && Wp && bp && W1 && b1 && W2 && b2 && h_in && h_out && gate1 && shift2 && scale2 && gate2 && M > 0);
     XD_CHECK_ARG(D == DM && hidden % 128 == 0 && hidden >= 128 && rows_per_mod > 0);
     XD_CHECK_ARG(ldo % 8 == 0 && ldh % 4 == 0 && mod_ld % 4 == 0);
@@ -1050,7 +1054,7 @@ extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void*
 #endif
     MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
                 reinterpret_cast<float2*>(stats_out), eps, h_out, ldh, prof,
-                static_cast<const uint8_t*>(Wp), static_cast<const uint8_t*>(W1), static_cast<const uint8_t*>(W2)};
+                static_cast<const uint8_t*>(Wp), static_cast<const uint8_t*>(W1), static_cast<const uint8_t*>(W2), g_mod_rows};
     cudaStream_t st = (cudaStream_t)stream;
     int G = split;
     if (G == 0) {
@@ -1081,13 +1085,33 @@ extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void*
 }
 
 // O[m, 64h : 64h + 64] = softmax_per_image( q_h k_h^T / sqrt(64) ) v_h  with [q_h | k_h | v_h] = LNmod(h) Wqkv_h^T + b_h:
+extern "C" int xd_dit_proj_mlp_bf16_tc(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
+                                       const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
+                                       float* h_out, long long ldh, int M, int D, const float* gate1, const float* shift2,
+                                       const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
+                                       float eps, float* stats_out, int split, void* stream) {
+    return dit_proj_mlp_impl(O, ldo, Wp, bp, W1, b1, W2, b2, hidden, h_in, h_out, ldh, M, D, gate1, shift2, scale2, gate2, mod_ld,
+                             rows_per_mod, eps, stats_out, split, nullptr, stream);
+}
+// ... with the modulation rows of image i taken from row mod_rows[i] of a table (device int32 [M / rows_per_mod])
+extern "C" int xd_dit_proj_mlp_bf16_tc_rows(const void* O, long long ldo, const void* Wp, const float* bp, const void* W1,
+                                            const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
+                                            float* h_out, long long ldh, int M, int D, const float* gate1,
+                                            const float* shift2, const float* scale2, const float* gate2, long long mod_ld,
+                                            int rows_per_mod, float eps, float* stats_out, int split, const int* mod_rows,
+                                            void* stream) {
+    XD_CHECK_ARG(mod_rows != nullptr);
+    return dit_proj_mlp_impl(O, ldo, Wp, bp, W1, b1, W2, b2, hidden, h_in, h_out, ldh, M, D, gate1, shift2, scale2, gate2, mod_ld,
+                             rows_per_mod, eps, stats_out, split, mod_rows, stream);
+}
+
 // LayerNorm-modulate + QKV projection + attention of a DiT block in one kernel.  h fp32 [M, 384] (rows_per_mod = tokens per
 // image = 16), Wh bf16 [heads * 192, 384] and bias fp32 [heads * 192] packed per head as [q | k | v] (64 rows each), stats
 // (mean, rstd) per row or NULL (computed in the kernel), out bf16 [M, 384] with head h in columns [64h, 64h + 64).
-extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats, const float* shift,
-                                          const float* scale, long long mod_ld, int rows_per_mod, float eps, const void* Wh,
-                                          const float* bias, int heads, int M, int D, float sm_scale, void* out,
-                                          long long ldo, void* stream) {
+static int dit_ln_qkv_attn_impl(const float* h, long long ldh, const float* stats, const float* shift,
+                                const float* scale, long long mod_ld, int rows_per_mod, float eps, const void* Wh,
+                                const float* bias, int heads, int M, int D, float sm_scale, void* out,
+                                long long ldo, const int* g_mod_rows, void* stream) {
     XD_CHECK_ARG(h && shift && scale && Wh && bias && out && M > 0 && D == DM && heads * 64 == DM);
     XD_CHECK_ARG(rows_per_mod == 16 && M % 16 == 0);                  // one image = 16 token rows = one attention problem
     XD_CHECK_ARG(ldh % 4 == 0 && mod_ld % 4 == 0 && ldo % 8 == 0);
@@ -1115,7 +1139,7 @@ extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const f
     if (const char* e = getenv("XDB200_DIT_PROF")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
 #endif
     AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, static_cast<const uint8_t*>(Wh), prof, ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
-                  shift, scale, bias, (bf16*)out, eps, sm_scale};
+                  shift, scale, bias, (bf16*)out, eps, sm_scale, g_mod_rows};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * tiles * groups);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -1135,4 +1159,20 @@ extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const f
         return XD_ERR_CUDA;
     }
     return XD_OK;
+}
+
+extern "C" int xd_dit_ln_qkv_attn_bf16_tc(const float* h, long long ldh, const float* stats, const float* shift,
+                                          const float* scale, long long mod_ld, int rows_per_mod, float eps, const void* Wh,
+                                          const float* bias, int heads, int M, int D, float sm_scale, void* out,
+                                          long long ldo, void* stream) {
+    return dit_ln_qkv_attn_impl(h, ldh, stats, shift, scale, mod_ld, rows_per_mod, eps, Wh, bias, heads, M, D, sm_scale, out, ldo,
+                                nullptr, stream);
+}
+extern "C" int xd_dit_ln_qkv_attn_bf16_tc_rows(const float* h, long long ldh, const float* stats, const float* shift,
+                                               const float* scale, long long mod_ld, int rows_per_mod, float eps,
+                                               const void* Wh, const float* bias, int heads, int M, int D, float sm_scale,
+                                               void* out, long long ldo, const int* mod_rows, void* stream) {
+    XD_CHECK_ARG(mod_rows != nullptr);
+    return dit_ln_qkv_attn_impl(h, ldh, stats, shift, scale, mod_ld, rows_per_mod, eps, Wh, bias, heads, M, D, sm_scale, out, ldo,
+                                mod_rows, stream);
 }

@@ -74,11 +74,12 @@ __global__ void class_combine_kernel(const float* __restrict__ table, const long
 // loop evaluates the timestep MLP once for all N timesteps when it is built; the loop index lives on the device).
 __global__ void class_combine_step_kernel(const float* __restrict__ table, const long long* __restrict__ labels,
                                           const float* __restrict__ temb_table, const int* __restrict__ idx, int B, int Dm,
-                                          float* c_out, bf16* silu_out) {
+                                          float* c_out, bf16* silu_out, int* rows_out, int n_steps) {
     pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Dm) return;
     const int b = i / Dm, d = i % Dm;
+    if (rows_out && d == 0) rows_out[b] = (labels ? (int)labels[b] : 0) * n_steps + *idx;
     float v = temb_table[(long long)(*idx) * Dm + d];
     if (table) v = table[labels[b] * Dm + d] + v;
     if (c_out) c_out[i] = v;
@@ -317,10 +318,10 @@ extern "C" int xd_class_combine(const float* table, const long long* labels, con
 }
 
 extern "C" int xd_class_combine_step(const float* table, const long long* labels, const float* temb_table, const int* idx_dev,
-                                     int B, int Dm, float* c_out, void* silu_out, void* stream) {
+                                     int B, int Dm, float* c_out, void* silu_out, int* rows_out, int n_steps, void* stream) {
     XD_CHECK_ARG(temb_table && idx_dev && (c_out || silu_out) && (table == nullptr) == (labels == nullptr) && B > 0 && Dm > 0);
     xd_launch(class_combine_step_kernel, blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream, table, labels, temb_table,
-              idx_dev, B, Dm, c_out, (bf16*)silu_out);
+              idx_dev, B, Dm, c_out, (bf16*)silu_out, rows_out, n_steps);
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

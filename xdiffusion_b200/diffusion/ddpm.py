@@ -397,7 +397,7 @@ class _DeviceLoop:
         c["timestep"], c["timestep_idx"], c["num_sampling_steps"] = self.timestep[:rows], self.idx, self.N
         c["row_offset"] = self.row_offset
         if self.temb is not None:
-            c[TIMESTEP_TABLE_KEY] = (self.temb[0], self.temb[1], self.idx)
+            c[TIMESTEP_TABLE_KEY] = (self.temb[0], self.temb[1], self.idx) + tuple(self.temb[2:])
         if self.logsnr_t is not None:
             c["logsnr_t"], c["logsnr_s"] = self.logsnr_t[:rows], self.logsnr_s[:rows]
         return c

@@ -93,6 +93,7 @@ class DiTTimestepEmbedding(torch.nn.Module, Packed):
 
 
 SILU_PREFIX = "_xdb_silu_"
+ROWS_PREFIX = "_xdb_rows_"
 TIMESTEP_TABLE_KEY = "_xdb_temb_table"      # context entry set by the sampling loop: (id(projection), table [N, D], loop index)
 
 
@@ -143,10 +144,13 @@ class DiTCombineEmbeddngs(torch.nn.Module):
             t, lk = steps[0], (lookups[0] if lookups else None)
             c = torch.empty((t.rows, t.table.shape[1]), device=t.table.device, dtype=torch.float32)
             silu = torch.empty(c.shape, device=c.device, dtype=torch.bfloat16)
+            rows = torch.empty(t.rows, device=c.device, dtype=torch.int32) if lk else None
             torch.ops.xdb200.class_combine_step(lk.table if lk else None, lk.labels.contiguous() if lk else None, t.table, t.idx,
-                                                t.rows, c, silu)
+                                                t.rows, c, silu, rows)
             context[self._output_context_key] = c
             context[SILU_PREFIX + self._output_context_key] = silu          # bf16 SiLU(c): the input of the adaLN GEMMs
+            if rows is not None:                                            # row of every image in a (label, step) table
+                context[ROWS_PREFIX + self._output_context_key] = (rows, lk.table)
             return context
         dense = [v for v in vals if torch.is_tensor(v)]
         if len(dense) != 1 or len(lookups) > 1:

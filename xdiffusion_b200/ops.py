@@ -273,6 +273,47 @@ def _dit_proj_mlp(o, wp, bp, w1, b1, w2, b2, h_in, h, gate1, shift2, scale2, gat
     _count()
 
 
+@_op("dit_attn_rows(Tensor h, Tensor? stats, Tensor shift, Tensor scale, int rows_per_mod, float eps, Tensor wh, Tensor bias, "
+     "int heads, float sm_scale, Tensor mod_rows, Tensor(a!) out) -> ()")
+def _dit_attn_rows(h, stats, shift, scale, rows_per_mod, eps, wh, bias, heads, sm_scale, mod_rows, out):
+    """dit_attn with the modulation row of image i = mod_rows[i] (rows of a per-loop (label, step) table)."""
+    _cuda(h, stats, shift, scale, wh, bias, mod_rows, out)
+    M, D = h.shape
+    assert h.dtype == torch.float32 and h.stride(1) == 1 and out.dtype == torch.bfloat16 and out.shape == (M, D) and out.stride(1) == 1
+    assert wh.dtype == torch.bfloat16 and wh.is_contiguous() and wh.shape == (heads * 192, D) and bias.is_contiguous()
+    assert shift.dtype == torch.float32 and shift.stride(1) == 1 and scale.stride(1) == 1 and shift.stride(0) == scale.stride(0)
+    assert stats is None or (stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= 2 * M)
+    assert mod_rows.dtype == torch.int32 and mod_rows.is_contiguous() and mod_rows.numel() * rows_per_mod == M
+    _lib.check(_lib.lib().xd_dit_ln_qkv_attn_bf16_tc_rows(_p(h), h.stride(0), _p(stats), _p(shift), _p(scale), shift.stride(0),
+                                                          rows_per_mod, eps, _p(wh), _p(bias), heads, M, D, sm_scale, _p(out),
+                                                          out.stride(0), _p(mod_rows), _stream()),
+               "xd_dit_ln_qkv_attn_bf16_tc_rows")
+    _count()
+
+
+@_op("dit_proj_mlp_rows(Tensor o, Tensor wp, Tensor bp, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor h_in, Tensor(a!) h, "
+     "Tensor gate1, Tensor shift2, Tensor scale2, Tensor gate2, int rows_per_mod, float eps, Tensor(b!)? stats, int split, "
+     "Tensor mod_rows) -> ()")
+def _dit_proj_mlp_rows(o, wp, bp, w1, b1, w2, b2, h_in, h, gate1, shift2, scale2, gate2, rows_per_mod, eps, stats, split, mod_rows):
+    """dit_proj_mlp with the modulation row of image i = mod_rows[i]."""
+    _cuda(o, wp, bp, w1, b1, w2, b2, h_in, h, gate1, shift2, scale2, gate2, stats, mod_rows)
+    M, D = h.shape
+    assert h_in.shape == h.shape and h_in.dtype == torch.float32 and h_in.stride() == h.stride()
+    hidden = w1.shape[0]
+    assert o.dtype == torch.bfloat16 and o.shape == (M, D) and o.stride(1) == 1 and h.dtype == torch.float32 and h.stride(1) == 1
+    assert wp.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and wp.shape == (D, D)
+    assert w1.shape == (hidden, D) and w2.shape == (D, hidden) and all(w.dtype == torch.bfloat16 for w in (wp, w1, w2))
+    mods = (gate1, shift2, scale2, gate2)
+    assert all(t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) == gate1.stride(0) for t in mods)
+    assert stats is None or (stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= 2 * M)
+    assert mod_rows.dtype == torch.int32 and mod_rows.is_contiguous() and mod_rows.numel() * rows_per_mod == M
+    _lib.check(_lib.lib().xd_dit_proj_mlp_bf16_tc_rows(_p(o), o.stride(0), _p(wp), _p(bp), _p(w1), _p(b1), _p(w2), _p(b2), hidden,
+                                                       _p(h_in), _p(h), h.stride(0), M, D, _p(gate1), _p(shift2), _p(scale2),
+                                                       _p(gate2), gate1.stride(0), rows_per_mod, eps, _p(stats), split,
+                                                       _p(mod_rows), _stream()), "xd_dit_proj_mlp_bf16_tc_rows")
+    _count()
+
+
 @_op("gemm(Tensor a, Tensor? a2, Tensor w, Tensor? bias, int act, Tensor? gate, int gate_rows, "
      "Tensor? residual, Tensor(a!) out, int force_bn) -> ()")
 def _gemm(a, a2, w, bias, act, gate, gate_rows, residual, out, force_bn):
@@ -529,14 +570,16 @@ def _class_combine(table, labels, temb, c_out, silu_out):
 
 
 @_op("class_combine_step(Tensor? table, Tensor? labels, Tensor temb_table, Tensor idx, int B, Tensor(a!)? c_out, "
-     "Tensor(b!)? silu_out) -> ()")
-def _class_combine_step(table, labels, temb_table, idx, B, c_out, silu_out):
-    _cuda(table, labels, temb_table, idx, c_out, silu_out)
+     "Tensor(b!)? silu_out, Tensor(c!)? rows_out) -> ()")
+def _class_combine_step(table, labels, temb_table, idx, B, c_out, silu_out, rows_out):
+    _cuda(table, labels, temb_table, idx, c_out, silu_out, rows_out)
+    assert rows_out is None or (rows_out.dtype == torch.int32 and rows_out.is_contiguous() and rows_out.numel() == B)
     D = temb_table.shape[1]
     assert temb_table.is_contiguous() and temb_table.dtype == torch.float32 and idx.dtype == torch.int32
     assert labels is None or (labels.dtype == torch.int64 and labels.shape[0] == B)
     _lib.check(_lib.lib().xd_class_combine_step(_p(table), _p(labels), _p(temb_table), _p(idx), B, D, _p(c_out),
-                                                _p(silu_out), _stream()), "xd_class_combine_step")
+                                                _p(silu_out), _p(rows_out), temb_table.shape[0], _stream()),
+               "xd_class_combine_step")
     _count()
 
 

@@ -14,7 +14,8 @@ import torch
 
 from .. import ops
 from ..layers.attention import MultiHeadSelfAttention
-from ..layers.embedding import SILU_PREFIX, TIMESTEP_TABLE_KEY, DiTTimestepEmbedding, PatchEmbed
+from ..layers.embedding import (ROWS_PREFIX, SILU_PREFIX, TIMESTEP_TABLE_KEY, DiTLabelEmbedding, DiTTimestepEmbedding,
+                                PatchEmbed)
 from ..layers.mlp import Mlp
 from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
 from ..utils import instantiate_from_config, instantiate_partial_from_config
@@ -29,6 +30,9 @@ MLP_SPLIT = int(os.environ.get("XDB200_DIT_MLP_SPLIT", "1"))
 # Below this many token rows (768 images; e.g. the 128-image shards of a batch sharded 8 ways) one kernel per operator,
 # each spread over all SMs along N, is faster (B = 128: 0.56 vs 0.71 ms per timestep; B = 1024: 1.42 vs 1.12).
 FUSED_MIN_ROWS = int(os.environ.get("XDB200_DIT_FUSED_MIN_ROWS", "12288"))
+# Budget for the per-loop (label, timestep) modulation table of the fused path (fp32 [(classes + 1) * N, depth * 6D + 2D]:
+# 1.2 GB for 10 classes x 1000 steps); above it, or with XDB200_DIT_MOD_TABLE_MB=0, the adaLN GEMM runs every step.
+MOD_TABLE_BYTES = int(os.environ.get("XDB200_DIT_MOD_TABLE_MB", "4096")) << 20
 
 
 class DiTBlock(torch.nn.Module):
@@ -110,7 +114,25 @@ class DiT(torch.nn.Module, Packed):
         if len(mods) != 1 or timesteps.dtype not in (torch.int64, torch.float32):
             return None
         with torch.no_grad():
-            return id(mods[0]), mods[0](timesteps.contiguous()).contiguous()
+            temb = mods[0](timesteps.contiguous()).contiguous()
+            return id(mods[0]), temb, self._modulation_table(temb)
+
+    def _modulation_table(self, temb):
+        """adaLN_modulation(SiLU(t_emb[step] + y_emb[label])) of every block (+ the final layer) for every (label, step) pair:
+        fp32 [(classes + 1) * N, depth * 6D + 2D], row = label * N + step, or None (no class conditioning / over budget).
+        The values are those the per-step path computes (same kernels, same operand order), so both paths agree bit for bit."""
+        labels = [m for m in self._projections.values() if isinstance(m, DiTLabelEmbedding)]
+        if len(labels) != 1 or labels[0]._drop_prob != 0.0:
+            return None
+        emb = labels[0].embedding_table.weight.detach().float()
+        w_ada, b_ada = self._adaln()
+        N, D = temb.shape
+        if emb.shape[0] * N * w_ada.shape[0] * 4 > MOD_TABLE_BYTES or emb.device != temb.device:
+            return None
+        c_all = (emb[:, None, :] + temb[None, :, :]).reshape(-1, D).contiguous()          # table[label] + temb: the combine's order
+        silu_all = torch.empty(c_all.shape, device=c_all.device, dtype=torch.bfloat16)
+        torch.ops.xdb200.act_cast(c_all, ops.ACT_SILU, silu_all)
+        return emb, ops.linear(silu_all, w_ada, b_ada, out_dtype=torch.float32)
 
     # ------------------------------------------------------------------ kernels
     def _side_stream(self, device):
@@ -136,8 +158,15 @@ class DiT(torch.nn.Module, Packed):
         # allocated on the main stream so that the caching allocator never recycles them early.
         main = torch.cuda.current_stream(x.device)
         side = self._side_stream(x.device)
+        fused = FUSED_BLOCK and D == 384 and ops.MATMUL_BACKEND == "tc"
+        if ops.BATCH_DEPENDENT_PATHS and B * T < FUSED_MIN_ROWS:
+            fused = False                                 # (never when bit-exact batch independence is requested)
+        fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
         silu_c = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
-        mod = torch.empty((B, w_ada.shape[0]), device=x.device, dtype=torch.float32)    # [B, depth*6D + 2D]
+        base = len(self.blocks) * 6 * D
+        tab = context.get(TIMESTEP_TABLE_KEY)
+        modtab = tab[3] if tab is not None and len(tab) > 3 else None            # per-loop (label, step) modulation table
+        mod = mod_rows = None
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for ct in self._context_transformers:
@@ -148,13 +177,19 @@ class DiT(torch.nn.Module, Packed):
             else:
                 c = context["timestep_embedding"]                      # fp32 [B, D]
                 torch.ops.xdb200.act_cast(c.contiguous(), ops.ACT_SILU, silu_c)
-            ops.linear(silu_c, w_ada, b_ada, out=mod)
+            rows = context.get(ROWS_PREFIX + "timestep_embedding")
+            if (modtab is not None and rows is not None and fused_attn and rows[1].data_ptr() == modtab[0].data_ptr()
+                    and self.blocks[0].mlp.act == ops.ACT_GELU):
+                # every image reads its (label, step) row of the table: no adaLN GEMM, at most classes + 1 distinct rows
+                # per block and step (L2-resident); only the final layer's two slices are materialised per image
+                mod_rows, mod = rows[0], modtab[1]
+                fin = ops.linear(silu_c, w_ada[base:], b_ada[base:], out_dtype=torch.float32)      # [B, 2D]
+            else:
+                mod = torch.empty((B, w_ada.shape[0]), device=x.device, dtype=torch.float32)       # [B, depth*6D + 2D]
+                ops.linear(silu_c, w_ada, b_ada, out=mod)
+                fin = mod[:, base:]
         h = self.x_embedder(x, self.pos_embed[0])                      # fp32 [B*T, D]
         main.wait_stream(side)
-        fused = FUSED_BLOCK and D == 384 and ops.MATMUL_BACKEND == "tc"
-        if ops.BATCH_DEPENDENT_PATHS and B * T < FUSED_MIN_ROWS:
-            fused = False                                 # (never when bit-exact batch independence is requested)
-        fused_attn = fused and T == 16 and self.num_heads * 64 == D and self.blocks[0].attn.qkv.bias is not None
         # (mean, rstd) of every row of h: emitted by the fused MLP kernel of block n, consumed by the LayerNorm of block n + 1
         stats = torch.empty((B * T, 2), device=x.device, dtype=torch.float32) if fused else None
         # The fused MLP kernel reads h and writes h_next.  In place by default: a second 25 MB fp32 stream (batch 1024) does
@@ -168,6 +203,17 @@ class DiT(torch.nn.Module, Packed):
                 # two kernels per block (csrc/dit_block.cu): LayerNorm-modulate + qkv + attention, then proj + gated
                 # residual + LayerNorm-modulate + fc1 + GELU + fc2 + gated residual; neither the [B*T, 3D] qkv nor the
                 # [B*T, 4D] MLP activation leaves the SM
+                _, wp = blk.attn.weights()
+                w1, w2 = blk.mlp.weights()
+                if mod_rows is not None:
+                    wh, bh = blk.attn.head_packed()
+                    o = torch.empty((B * T, D), device=x.device, dtype=torch.bfloat16)
+                    torch.ops.xdb200.dit_attn_rows(h, stats if n > 0 else None, s1, sc1, T, 1e-6, wh, bh, self.num_heads,
+                                                   blk.attn.scale, mod_rows, o)
+                    torch.ops.xdb200.dit_proj_mlp_rows(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h,
+                                                       h_next, g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT, mod_rows)
+                    h, h_next = h_next, h
+                    continue
                 if fused_attn:
                     wh, bh = blk.attn.head_packed()
                     o = torch.empty((B * T, D), device=x.device, dtype=torch.bfloat16)
@@ -175,8 +221,6 @@ class DiT(torch.nn.Module, Packed):
                                               blk.attn.scale, o)
                 else:
                     o = blk.attn.attend(h, T, ln=(s1, sc1, T))
-                _, wp = blk.attn.weights()
-                w1, w2 = blk.mlp.weights()
                 torch.ops.xdb200.dit_proj_mlp(o, wp, blk.attn.proj.bias, w1, blk.mlp.fc1.bias, w2, blk.mlp.fc2.bias, h, h_next,
                                               g1, s2, sc2, g2, T, 1e-6, stats, MLP_SPLIT)
                 h, h_next = h_next, h
@@ -184,8 +228,7 @@ class DiT(torch.nn.Module, Packed):
             # ln=: LayerNorm + modulate feeding qkv / fc1 (layernorm_modulate kernel; fused into the GEMM with XDB200_LN_FUSED=1)
             blk.attn(h, T, ln=(s1, sc1, T), gate=g1, gate_rows=T, residual=h, out=h)    # h += g1 * attn(modulate(norm(h)))
             blk.mlp(h, ln=(s2, sc2, T), gate=g2, gate_rows=T, residual=h, out=h)        # h += g2 * mlp(modulate(norm(h)))
-        base = len(self.blocks) * 6 * D
-        a = ops.layernorm_modulate(h, mod[:, base:base + D], mod[:, base + D:base + 2 * D], T)
+        a = ops.layernorm_modulate(h, fin[:, :D], fin[:, D:2 * D], T)
         w_lin = self.packed("final", (self.final_layer.linear.weight,),
                             lambda: bf16_weight(self.final_layer.linear.weight))
         y = ops.linear(a, w_lin, self.final_layer.linear.bias, out_dtype=torch.float32)
