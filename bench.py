@@ -457,7 +457,12 @@ class Runner:
                 extra["weak_scaling"] = {"value": wrec["value"], "unit": wrec["unit"], "global_batch": gb * world,
                                          "per_gpu_batch": gb, "ms_per_step": wrec["ms_per_step"]}
             # the other configurations of SURVEY.md section 8: one timed loop each (device-timed, no e2e leg); a failure
-            # here must not cost the main line
+            # here must not cost the main line.  The main model's captured loop (graph pool, 1.2 GB modulation table) is
+            # released first.
+            model._loops.clear()
+            model = None
+            umodel._loops.clear()
+            torch.cuda.empty_cache()
             others = {}
             for name, wl in (("rf_c3", "rf"), ("pixart_c4", "pixart"), ("video_c5", "video"), ("edm_ddpmpp", None)):
                 try:
