@@ -227,6 +227,11 @@ int xd_class_combine(const float* table, const long long* labels, const float* t
  * labels[b] * n_steps + *idx_dev, the row of image b in a (label, step) modulation table (xd_dit_*_rows). */
 int xd_class_combine_step(const float* table, const long long* labels, const float* temb_table, const int* idx_dev, int B,
                           int D, float* c_out, void* silu_out, int* rows_out, int n_steps, void* stream);
+/* out[0 .. W) = table[*idx_dev][0 .. W) (fp32): the current timestep's row of a per-loop table.  PixArt-alpha's adaLN-single
+ * modulation `scale_shift_table[None] + t_block(t)` (score_networks/pixart.py:82-92,253-262) depends on the timestep only, so a
+ * sampling loop evaluates it once for all N timesteps; per step this copy replaces the timestep MLP, t_block and the table adds,
+ * and every image reads the same row (row stride 0 in the modulation arguments of the other entry points). */
+int xd_gather_row_f32(const float* table, long long ld, const int* idx_dev, int W, float* out, void* stream);
 /* PatchEmbed im2col (layers/embedding.py:455-457,502-504) and unpatchify (score_networks/dit.py:187-204). */
 int xd_patchify(const float* x, int B, int C, int H, int W, int p, void* out_bf16, void* stream);
 int xd_unpatchify(const float* y, long long ldy, int B, int C, int H, int W, int p, float* out, void* stream);

@@ -86,6 +86,14 @@ __global__ void class_combine_step_kernel(const float* __restrict__ table, const
     if (silu_out) silu_out[i] = __float2bfloat16_rn(silu_f(v));
 }
 
+// out[0 .. W) = table[*idx][0 .. W): the current timestep's row of a per-loop table (the loop index lives on the device)
+__global__ void gather_row_kernel(const float4* __restrict__ table, long long ld4, const int* __restrict__ idx, int W4,
+                                  float4* __restrict__ out) {
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W4) out[i] = table[(long long)(*idx) * ld4 + i];
+}
+
 // x fp32 NCHW -> bf16 [B*gh*gw, C*p*p], column order (c, py, px) = flattened Conv2d weight
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p, bf16* out) {
     pdl_prologue();
@@ -322,6 +330,15 @@ extern "C" int xd_class_combine_step(const float* table, const long long* labels
     XD_CHECK_ARG(temb_table && idx_dev && (c_out || silu_out) && (table == nullptr) == (labels == nullptr) && B > 0 && Dm > 0);
     xd_launch(class_combine_step_kernel, blocks_for((long long)B * Dm), 256, 0, (cudaStream_t)stream, table, labels, temb_table,
               idx_dev, B, Dm, c_out, (bf16*)silu_out, rows_out, n_steps);
+    XD_CHECK_LAUNCH();
+    return XD_OK;
+}
+
+extern "C" int xd_gather_row_f32(const float* table, long long ld, const int* idx_dev, int W, float* out, void* stream) {
+    XD_CHECK_ARG(table && idx_dev && out && W > 0 && W % 4 == 0 && ld % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    xd_launch(gather_row_kernel, blocks_for(W / 4), 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(table), ld / 4,
+              idx_dev, W / 4, reinterpret_cast<float4*>(out));
     XD_CHECK_LAUNCH();
     return XD_OK;
 }

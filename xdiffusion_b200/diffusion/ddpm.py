@@ -311,7 +311,8 @@ class _DeviceLoop:
         self.x = torch.empty(shape, dtype=torch.float32, device=dev)
         # timestep-only part of the conditioning, evaluated once for all N timesteps (score networks that offer it)
         net = model._score_network
-        self.temb = net.timestep_table(self.tabs["timestep"]) if TIMESTEP_TABLE and hasattr(net, "timestep_table") else None
+        self.temb = (net.timestep_table(self.tabs["timestep"], context=self.context)
+                     if TIMESTEP_TABLE and hasattr(net, "timestep_table") else None)
         self.noise = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # Philox key, read by the step kernel
         self.graph = None

@@ -583,6 +583,17 @@ def _class_combine_step(table, labels, temb_table, idx, B, c_out, silu_out, rows
     _count()
 
 
+@_op("gather_row(Tensor table, Tensor idx, Tensor(a!) out) -> ()")
+def _gather_row(table, idx, out):
+    """out fp32 [W] = table[idx[0]] (idx int32 on the device)."""
+    _cuda(table, idx, out)
+    assert table.dtype == torch.float32 and table.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    assert idx.dtype == torch.int32 and out.numel() == table.shape[1]
+    _lib.check(_lib.lib().xd_gather_row_f32(_p(table), table.stride(0), _p(idx), table.shape[1], _p(out), _stream()),
+               "xd_gather_row_f32")
+    _count()
+
+
 @_op("patchify(Tensor x, int p, Tensor(a!) out) -> ()")
 def _patchify(x, p, out):
     _cuda(x, out)

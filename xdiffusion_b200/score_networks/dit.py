@@ -105,7 +105,7 @@ class DiT(torch.nn.Module, Packed):
             torch.nn.init.constant_(lin.bias, 0)
         run_custom_initializers(self)
 
-    def timestep_table(self, timesteps):
+    def timestep_table(self, timesteps, context=None):
         """(id(projection), table): the timestep MLP for every timestep of a sampling loop, [N, D] fp32 (row = loop index).
         The loop hands it back through ``context[TIMESTEP_TABLE_KEY]`` with its device-resident loop index, and the per-step
         conditioning chain (sinusoid, two GEMMs, combine, SiLU cast: five launches) becomes one kernel in front of the

@@ -13,7 +13,7 @@ import torch
 
 from .. import ops
 from ..layers.attention import LastChannelCrossAttention, MultiHeadSelfAttention
-from ..layers.embedding import ContextProjection, PatchEmbed
+from ..layers.embedding import TIMESTEP_TABLE_KEY, ContextProjection, PatchEmbed
 from ..layers.mlp import Mlp
 from ..layers.utils import Packed, bf16_weight, get_2d_sincos_pos_embed
 from . import dit as _dit
@@ -128,6 +128,57 @@ class PixArtAlpha(torch.nn.Module, Packed):
         else:
             context[self.KV_KEY] = kvs
 
+    def _conditioning(self, context, B, device):
+        """adaLN-single rows of every block, fp32 [depth, B, 7D] (six slices + a slice of exact ones), and of the final layer,
+        fp32 [2, B, D], from the timestep embedding of the context."""
+        D, depth = self.hidden_size, len(self.blocks)
+        for ct in self._context_transformers:
+            if not isinstance(ct, ContextProjection):
+                context = ct(context=context, device=device)
+        t = context["timestep_embedding"].contiguous()                    # fp32 [B, D]
+        silu_t = torch.empty((B, D), device=device, dtype=torch.bfloat16)
+        torch.ops.xdb200.act_cast(t, ops.ACT_SILU, silu_t)
+        # adaLN-single: mod[n] = scale_shift_table[n] + t_block(t), six [B, D] slices per block.  A seventh slice of
+        # exact ones rides along (zero weight rows, bias 1, zero table entries): the gate of the ungated cross-attention
+        # residual for the fused kernel, at the same row pitch as the other slices and without a launch of its own.
+        w_t, b_t = self.packed("t_block", (self.t_block[1].weight, self.t_block[1].bias), lambda: (
+            torch.cat([bf16_weight(self.t_block[1].weight), torch.zeros((D, D), device=device, dtype=torch.bfloat16)], 0),
+            torch.cat([self.t_block[1].bias.detach().float(), torch.ones(D, device=device)], 0)))
+        t0 = ops.linear(silu_t, w_t, b_t, out_dtype=torch.float32)                        # [B, 7D]
+        tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.cat(
+            [torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float(),
+             torch.zeros((depth, D), device=device)], 1).contiguous())
+        mod = torch.empty((depth, B, 7 * D), device=device, dtype=torch.float32)
+        torch.ops.xdb200.add_table(t0, tables, mod)                   # table + t0 for all blocks
+        fmod = torch.empty((2, B, D), device=device, dtype=torch.float32)
+        torch.ops.xdb200.add_table(t, self.final_layer.scale_shift_table.detach().float().contiguous(), fmod)
+        return mod, fmod
+
+    @torch.no_grad()
+    def timestep_table(self, timesteps, context=None):
+        """(id(self), table): the adaLN-single rows of all blocks and the final layer for every timestep of a sampling loop,
+        fp32 [N, depth * 7D + 2D] (row = loop index), when the conditioning depends on the timestep only -- checked against
+        the loop's own context at one timestep; None otherwise (the rows are then computed per step)."""
+        if context is None or timesteps.dim() != 1:
+            return None
+        N, dev = timesteps.shape[0], timesteps.device
+        D, depth = self.hidden_size, len(self.blocks)
+        try:
+            probe = {k: v for k, v in context.items()}
+            B = next(v.shape[0] for v in probe.values() if torch.is_tensor(v) and v.dim() > 0)
+            probe["timestep"] = timesteps[-1:].expand(B).contiguous()
+            mod_b, fmod_b = self._conditioning(probe, B, dev)
+            generic = {"timestep": timesteps.contiguous()}
+            if "classes" in context:
+                generic["classes"] = torch.zeros(N, dtype=torch.long, device=dev)
+            mod_n, fmod_n = self._conditioning(generic, N, dev)
+        except Exception:  # noqa: BLE001  (a conditioning head that needs more than the timestep)
+            return None
+        if not (torch.equal(mod_b, mod_n[:, -1:].expand_as(mod_b)) and torch.equal(fmod_b, fmod_n[:, -1:].expand_as(fmod_b))):
+            return None
+        table = torch.cat([mod_n.permute(1, 0, 2).reshape(N, depth * 7 * D), fmod_n.permute(1, 0, 2).reshape(N, 2 * D)], 1)
+        return id(self), table.contiguous()
+
     def forward(self, x, context: Dict, **kwargs):
         context = context.copy()
         kvs = context.get(self.KV_KEY)
@@ -139,27 +190,17 @@ class PixArtAlpha(torch.nn.Module, Packed):
         # stream (a fork / join in the captured graph), (b) patch embedding on the main stream.
         main, side = torch.cuda.current_stream(x.device), _dit.DiT._side_stream(self, x.device)
         side.wait_stream(main)
+        tab = context.get(TIMESTEP_TABLE_KEY)
         with torch.cuda.stream(side):
-            for ct in self._context_transformers:
-                if not isinstance(ct, ContextProjection):
-                    context = ct(context=context, device=x.device)
-            t = context["timestep_embedding"].contiguous()                    # fp32 [B, D]
-            silu_t = torch.empty((B, D), device=x.device, dtype=torch.bfloat16)
-            torch.ops.xdb200.act_cast(t, ops.ACT_SILU, silu_t)
-            # adaLN-single: mod[n] = scale_shift_table[n] + t_block(t), six [B, D] slices per block.  A seventh slice of
-            # exact ones rides along (zero weight rows, bias 1, zero table entries): the gate of the ungated cross-attention
-            # residual for the fused kernel, at the same row pitch as the other slices and without a launch of its own.
-            w_t, b_t = self.packed("t_block", (self.t_block[1].weight, self.t_block[1].bias), lambda: (
-                torch.cat([bf16_weight(self.t_block[1].weight), torch.zeros((D, D), device=x.device, dtype=torch.bfloat16)], 0),
-                torch.cat([self.t_block[1].bias.detach().float(), torch.ones(D, device=x.device)], 0)))
-            t0 = ops.linear(silu_t, w_t, b_t, out_dtype=torch.float32)                        # [B, 7D]
-            tables = self.packed("tables", tuple(b.scale_shift_table for b in self.blocks), lambda: torch.cat(
-                [torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks]).float(),
-                 torch.zeros((depth, D), device=x.device)], 1).contiguous())
-            mod = torch.empty((depth, B, 7 * D), device=x.device, dtype=torch.float32)
-            torch.ops.xdb200.add_table(t0, tables, mod)                   # table + t0 for all blocks
-            fmod = torch.empty((2, B, D), device=x.device, dtype=torch.float32)
-            torch.ops.xdb200.add_table(t, self.final_layer.scale_shift_table.detach().float().contiguous(), fmod)
+            if tab is not None and tab[0] == id(self):
+                # the loop evaluated the whole timestep-only conditioning for all of its timesteps (timestep_table): this
+                # step's row is copied out and every image reads it (row stride 0)
+                row = torch.empty(tab[1].shape[1], device=x.device, dtype=torch.float32)
+                torch.ops.xdb200.gather_row(tab[1], tab[2], row)
+                mod = row[:depth * 7 * D].view(depth, 1, 7 * D).expand(depth, B, 7 * D)
+                fmod = row[depth * 7 * D:].view(2, 1, D).expand(2, B, D)
+            else:
+                mod, fmod = self._conditioning(context, B, x.device)
         h = self.x_embedder(x, self.pos_embed[0])                         # fp32 [B*T, D]
         main.wait_stream(side)
         fused = (_dit.FUSED_BLOCK and kvs is not None and D == 384 and T == 16 and self.num_heads * 64 == D
