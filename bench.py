@@ -469,7 +469,7 @@ class Runner:
                     if wl is None:
                         others[name] = self.run_edm()
                     else:
-                        others[name] = self.run_workload(wl, GLOBAL_BATCH[wl], with_e2e=False, steps=1, warmup=1)[0]
+                        others[name] = self.run_workload(wl, GLOBAL_BATCH[wl], with_e2e=False, steps=1, warmup=2)[0]
                 except Exception as exc:  # noqa: BLE001
                     others[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
                 torch.cuda.empty_cache()
