@@ -83,3 +83,23 @@ def test_cpu_model_refuses_to_sample(golden):
     m = _build(golden("c2"))
     with pytest.raises(RuntimeError):
         m.sample(context={"classes": torch.tensor([1, 2])}, num_samples=2, num_sampling_steps=2)
+
+
+def test_cfg_merge_lines_up_conditional_and_unconditional_rows():
+    """Host logic of the one-forward classifier-free guidance (diffusion/ddpm.py: _DeviceLoop._merge): per-sample tensors are
+    stacked [conditional | unconditional], equal scalars pass through, anything that does not line up row for row disables the
+    merge (the loop then runs two forwards)."""
+    import types
+    import numpy as np
+    from xdiffusion_b200.diffusion.ddpm import _DeviceLoop
+    B = 3
+    cond = {"text_embeddings": torch.randn(B, 5, 8), "classes": torch.arange(B), "flag": 7}
+    unc = {"text_embeddings": torch.zeros(B, 5, 8), "classes": torch.full((B,), 10), "flag": 7}
+    both = _DeviceLoop._merge(types.SimpleNamespace(context=cond, uncond=unc), B)
+    assert both["flag"] == 7 and both["classes"].tolist() == [0, 1, 2, 10, 10, 10]
+    assert torch.equal(both["text_embeddings"][:B], cond["text_embeddings"]) and float(both["text_embeddings"][B:].abs().max()) == 0
+    assert _DeviceLoop._merge(types.SimpleNamespace(context=cond, uncond={**unc, "flag": 8}), B) is None
+    assert _DeviceLoop._merge(types.SimpleNamespace(context=cond, uncond={k: v for k, v in unc.items() if k != "flag"}), B) is None
+    assert _DeviceLoop._merge(types.SimpleNamespace(context=cond, uncond={**unc, "classes": torch.zeros(B + 1)}), B) is None
+    arr = {"a": np.zeros(2)}
+    assert _DeviceLoop._merge(types.SimpleNamespace(context={**cond, **arr}, uncond={**unc, **arr}), B) is None
