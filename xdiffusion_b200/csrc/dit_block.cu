@@ -1031,7 +1031,7 @@ static int dit_proj_mlp_impl(const void* O, long long ldo, const void* Wp, const
                              const float* b1, const void* W2, const float* b2, int hidden, const float* h_in,
                              float* h_out, long long ldh, int M, int D, const float* gate1, const float* shift2,
                              const float* scale2, const float* gate2, long long mod_ld, int rows_per_mod,
-                             float eps, float* stats_out, int split, const int* g_mod_rows, void* stream) {
+                             float eps, float* stats_out, int split, const int* mod_rows, void* stream) {
     XD_CHECK_ARG(O && Wp && bp && W1 && b1 && W2 && b2 && h_in && h_out && gate1 && shift2 && scale2 && gate2 && M > 0);
     XD_CHECK_ARG(D == DM && hidden % 128 == 0 && hidden >= 128 && rows_per_mod > 0);
     XD_CHECK_ARG(ldo % 8 == 0 && ldh % 4 == 0 && mod_ld % 4 == 0);
@@ -1054,7 +1054,7 @@ static int dit_proj_mlp_impl(const void* O, long long ldo, const void* Wp, const
 #endif
     MlpParams p{M, hidden, rows_per_mod, mod_ld, bp, b1, b2, gate1, shift2, scale2, gate2,
                 reinterpret_cast<float2*>(stats_out), eps, h_out, ldh, prof,
-                static_cast<const uint8_t*>(Wp), static_cast<const uint8_t*>(W1), static_cast<const uint8_t*>(W2), g_mod_rows};
+                static_cast<const uint8_t*>(Wp), static_cast<const uint8_t*>(W1), static_cast<const uint8_t*>(W2), mod_rows};
     cudaStream_t st = (cudaStream_t)stream;
     int G = split;
     if (G == 0) {
@@ -1111,7 +1111,7 @@ extern "C" int xd_dit_proj_mlp_bf16_tc_rows(const void* O, long long ldo, const 
 static int dit_ln_qkv_attn_impl(const float* h, long long ldh, const float* stats, const float* shift,
                                 const float* scale, long long mod_ld, int rows_per_mod, float eps, const void* Wh,
                                 const float* bias, int heads, int M, int D, float sm_scale, void* out,
-                                long long ldo, const int* g_mod_rows, void* stream) {
+                                long long ldo, const int* mod_rows, void* stream) {
     XD_CHECK_ARG(h && shift && scale && Wh && bias && out && M > 0 && D == DM && heads * 64 == DM);
     XD_CHECK_ARG(rows_per_mod == 16 && M % 16 == 0);                  // one image = 16 token rows = one attention problem
     XD_CHECK_ARG(ldh % 4 == 0 && mod_ld % 4 == 0 && ldo % 8 == 0);
@@ -1139,7 +1139,7 @@ static int dit_ln_qkv_attn_impl(const float* h, long long ldh, const float* stat
     if (const char* e = getenv("XDB200_DIT_PROF")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
 #endif
     AttnFParams p{M, rows_per_mod, heads, heads / groups, groups, static_cast<const uint8_t*>(Wh), prof, ldh, mod_ld, ldo, h, reinterpret_cast<const float2*>(stats),
-                  shift, scale, bias, (bf16*)out, eps, sm_scale, g_mod_rows};
+                  shift, scale, bias, (bf16*)out, eps, sm_scale, mod_rows};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * tiles * groups);
     cfg.blockDim = dim3(NUM_THREADS);
