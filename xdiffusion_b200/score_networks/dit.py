@@ -4,8 +4,12 @@ Drop-in for ``xdiffusion.score_networks.dit.DiT`` (reference: score_networks/dit
 constructor (a DotConfig), same ``forward(x, context) -> Tensor`` and identical ``state_dict`` keys.
 Per forward: patchify+GEMM, ONE batched adaLN GEMM for all blocks (the conditioning vector is
 block-independent), then per block LayerNorm+modulate -> QKV GEMM -> fused attention -> proj GEMM
-with gate*+residual epilogue -> LayerNorm+modulate -> fc1 GEMM (+GELU) -> fc2 GEMM (gate*+residual).
+with gate*+residual epilogue -> LayerNorm+modulate -> fc1 GEMM (+GELU) -> fc2 GEMM (gate*+residual);
+from 768 images per GPU two fused tcgen05 kernels per block instead (csrc/dit_block.cu).
 The token residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation in TMEM.
+Inside a sampling loop the conditioning does not run per step at all: ``timestep_table`` evaluates the
+timestep MLP for all N timesteps and the adaLN modulation for every (label, timestep) pair once, and
+the fused kernels read each image's row of that table through an index.
 """
 import os
 from typing import Dict
